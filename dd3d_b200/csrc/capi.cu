@@ -1,0 +1,334 @@
+// extern "C" boundary of libdd3d_b200.so (declared in include/dd3d_b200.h).  Plain pointers and sizes only.
+#include <string.h>
+
+#include <string>
+
+#include "engine.cuh"
+
+using namespace dd3d;
+
+struct dd3d_engine {
+    Engine* eng = nullptr;
+    std::string err;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename F>
+int guarded(dd3d_handle h, F&& f) {
+    try {
+        if (h == nullptr || h->eng == nullptr) return DD3D_ERR_INVALID;
+        cudaSetDevice(h->eng->device);
+        f(*h->eng);
+        return DD3D_OK;
+    } catch (const EngineError& e) {
+        h->err = e.msg;
+        return e.status;
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return DD3D_ERR_INVALID;
+    }
+}
+
+int cuda_status(cudaError_t e, std::string* err) {
+    if (e == cudaSuccess) return DD3D_OK;
+    if (err) *err = cudaGetErrorString(e);
+    return DD3D_ERR_CUDA;
+}
+
+int device_sms() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dd3d_create(const dd3d_model_desc* h_desc, dd3d_handle* out) {
+    if (h_desc == nullptr || out == nullptr) return DD3D_ERR_INVALID;
+    *out = nullptr;
+    try {
+        dd3d_engine* h = new dd3d_engine();
+        h->eng = new Engine(*h_desc);
+        *out = h;
+        return DD3D_OK;
+    } catch (const EngineError& e) {
+        g_create_error = e.msg;
+        return e.status;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return DD3D_ERR_INVALID;
+    }
+}
+
+void dd3d_destroy(dd3d_handle h) {
+    if (h == nullptr) return;
+    delete h->eng;
+    delete h;
+}
+
+const char* dd3d_last_error(dd3d_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dd3d_size_divisibility(dd3d_handle h) { return (h && h->eng) ? h->eng->size_divisibility() : DD3D_ERR_INVALID; }
+
+int dd3d_load_weight(dd3d_handle h, const char* name, const float* data, const int64_t* shape, int ndim) {
+    if (name == nullptr || data == nullptr || (ndim > 0 && shape == nullptr) || ndim < 0 || ndim > 8)
+        return DD3D_ERR_INVALID;
+    return guarded(h, [&](Engine& e) { e.load_weight(name, data, shape, ndim); });
+}
+
+int dd3d_finalize(dd3d_handle h) {
+    return guarded(h, [&](Engine& e) { e.finalize(); });
+}
+
+int64_t dd3d_workspace_bytes(dd3d_handle h, int B, int Hs, int Ws) {
+    int64_t bytes = 0;
+    int st = guarded(h, [&](Engine& e) { bytes = static_cast<int64_t>(e.workspace_bytes(B, Hs, Ws)); });
+    return st == DD3D_OK ? bytes : st;
+}
+
+int dd3d_plan(dd3d_handle h, int B, int Hs, int Ws, void* d_workspace, int64_t workspace_bytes) {
+    return guarded(h, [&](Engine& e) { e.make_plan(B, Hs, Ws, d_workspace, static_cast<size_t>(workspace_bytes)); });
+}
+
+int dd3d_forward(dd3d_handle h, const void* d_images, int img_dtype, const float* d_intrinsics, const int32_t* d_sizes,
+                 dd3d_det* d_out, int32_t* d_counts, dd3d_stream stream) {
+    if (!d_images || !d_intrinsics || !d_sizes || !d_out || !d_counts) return DD3D_ERR_INVALID;
+    return guarded(h, [&](Engine& e) {
+        e.forward(d_images, img_dtype, d_intrinsics, d_sizes, reinterpret_cast<Det*>(d_out), d_counts,
+                  static_cast<cudaStream_t>(stream));
+    });
+}
+
+int dd3d_forward_host(dd3d_handle h, const void* h_images, int img_dtype, const float* h_intrinsics,
+                      const int32_t* h_sizes, dd3d_det* h_out, int32_t* h_counts, dd3d_stream stream) {
+    if (!h_images || !h_intrinsics || !h_sizes || !h_out || !h_counts) return DD3D_ERR_INVALID;
+    return guarded(h, [&](Engine& e) {
+        e.forward_host(h_images, img_dtype, h_intrinsics, h_sizes, reinterpret_cast<Det*>(h_out), h_counts,
+                       static_cast<cudaStream_t>(stream));
+    });
+}
+
+int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags) {
+    return guarded(h, [&](Engine& e) {
+        if (!e.plan.valid) throw EngineError(DD3D_ERR_STATE, "no plan");
+        cudaError_t c = cudaMemcpyAsync(h_flags, e.plan.decode.flags, 4, cudaMemcpyDeviceToHost,
+                                        static_cast<cudaStream_t>(stream));
+        if (c == cudaSuccess) c = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+        if (c != cudaSuccess) throw EngineError(DD3D_ERR_CUDA, cudaGetErrorString(c));
+    });
+}
+
+int dd3d_set_option(dd3d_handle h, const char* name, int value) {
+    return guarded(h, [&](Engine& e) {
+        const std::string n(name ? name : "");
+        if (n == "do_postprocess") {
+            e.opt_do_postprocess = value ? 1 : 0;
+        } else if (n == "do_nms") {
+            e.desc.do_nms = value ? 1 : 0;
+        } else {
+            throw EngineError(DD3D_ERR_INVALID, "unknown option: " + n);
+        }
+    });
+}
+
+int dd3d_launches_per_forward(dd3d_handle h) {
+    int n = 0;
+    int st = guarded(h, [&](Engine& e) { n = e.launches_per_forward(); });
+    return st == DD3D_OK ? n : st;
+}
+
+int dd3d_get_tensor(dd3d_handle h, const char* name, void** d_ptr, int32_t dims[6]) {
+    return guarded(h, [&](Engine& e) {
+        if (!e.plan.valid) throw EngineError(DD3D_ERR_STATE, "no plan");
+        const Plan& P = e.plan;
+        const std::string n(name ? name : "");
+        auto level = [&](size_t prefix_len) {
+            const int l = n.size() == prefix_len + 1 ? n[prefix_len] - '0' : -1;
+            if (l < 0 || l >= kLevels) throw EngineError(DD3D_ERR_INVALID, "unknown tensor: " + n);
+            return l;
+        };
+        if (n == "input") {
+            *d_ptr = P.input.ptr;
+            const int32_t d[6] = {P.B, P.Hp, P.Wp, 4, 4, 2};
+            memcpy(dims, d, sizeof(d));
+        } else if (n[0] == 'p') {
+            const View& v = P.fpn[level(1)];
+            *d_ptr = v.ptr;
+            const int32_t d[6] = {v.B, v.H, v.W, v.C, v.pitch, 2};
+            memcpy(dims, d, sizeof(d));
+        } else if (n.rfind("cls", 0) == 0) {
+            const int l = level(3);
+            *d_ptr = P.cls_map[l];
+            const int32_t d[6] = {P.B, P.lvl_h[l], P.lvl_w[l], e.desc.num_classes, P.cls_pitch, 4};
+            memcpy(dims, d, sizeof(d));
+        } else if (n.rfind("box", 0) == 0) {
+            const int l = level(3);
+            *d_ptr = P.box_map[l];
+            const int32_t d[6] = {P.B, P.lvl_h[l], P.lvl_w[l], 5, 16, 4};
+            memcpy(dims, d, sizeof(d));
+        } else if (n.rfind("b3d", 0) == 0) {
+            const int l = level(3);
+            *d_ptr = P.b3d_map[l];
+            const int32_t d[6] = {P.B, P.lvl_h[l], P.lvl_w[l], 11 * e.desc.num_classes, P.b3d_pitch, 4};
+            memcpy(dims, d, sizeof(d));
+        } else {
+            throw EngineError(DD3D_ERR_INVALID, "unknown tensor: " + n);
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ operators
+
+int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch, const void* d_w, int cout, int ksize,
+                   int stride, const float* d_scale, const float* d_bias, int relu, const void* d_residual,
+                   int res_pitch, int res_up2, void* d_out, int out_pitch, int out_f32, dd3d_stream stream) {
+    if (!d_in || !d_w || !d_scale || !d_bias || !d_out) return DD3D_ERR_INVALID;
+    if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2) || (stride == 2 && ksize != 3)) return DD3D_ERR_INVALID;
+    if (stride == 2 && ((H | W) & 1)) return DD3D_ERR_INVALID;
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    const int kchunks = (cin + kBlockK - 1) / kBlockK;
+    const int taps = ksize * ksize;
+    const int cout_pad = (cout + 15) / 16 * 16;
+    const int block_n = cout_pad > 256 ? 256 : cout_pad;
+    if (cout_pad % block_n) return DD3D_ERR_INVALID;
+    if (!out_f32 && cout % 16) return DD3D_ERR_INVALID;
+    p.nseg = 1;
+    p.B = B;
+    p.taps = taps;
+    p.stride = stride;
+    p.kchunks = kchunks;
+    p.n_blocks = cout_pad / block_n;
+    p.block_n = block_n;
+    p.relu = relu;
+    p.out_mode = out_f32 ? 1 : 0;
+    ConvSeg& g = p.seg[0];
+    const int Ho = H / stride, Wo = W / stride;
+    g.H = Ho;
+    g.W = Wo;
+    choose_tile(Ho, Wo, &g.th, &g.tw);
+    bool ok = make_weight_map(&p.w_map, d_w, taps * kchunks * kBlockK, cout_pad, block_n);
+    if (stride == 1) {
+        ok = ok && make_act_map(&g.in_map[0], d_in, B, H, W, cin, in_pitch, g.th, g.tw);
+    } else {
+        ok = ok && make_act_map_s2(&g.in_map[0], d_in, 0, B, H, W, cin, in_pitch, g.th, g.tw) &&
+             make_act_map_s2(&g.in_map[1], d_in, 1, B, H, W, cin, in_pitch, g.th, g.tw);
+    }
+    if (!out_f32) ok = ok && make_act_map(&g.out_map, d_out, B, Ho, Wo, cout, out_pitch, g.th, g.tw);
+    if (!ok) {
+        fprintf(stderr, "dd3d_op_conv2d: %s\n", conv_last_error());
+        return DD3D_ERR_CUDA;
+    }
+    g.scale = d_scale;
+    g.bias = d_bias;
+    g.lo = nullptr;
+    g.out_f32 = static_cast<float*>(out_f32 ? d_out : nullptr);
+    g.out_pitch = out_pitch;
+    if (d_residual) {
+        g.residual = static_cast<const __nv_bfloat16*>(d_residual);
+        g.res_pitch = res_pitch;
+        g.res_up2 = res_up2;
+        g.res_H = res_up2 ? Ho / 2 : Ho;
+        g.res_W = res_up2 ? Wo / 2 : Wo;
+    }
+    conv_finalize_params(&p);
+    return cuda_status(launch_conv(p, device_sms(), static_cast<cudaStream_t>(stream)), nullptr);
+}
+
+int dd3d_op_stem_conv(const void* d_in4, const float* d_w, const float* d_scale, const float* d_bias, void* d_out, int B,
+                      int H, int W, int ksize, int stride, int cout, int out_pitch, dd3d_stream stream) {
+    if (cout % 16) return DD3D_ERR_INVALID;
+    return cuda_status(launch_stem_conv(static_cast<const __nv_bfloat16*>(d_in4), d_w, d_scale, d_bias,
+                                        static_cast<__nv_bfloat16*>(d_out), B, H, W, ksize, stride, cout, out_pitch,
+                                        static_cast<cudaStream_t>(stream)),
+                       nullptr);
+}
+
+int dd3d_op_preprocess(const void* d_images, int img_dtype, const int32_t* d_sizes2, void* d_out4, int B, int Hs, int Ws,
+                       int Hp, int Wp, const float* h_mean, const float* h_std, dd3d_stream stream) {
+    return cuda_status(launch_preprocess(d_images, img_dtype == DD3D_IMG_U8, d_sizes2, 2, static_cast<__nv_bfloat16*>(d_out4),
+                                         B, Hs, Ws, Hp, Wp, h_mean, h_std, static_cast<cudaStream_t>(stream)),
+                       nullptr);
+}
+
+int dd3d_op_maxpool(const void* d_in, void* d_out, int B, int H, int W, int C, int in_pitch, int out_pitch, int ksize,
+                    dd3d_stream stream) {
+    if (C % 8 || (ksize != 2 && ksize != 3)) return DD3D_ERR_INVALID;
+    const int Ho = ksize == 2 ? H / 2 : (H - 3 + 1) / 2 + 1;
+    const int Wo = ksize == 2 ? W / 2 : (W - 3 + 1) / 2 + 1;
+    return cuda_status(launch_maxpool(static_cast<const __nv_bfloat16*>(d_in), static_cast<__nv_bfloat16*>(d_out), B, H,
+                                      W, C, in_pitch, Ho, Wo, out_pitch, ksize, device_sms(),
+                                      static_cast<cudaStream_t>(stream)),
+                       nullptr);
+}
+
+int64_t dd3d_op_ese_scratch_bytes(int B, int HW, int C) {
+    return static_cast<int64_t>(B) * (ese_nsplit(HW) + 1) * C * 4;
+}
+
+int dd3d_op_ese(const void* d_x, int x_pitch, const float* d_fc_w, const float* d_fc_b, const void* d_identity,
+                int id_pitch, void* d_out, int out_pitch, float* d_scratch, int B, int HW, int C, dd3d_stream stream) {
+    if (C % 8) return DD3D_ERR_INVALID;
+    float* partial = d_scratch;
+    float* gate = d_scratch + static_cast<size_t>(B) * ese_nsplit(HW) * C;
+    return cuda_status(launch_ese(static_cast<const __nv_bfloat16*>(d_x), x_pitch, d_fc_w, d_fc_b,
+                                  static_cast<const __nv_bfloat16*>(d_identity), id_pitch,
+                                  static_cast<__nv_bfloat16*>(d_out), out_pitch, partial, gate, B, HW, C, device_sms(),
+                                  static_cast<cudaStream_t>(stream)),
+                       nullptr);
+}
+
+int64_t dd3d_op_detect_scratch_bytes(int B, int pre_nms_topk) {
+    return static_cast<int64_t>(decode_scratch_bytes(B, pre_nms_topk)) + DD3D_MAX_CLASSES * 3 * 4 + 256;
+}
+
+int dd3d_op_detect(const dd3d_model_desc* desc, int B, const int32_t* h_level_hw, const int32_t* h_strides,
+                   const float* const* d_cls, const float* const* d_box, const float* const* d_b3d, int cls_pitch,
+                   int b3d_pitch, const float* d_intrinsics, const int32_t* d_sizes, void* d_scratch, dd3d_det* d_pre_nms,
+                   int32_t* d_pre_counts, dd3d_det* d_out, int32_t* d_counts, dd3d_stream stream_) {
+    if (!desc || !h_level_hw || !h_strides || !d_cls || !d_box || !d_b3d || !d_scratch || !d_out || !d_counts)
+        return DD3D_ERR_INVALID;
+    if (desc->pre_nms_topk < 1 || desc->pre_nms_topk * kLevels > 8192) return DD3D_ERR_INVALID;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DecodeParams dp;
+    memset(&dp, 0, sizeof(dp));
+    for (int l = 0; l < kLevels; ++l) {
+        dp.lvl[l].cls = d_cls[l];
+        dp.lvl[l].box = d_box[l];
+        dp.lvl[l].b3d = d_b3d[l];
+        dp.lvl[l].H = h_level_hw[2 * l];
+        dp.lvl[l].W = h_level_hw[2 * l + 1];
+        dp.lvl[l].stride = h_strides[l];
+    }
+    // canonical sizes live at the tail of the caller's scratch
+    const size_t dec_bytes = decode_scratch_bytes(B, desc->pre_nms_topk);
+    float* d_canon = reinterpret_cast<float*>(static_cast<uint8_t*>(d_scratch) + (dec_bytes + 255) / 256 * 256);
+    cudaError_t c = cudaMemcpyAsync(d_canon, desc->canonical_box3d_sizes, DD3D_MAX_CLASSES * 3 * 4,
+                                    cudaMemcpyHostToDevice, stream);
+    if (c != cudaSuccess) return DD3D_ERR_CUDA;
+    fill_decode_params(&dp, *desc, B, cls_pitch, b3d_pitch, d_canon);
+    decode_bind_scratch(&dp, d_scratch);
+    decode_finalize_params(&dp);
+    dp.K = d_intrinsics;
+    c = launch_decode(dp, stream);
+    if (c != cudaSuccess) return cuda_status(c, nullptr);
+    if (d_pre_nms && d_pre_counts) {
+        cudaMemcpyAsync(d_pre_nms, dp.cand, static_cast<size_t>(B) * kLevels * desc->pre_nms_topk * sizeof(Det),
+                        cudaMemcpyDeviceToDevice, stream);
+        cudaMemcpyAsync(d_pre_counts, dp.cand_count, static_cast<size_t>(B) * kLevels * 4, cudaMemcpyDeviceToDevice,
+                        stream);
+    }
+    NmsParams np;
+    fill_nms_params(&np, *desc, dp, B);
+    np.sizes = d_sizes;
+    np.out = reinterpret_cast<Det*>(d_out);
+    np.out_count = d_counts;
+    return cuda_status(launch_nms(np, stream), nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,451 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// Replaces every cuDNN conv + FrozenBN/BN + ReLU (+residual, +FPN upsample-add) launch of the reference's
+// DD3D.forward (reference call sites dla.py:27-46,149-157,229-231, vovnet.py:129-157,
+// detectron2 FPN, fcos2d.py:81-98, fcos3d.py:90-126).
+//
+// GEMM view:  D[m][n] = sum_k A[m][k] * W[n][k]
+//   m : 128 output pixels of one th x tw patch of one image          (UMMA M = 128, one TMEM lane per pixel)
+//   n : output channels, block_n <= 256 per tile                       (UMMA N)
+//   k : taps x input channels, 64 channels (128 B) per k-block         (UMMA K = 16, 4 MMAs per k-block)
+// A is never materialised: for tap (r,s) the k-block is ONE tiled TMA box [1][th][tw][64ch] of the NHWC bf16
+// input at spatial offset (r-1, s-1); TMA zero-fills out-of-image pixels (= conv zero padding) and channels
+// beyond C (ragged C such as 160/224).  Stride-2 convs read a parity-split 5-D view of the same tensor.
+// Concats are free: producers TMA-store into channel slices of one wide NHWC buffer, the 1x1 reads it whole.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer      (full/empty mbarrier ring, num_stages deep)
+//   warp 1 lane 0 : tcgen05.mma issuer (accumulators double-buffered in TMEM: 2 x block_n columns)
+//   warps 2..5    : epilogue           (tcgen05.ld -> scale/bias/residual/ReLU -> bf16 -> swizzled smem -> TMA store,
+//                                       or fp32 direct stores for the predictor heads)
+#include "conv_igemm.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "ptx.cuh"
+
+namespace dd3d {
+
+namespace {
+
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kStagingBytes = kBlockM * 128;    // one 64-channel bf16 output chunk
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 227 * 1024;
+
+struct TileCoord {
+    int seg, img, y0, x0, n_blk;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work) {
+    TileCoord t;
+    t.n_blk = work % p.n_blocks;
+    int mt = work / p.n_blocks;
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxSeg; ++i) {
+        if (i < p.nseg && mt >= p.seg[i].tile_begin) s = i;
+    }
+    t.seg = s;
+    const ConvSeg& g = p.seg[s];
+    int local = mt - g.tile_begin;
+    int per_img = g.tiles_x * g.tiles_y;
+    t.img = local / per_img;
+    int r = local - t.img * per_img;
+    int ty = r / g.tiles_x;
+    int tx = r - ty * g.tiles_x;
+    t.y0 = ty * g.th;
+    t.x0 = tx * g.tw;
+    return t;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = kABytes + p.block_n * 128;
+    uint8_t* staging = smem + p.num_stages * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+    uint64_t* full_bar = bars;                     // [kMaxStages]
+    uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
+    uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&p.w_map);
+        for (int s = 0; s < p.nseg; ++s) {
+            ptx::prefetch_tensormap(&p.seg[s].in_map[0]);
+            if (p.out_mode == 0) ptx::prefetch_tensormap(&p.seg[s].out_map);
+        }
+        for (int i = 0; i < p.num_stages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int kblocks = p.taps * p.kchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ TMA producer
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = kABytes + p.block_n * 128;
+            for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+                const TileCoord t = decode_tile(p, work);
+                const ConvSeg& g = p.seg[t.seg];
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int r = (p.taps == 9) ? tap / 3 : 1;
+                    const int s = (p.taps == 9) ? tap - 3 * (tap / 3) : 1;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                        uint8_t* a_dst = smem + stage * stage_bytes;
+                        uint8_t* b_dst = a_dst + kABytes;
+                        ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        if (p.stride == 1) {
+                            ptx::tma_load_4d(a_dst, &g.in_map[0], &full_bar[stage], kc * kBlockK, t.x0 + s - 1,
+                                             t.y0 + r - 1, t.img);
+                        } else {
+                            // input (2*oy + r - 1, 2*ox + s - 1) in the parity-split view [B][H/2][2][W/2][wp*C..]
+                            const int wp = (s == 1) ? 0 : 1;
+                            const int dw = (s == 0) ? -1 : 0;
+                            const int hp = (r == 1) ? 0 : 1;
+                            const int dh = (r == 0) ? -1 : 0;
+                            ptx::tma_load_5d(a_dst, &g.in_map[wp], &full_bar[stage], kc * kBlockK, t.x0 + dw, hp,
+                                             t.y0 + dh, t.img);
+                        }
+                        ptx::tma_load_2d(b_dst, &p.w_map, &full_bar[stage], (tap * p.kchunks + kc) * kBlockK,
+                                         t.n_blk * p.block_n);
+                        if (++stage == p.num_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ MMA issuer
+            const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, p.block_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+                ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * p.block_n;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase, 3);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem + stage * stage_bytes);
+                    const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t adesc = ptx::make_sw128_desc(a_addr + k * 32);
+                        const uint64_t bdesc = ptx::make_sw128_desc(b_addr + k * 32);
+                        ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == p.num_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (warps 2..5)
+        const int q = warp & 3;  // TMEM lane quarter accessible to this warp
+        const int row = q * 32 + lane;
+        const bool store_leader = (threadIdx.x == 64);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int sbuf = 0;
+        for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+            const TileCoord t = decode_tile(p, work);
+            const ConvSeg& g = p.seg[t.seg];
+            const int ly = row / g.tw;
+            const int lx = row - ly * g.tw;
+            const int oy = t.y0 + ly, ox = t.x0 + lx;
+            const bool in_img = (oy < g.H) && (ox < g.W);
+            const int n_base = t.n_blk * p.block_n;
+
+            const __nv_bfloat16* res_ptr = nullptr;
+            if (g.residual != nullptr && in_img) {
+                const int ry = g.res_up2 ? (oy >> 1) : oy;
+                const int rx = g.res_up2 ? (ox >> 1) : ox;
+                res_ptr = g.residual + (static_cast<size_t>(t.img * g.res_H + ry) * g.res_W + rx) * g.res_pitch + n_base;
+            }
+            float* f32_ptr = nullptr;
+            if (p.out_mode == 1 && in_img) {
+                f32_ptr = g.out_f32 + (static_cast<size_t>(t.img * g.H + oy) * g.W + ox) * g.out_pitch + n_base;
+            }
+
+            ptx::mbar_wait(&tfull_bar[acc], acc_phase, 4);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
+
+            for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+                const int chunk_cols = min(64, p.block_n - c0);
+                uint8_t* stag = staging + sbuf * kStagingBytes;
+                if (p.out_mode == 0) {
+                    // the TMA store that last read this staging buffer must have drained
+                    if (store_leader) ptx::tma_store_wait_read<1>();
+                    ptx::named_bar_sync(1, 128);
+                }
+                for (int h = 0; h < chunk_cols; h += 32) {
+                    const int cols = min(32, chunk_cols - h);
+                    uint32_t v[32];
+                    if (cols == 32) {
+                        ptx::tmem_ld32(t_addr + c0 + h, v);
+                    } else {
+                        ptx::tmem_ld16(t_addr + c0 + h, v);
+                    }
+                    ptx::tmem_ld_wait();
+                    const int n0 = n_base + c0 + h;  // absolute output channel of v[0]
+                    float y[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (i < cols) {
+                            const float4 sc = __ldg(reinterpret_cast<const float4*>(g.scale + n0 + i));
+                            const float4 bi = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+                            y[i + 0] = fmaf(__uint_as_float(v[i + 0]), sc.x, bi.x);
+                            y[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc.y, bi.y);
+                            y[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc.z, bi.z);
+                            y[i + 3] = fmaf(__uint_as_float(v[i + 3]), sc.w, bi.w);
+                        }
+                    }
+                    if (res_ptr != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            if (i < cols) {
+                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_ptr + c0 + h + i));
+                                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 f = __bfloat1622float2(rb[j]);
+                                    y[i + 2 * j] += f.x;
+                                    y[i + 2 * j + 1] += f.y;
+                                }
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.0f);
+                    }
+                    if (p.out_mode == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            if (i < cols) {
+                                uint4 o;
+                                o.x = pack_bf16(y[i + 0], y[i + 1]);
+                                o.y = pack_bf16(y[i + 2], y[i + 3]);
+                                o.z = pack_bf16(y[i + 4], y[i + 5]);
+                                o.w = pack_bf16(y[i + 6], y[i + 7]);
+                                const int c16 = (h + i) >> 3;  // 16-byte chunk within the 128-byte row
+                                *reinterpret_cast<uint4*>(stag + row * 128 + ((c16 ^ (row & 7)) << 4)) = o;
+                            }
+                        }
+                    } else if (f32_ptr != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            if (i < cols) {
+                                float4 o = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+                                if (g.lo != nullptr) {
+                                    const float4 lo = __ldg(reinterpret_cast<const float4*>(g.lo + n0 + i));
+                                    o.x = fmaxf(o.x, lo.x);
+                                    o.y = fmaxf(o.y, lo.y);
+                                    o.z = fmaxf(o.z, lo.z);
+                                    o.w = fmaxf(o.w, lo.w);
+                                }
+                                *reinterpret_cast<float4*>(f32_ptr + c0 + h + i) = o;
+                            }
+                        }
+                    }
+                }
+                if (p.out_mode == 0) {
+                    ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+                    ptx::named_bar_sync(1, 128);
+                    if (store_leader) {
+                        ptx::tma_store_4d(&g.out_map, stag, n_base + c0, t.x0, t.y0, t.img);
+                        ptx::tma_store_commit();
+                    }
+                    sbuf ^= 1;
+                }
+            }
+            // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+        if (store_leader) ptx::tma_store_wait_all();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+
+thread_local std::string g_conv_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || sym == nullptr) {
+            g_conv_error = std::string("cuTensorMapEncodeTiled unavailable: ") + cudaGetErrorString(e);
+            return nullptr;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+bool encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+            const cuuint32_t* box, CUtensorMapL2promotion promo) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return false;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu]",
+                 static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                 (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0));
+        g_conv_error = buf;
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+const char* conv_last_error() { return g_conv_error.c_str(); }
+
+// NHWC bf16 activation view: C logical channels of a buffer with `pitch` channels per pixel.
+bool make_act_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch, int th, int tw) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    return encode(map, base, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+}
+
+// Parity-split view for stride-2 convs: element (b, 2*h2+hp, 2*w2+wp, c) -> coords {c, w2, hp, h2, b} of map[wp].
+bool make_act_map_s2(CUtensorMap* map, const void* base, int wp, int B, int H, int W, int C, int pitch, int th,
+                     int tw) {
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(base) + (size_t)wp * pitch;
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)(W / 2), 2, (cuuint64_t)(H / 2), (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)2 * pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)2 * W * pitch * 2,
+                             (cuuint64_t)H * W * pitch * 2};
+    cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, 1, (cuuint32_t)th, 1};
+    return encode(map, b, 5, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+}
+
+bool make_weight_map(CUtensorMap* map, const void* base, int ktot, int cout_pad, int block_n) {
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
+    return encode(map, base, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+}
+
+// Pick the 128-pixel patch shape that wastes the fewest out-of-image pixels.
+void choose_tile(int H, int W, int* th, int* tw) {
+    static const int shapes[][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}, {32, 4}};
+    long best = -1;
+    for (auto& s : shapes) {
+        long tiles = (long)((H + s[0] - 1) / s[0]) * ((W + s[1] - 1) / s[1]);
+        if (best < 0 || tiles < best) {
+            best = tiles;
+            *th = s[0];
+            *tw = s[1];
+        }
+    }
+}
+
+void conv_finalize_params(ConvParams* p) {
+    int tile = 0;
+    for (int s = 0; s < p->nseg; ++s) {
+        ConvSeg& g = p->seg[s];
+        g.tiles_x = (g.W + g.tw - 1) / g.tw;
+        g.tiles_y = (g.H + g.th - 1) / g.th;
+        g.tile_begin = tile;
+        tile += g.tiles_x * g.tiles_y * p->B;
+    }
+    p->total_work = tile * p->n_blocks;
+    const int stage_bytes = kABytes + p->block_n * 128;
+    const int fixed = 2 * kStagingBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    int stages = (kSmemBudget - fixed) / stage_bytes;
+    p->num_stages = std::max(2, std::min(kMaxStages, stages));
+    int cols = 32;
+    while (cols < 2 * p->block_n) cols *= 2;
+    p->tmem_cols = cols;
+}
+
+cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
+    const int stage_bytes = kABytes + p.block_n * 128;
+    const int smem_bytes = p.num_stages * stage_bytes + 2 * kStagingBytes + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e =
+            cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (p.total_work <= 0) return cudaSuccess;
+    const int grid = std::min(p.total_work, num_sms);
+    conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace dd3d

@@ -1,0 +1,63 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a): interface.
+//
+// One launch covers up to kMaxSeg "segments" (FPN levels) that share one weight tensor (the FCOS towers share
+// weights across levels, reference fcos2d.py:74-91 / fcos3d.py:81-100) but have their own activation tensors,
+// spatial sizes and folded-BN epilogue vectors (ModuleListDial, normalization.py:30-40).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dd3d {
+
+constexpr int kMaxSeg = 5;
+constexpr int kBlockM = 128;  // output pixels per tile (th * tw)
+constexpr int kBlockK = 64;   // bf16 channels per k-block = one 128-byte swizzle row
+constexpr int kConvThreads = 192;
+
+struct ConvSeg {
+    CUtensorMap in_map[2];  // NHWC bf16 input.  stride 1: [0] (4-D).  stride 2: [w-parity] (5-D parity split)
+    CUtensorMap out_map;    // NHWC bf16 output (out_mode 0), 4-D, TMA store clips partial tiles
+    const float* scale;     // [n_pad] folded BN scale (1 when no norm)
+    const float* bias;      // [n_pad] folded BN bias / conv bias
+    const float* lo;        // [n_pad] per-channel lower clamp (out_mode 1 only; -inf = none) or nullptr
+    const __nv_bfloat16* residual;  // NHWC bf16 added before the activation, or nullptr
+    float* out_f32;         // out_mode 1: NHWC fp32, pitch out_pitch
+    int res_pitch, res_up2, res_H, res_W;  // res_up2: residual is the 2x-coarser map (FPN nearest upsample)
+    int out_pitch;
+    int H, W;         // OUTPUT spatial size
+    int th, tw;       // tile shape, th * tw == 128
+    int tiles_x, tiles_y;
+    int tile_begin;   // index of this segment's first M-tile
+};
+
+struct ConvParams {
+    CUtensorMap w_map;  // weights [cout_pad][taps * kchunks * 64] bf16, K contiguous
+    ConvSeg seg[kMaxSeg];
+    int nseg;
+    int B;
+    int taps;      // 1 or 9
+    int stride;    // 1 or 2 (3x3 only)
+    int kchunks;   // ceil(cin / 64)
+    int n_blocks;  // cout_pad / block_n
+    int block_n;   // UMMA N (multiple of 16, <= 256)
+    int relu;
+    int out_mode;  // 0: bf16 via TMA store, 1: fp32 direct
+    int total_work;  // (sum of M-tiles) * n_blocks
+    int num_stages;
+    int tmem_cols;
+};
+
+// Host helpers (conv_igemm.cu)
+const char* conv_last_error();
+bool make_act_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch, int th, int tw);
+bool make_act_map_s2(CUtensorMap* map, const void* base, int wp, int B, int H, int W, int C, int pitch, int th,
+                     int tw);
+bool make_weight_map(CUtensorMap* map, const void* base, int ktot, int cout_pad, int block_n);
+void choose_tile(int H, int W, int* th, int* tw);
+// Fills num_stages / tmem_cols / total_work / tile bookkeeping from the already-set fields.
+void conv_finalize_params(ConvParams* p);
+cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream);
+
+}  // namespace dd3d

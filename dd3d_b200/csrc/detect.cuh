@@ -1,0 +1,81 @@
+// Detection post-processing: dense threshold + exact per-level top-k + fused 2-D/3-D box decode (decode.cu) and
+// per-image class-aware NMS + top-k + rescale (nms.cu).  All fp32, sync-free, deterministic output order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dd3d {
+
+constexpr int kLevels = 5;
+constexpr int kHistBins = 2048;
+constexpr int kBoundaryCap = 4096;  // candidates sharing the histogram bin of the k-th score (per image x level)
+
+// One decoded detection, 24 x 4 bytes.  Also the element type of the C-ABI output buffer (dd3d_det in the header).
+struct Det {
+    float box[4];      // x1, y1, x2, y2
+    float score;       // sqrt(sigmoid(cls) * sigmoid(ctr))                    fcos2d.py:333
+    float score3d;     // score * sigmoid(conf)                                fcos3d.py:375-376
+    int32_t cls;
+    int32_t level;
+    float quat[4];     // egocentric, (w, x, y, z)
+    float proj_ctr[2];
+    float depth;
+    float size[3];     // (W, L, H)
+    float loc[2];      // feature location (x, y)
+    int32_t index;     // pixel * num_classes + class at its level (deterministic tie-break key)
+    int32_t pad[3];
+};
+static_assert(sizeof(Det) == 96, "Det must be 24 words");
+
+struct DecodeLevel {
+    const float* cls;  // [B][H*W][cls_pitch]   logits
+    const float* box;  // [B][H*W][16]          0..3 = relu(scale*reg) (l,t,r,b), 4 = centerness logit
+    const float* b3d;  // [B][H*W][b3d_pitch]   channel = comp*C + class; comps: quat 0-3, ctr 4-5, depth 6, size 7-9, conf 10
+    int H, W, stride;
+    int block_begin;   // first block (of the dense kernels' grid.x) that belongs to this level
+};
+
+struct DecodeParams {
+    DecodeLevel lvl[kLevels];
+    int B, C, cls_pitch, b3d_pitch;
+    int topk;           // PRE_NMS_TOPK
+    float thresh;       // PRE_NMS_THRESH
+    int loc_offset_half;  // FEATURE_LOCATIONS_OFFSET == "half"
+    int hist_shift;
+    uint32_t thresh_bits;
+    int total_blocks;
+    // 3-D decode constants
+    const float* K;       // [B][9] intrinsics (row-major)
+    const float* canon;   // [C][3]
+    float min_depth, max_depth, depth_factor;
+    int scale_depth_by_focal, allocentric, predict_distance;
+    // scratch (all per image x level)
+    uint32_t* hist;       // [B][L][kHistBins]
+    int32_t* sel;         // [B][L][4] : T, n_above, need, total
+    int32_t* counters;    // [B][L][2] : sure, boundary
+    uint2* sure;          // [B][L][topk]          (score bits, index)
+    uint2* boundary;      // [B][L][kBoundaryCap]
+    Det* cand;            // [B][L*topk]           decoded candidates
+    int32_t* cand_count;  // [B][L]
+    int32_t* flags;       // [1] bit0: boundary overflow
+};
+
+struct NmsParams {
+    const Det* cand;            // [B][L*topk]
+    const int32_t* cand_count;  // [B][L]
+    const int32_t* sizes;       // [B][4] : image h, w, output h, w
+    Det* out;                   // [B][out_cap]
+    int32_t* out_count;         // [B]
+    int32_t* flags;             // bit1: output overflow
+    int B, topk, out_cap;
+    int do_nms, post_topk, do_postprocess;
+    float nms_thresh;
+};
+
+size_t decode_scratch_bytes(int B, int topk);
+void decode_bind_scratch(DecodeParams* p, void* scratch);
+void decode_finalize_params(DecodeParams* p);
+cudaError_t launch_decode(const DecodeParams& p, cudaStream_t stream);
+cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream);
+
+}  // namespace dd3d

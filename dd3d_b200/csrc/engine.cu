@@ -1,0 +1,902 @@
+// DD3D inference engine: weight folding/packing, static graph for DLA-34 / VoVNetV2-99 + FPN + FCOS2D/3D heads,
+// workspace planning and the forward launch sequence.  Reference structure being reproduced:
+//   DD3D.forward                      tridet/modeling/dd3d/core.py:64-164
+//   DLA-34                            tridet/modeling/feature_extractor/dla.py:24-62,146-247,250-361
+//   VoVNetV2-99-eSE                   tridet/modeling/feature_extractor/vovnet.py:79-87,173-273,276-367
+//   FPN + LastLevelP6P7 / LastLevelP6 detectron2, dla.py:537-561, vovnet.py:411-454
+//   FCOS2DHead / FCOS3DHead           fcos2d.py:30-156, fcos3d.py:55-188 (+ normalization.py Scale/Offset/ModuleListDial)
+// Design notes: NHWC bf16 activations; BN folded to fp32 (scale, bias) applied in the conv epilogue;
+// concats never materialised (producers write channel slices); predictors fused per tower.
+#include "engine.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <stdexcept>
+
+namespace dd3d {
+
+namespace {
+
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+inline size_t round_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+[[noreturn]] void fail(int status, const std::string& msg) { throw EngineError(status, msg); }
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) fail(DD3D_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+uint16_t f32_to_bf16(float f) {  // round to nearest even (matches __float2bfloat16_rn / torch .to(bfloat16))
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+    const uint32_t lsb = (u >> 16) & 1u;
+    u += 0x7fffu + lsb;
+    return static_cast<uint16_t>(u >> 16);
+}
+
+}  // namespace
+
+// ================================================================================================ Engine basics
+
+Engine::Engine(const dd3d_model_desc& d) : desc(d) {
+    if (d.arch != DD3D_ARCH_DLA34 && d.arch != DD3D_ARCH_V2_99) fail(DD3D_ERR_INVALID, "unknown arch");
+    if (d.num_classes < 1 || d.num_classes > DD3D_MAX_CLASSES) fail(DD3D_ERR_INVALID, "num_classes out of range");
+    if (d.pre_nms_topk < 1 || d.pre_nms_topk * kLevels > 8192) fail(DD3D_ERR_INVALID, "pre_nms_topk out of range");
+    if (d.out_cap < 1) fail(DD3D_ERR_INVALID, "out_cap must be positive");
+    cuda_check(cudaGetDevice(&device), "cudaGetDevice");
+    cudaDeviceProp prop;
+    cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major != 10) {
+        fail(DD3D_ERR_CUDA, std::string("dd3d_b200 needs an sm_100 (B200) device, found ") + prop.name + " sm_" +
+                                std::to_string(prop.major) + std::to_string(prop.minor));
+    }
+    num_sms = prop.multiProcessorCount;
+}
+
+Engine::~Engine() {
+    release_plan();
+    for (void* p : device_allocs) cudaFree(p);
+}
+
+void* Engine::dev_alloc(size_t bytes) {
+    void* p = nullptr;
+    cuda_check(cudaMalloc(&p, std::max<size_t>(bytes, 16)), "cudaMalloc(weights)");
+    device_allocs.push_back(p);
+    return p;
+}
+
+float* Engine::upload_f32(const std::vector<float>& v) {
+    float* d = static_cast<float*>(dev_alloc(v.size() * 4));
+    cuda_check(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice), "upload f32");
+    return d;
+}
+
+const HostTensor& Engine::weight(const std::string& name) const {
+    auto it = weights.find(name);
+    if (it == weights.end()) fail(DD3D_ERR_MISSING, "missing weight: " + name);
+    return it->second;
+}
+
+void Engine::load_weight(const char* name, const float* data, const int64_t* shape, int ndim) {
+    if (finalized) fail(DD3D_ERR_STATE, "load_weight after finalize");
+    HostTensor t;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        t.shape.push_back(shape[i]);
+        n *= static_cast<size_t>(shape[i]);
+    }
+    t.data.assign(data, data + n);
+    weights[name] = std::move(t);
+}
+
+// ------------------------------------------------------------------------------------------------ layer builders
+
+// Conv weights of one or more reference tensors stacked along Cout -> bf16 [cout_pad][taps][cin_pad64].
+const ConvLayer& Engine::conv_layer(const std::string& key, const std::vector<std::string>& wnames, int cin,
+                                    int ksize) {
+    auto it = convs.find(key);
+    if (it != convs.end()) return it->second;
+    ConvLayer L;
+    L.cin = cin;
+    L.ksize = ksize;
+    L.taps = ksize * ksize;
+    L.kchunks = (cin + kBlockK - 1) / kBlockK;
+    const int cin_pad = L.kchunks * kBlockK;
+    L.ktot = L.taps * cin_pad;
+    int cout = 0;
+    for (auto& n : wnames) {
+        const HostTensor& w = weight(n + ".weight");
+        if (w.shape.size() != 4 || w.shape[1] != cin || w.shape[2] != ksize || w.shape[3] != ksize)
+            fail(DD3D_ERR_INVALID, "bad conv weight shape: " + n);
+        cout += static_cast<int>(w.shape[0]);
+    }
+    L.cout = cout;
+    L.cout_pad = round_up(cout, 16);
+    if (L.cout_pad > 256) {
+        if (L.cout_pad % 256) fail(DD3D_ERR_INVALID, "cout > 256 must be a multiple of 256: " + key);
+        L.block_n = 256;
+    } else {
+        L.block_n = L.cout_pad;
+    }
+    L.n_blocks = L.cout_pad / L.block_n;
+    std::vector<uint16_t> packed(static_cast<size_t>(L.cout_pad) * L.ktot, 0);
+    int co0 = 0;
+    for (auto& n : wnames) {
+        const HostTensor& w = weight(n + ".weight");
+        const int co_n = static_cast<int>(w.shape[0]);
+        for (int co = 0; co < co_n; ++co)
+            for (int ci = 0; ci < cin; ++ci)
+                for (int t = 0; t < L.taps; ++t)
+                    packed[(static_cast<size_t>(co0 + co) * L.taps + t) * cin_pad + ci] =
+                        f32_to_bf16(w.data[(static_cast<size_t>(co) * cin + ci) * L.taps + t]);
+        co0 += co_n;
+    }
+    L.d_w = static_cast<__nv_bfloat16*>(dev_alloc(packed.size() * 2));
+    cuda_check(cudaMemcpy(L.d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice), "upload conv weights");
+    if (!make_weight_map(&L.w_map, L.d_w, L.ktot, L.cout_pad, L.block_n)) fail(DD3D_ERR_CUDA, conv_last_error());
+    return convs.emplace(key, L).first->second;
+}
+
+// (scale, bias) of `conv (+bias) -> BN` for channels [0, cout); identity on the padding channels.
+void Engine::bn_fold(const std::string& bn_prefix, const std::string& conv_bias_name, int cout, std::vector<float>* scale,
+                     std::vector<float>* bias) const {
+    scale->assign(cout, 1.0f);
+    bias->assign(cout, 0.0f);
+    if (!conv_bias_name.empty()) {
+        const HostTensor& b = weight(conv_bias_name);
+        if (static_cast<int>(b.data.size()) != cout) fail(DD3D_ERR_INVALID, "bad bias shape: " + conv_bias_name);
+        *bias = b.data;
+    }
+    if (!bn_prefix.empty()) {
+        const HostTensor& g = weight(bn_prefix + ".weight");
+        const HostTensor& be = weight(bn_prefix + ".bias");
+        const HostTensor& mu = weight(bn_prefix + ".running_mean");
+        const HostTensor& var = weight(bn_prefix + ".running_var");
+        if (static_cast<int>(g.data.size()) != cout) fail(DD3D_ERR_INVALID, "bad BN shape: " + bn_prefix);
+        for (int c = 0; c < cout; ++c) {
+            // FrozenBatchNorm2d / eval BatchNorm2d, eps = 1e-5: s = gamma * rsqrt(var + eps); b = beta - mean * s
+            const float s = g.data[c] * (1.0f / sqrtf(var.data[c] + 1e-5f));
+            const float b = be.data[c] - mu.data[c] * s;
+            (*bias)[c] = (*bias)[c] * s + b;
+            (*scale)[c] = s;
+        }
+    }
+}
+
+const Epilogue& Engine::epilogue(const std::string& key, const std::vector<float>& scale, const std::vector<float>& bias,
+                                 const std::vector<float>* lo) {
+    auto it = epis.find(key);
+    if (it != epis.end()) return it->second;
+    const int n_pad = round_up(static_cast<int>(scale.size()), 16);
+    std::vector<float> s(n_pad, 1.0f), b(n_pad, 0.0f);
+    std::copy(scale.begin(), scale.end(), s.begin());
+    std::copy(bias.begin(), bias.end(), b.begin());
+    Epilogue e;
+    e.d_scale = upload_f32(s);
+    e.d_bias = upload_f32(b);
+    e.d_lo = nullptr;
+    if (lo != nullptr) {
+        std::vector<float> l(n_pad, -INFINITY);
+        std::copy(lo->begin(), lo->end(), l.begin());
+        e.d_lo = upload_f32(l);
+    }
+    return epis.emplace(key, e).first->second;
+}
+
+const Epilogue& Engine::bn_epilogue(const std::string& key, const std::string& bn_prefix,
+                                    const std::string& conv_bias_name, int cout) {
+    auto it = epis.find(key);
+    if (it != epis.end()) return it->second;
+    std::vector<float> s, b;
+    bn_fold(bn_prefix, conv_bias_name, cout, &s, &b);
+    return epilogue(key, s, b, nullptr);
+}
+
+// ================================================================================================ graph builder
+
+struct Builder {
+    Engine* E;
+    Plan* P;
+    bool dry;       // true: only size the arena and create layers (no tensor maps, no ops)
+    uint8_t* base;  // arena base (nullptr when dry)
+    size_t off = 0;
+    int B;
+
+    View alloc(int H, int W, int C) {
+        View v;
+        v.B = B; v.H = H; v.W = W; v.C = C; v.pitch = C;
+        const size_t bytes = static_cast<size_t>(B) * H * W * C * 2;
+        v.ptr = dry ? nullptr : reinterpret_cast<__nv_bfloat16*>(base + off);
+        off += round_up_sz(bytes, 1024);
+        return v;
+    }
+    float* alloc_f32(size_t n) {
+        float* p = dry ? nullptr : reinterpret_cast<float*>(base + off);
+        off += round_up_sz(n * 4, 1024);
+        return p;
+    }
+    void* alloc_bytes(size_t n) {
+        void* p = dry ? nullptr : static_cast<void*>(base + off);
+        off += round_up_sz(n, 1024);
+        return p;
+    }
+    static View slice(View v, int c0, int C) {
+        if (v.ptr) v.ptr += c0;
+        v.C = C;
+        return v;
+    }
+
+    // ---- conv (one or several segments sharing the weights) ------------------------------------------------
+    struct SegSpec {
+        View in, out;
+        const Epilogue* epi;
+        View res;           // residual (ptr == nullptr: none)
+        bool has_res = false;
+        bool res_up2 = false;
+        float* out_f32 = nullptr;
+        int out_pitch = 0;
+    };
+
+    void conv(const ConvLayer& L, int stride, bool relu, std::vector<SegSpec>& segs, bool f32_out) {
+        if (dry) return;
+        Op op;
+        op.type = Op::CONV;
+        ConvParams& p = op.conv;
+        memset(&p, 0, sizeof(p));
+        p.w_map = L.w_map;
+        p.nseg = static_cast<int>(segs.size());
+        p.B = B;
+        p.taps = L.taps;
+        p.stride = stride;
+        p.kchunks = L.kchunks;
+        p.n_blocks = L.n_blocks;
+        p.block_n = L.block_n;
+        p.relu = relu ? 1 : 0;
+        p.out_mode = f32_out ? 1 : 0;
+        for (int s = 0; s < p.nseg; ++s) {
+            SegSpec& sp = segs[s];
+            ConvSeg& g = p.seg[s];
+            if (sp.in.C != L.cin) fail(DD3D_ERR_INVALID, "conv input channel mismatch");
+            int Ho = sp.in.H, Wo = sp.in.W;
+            if (stride == 2) {
+                if ((sp.in.H & 1) || (sp.in.W & 1)) fail(DD3D_ERR_INVALID, "stride-2 conv needs even input size");
+                Ho = sp.in.H / 2;
+                Wo = sp.in.W / 2;
+            }
+            g.H = Ho;
+            g.W = Wo;
+            choose_tile(Ho, Wo, &g.th, &g.tw);
+            bool ok;
+            if (stride == 1) {
+                ok = make_act_map(&g.in_map[0], sp.in.ptr, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, g.th, g.tw);
+            } else {
+                ok = make_act_map_s2(&g.in_map[0], sp.in.ptr, 0, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, g.th, g.tw) &&
+                     make_act_map_s2(&g.in_map[1], sp.in.ptr, 1, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, g.th, g.tw);
+            }
+            if (!ok) fail(DD3D_ERR_CUDA, conv_last_error());
+            g.scale = sp.epi->d_scale;
+            g.bias = sp.epi->d_bias;
+            g.lo = sp.epi->d_lo;
+            if (f32_out) {
+                g.out_f32 = sp.out_f32;
+                g.out_pitch = sp.out_pitch;
+            } else {
+                if (sp.out.H != Ho || sp.out.W != Wo || sp.out.C != L.cout)
+                    fail(DD3D_ERR_INVALID, "conv output view mismatch");
+                if (!make_act_map(&g.out_map, sp.out.ptr, B, Ho, Wo, sp.out.C, sp.out.pitch, g.th, g.tw))
+                    fail(DD3D_ERR_CUDA, conv_last_error());
+            }
+            if (sp.has_res) {
+                g.residual = sp.res.ptr;
+                g.res_pitch = sp.res.pitch;
+                g.res_up2 = sp.res_up2 ? 1 : 0;
+                g.res_H = sp.res.H;
+                g.res_W = sp.res.W;
+            }
+        }
+        conv_finalize_params(&p);
+        P->ops.push_back(op);
+    }
+
+    // single-segment convenience: conv -> (BN) -> (+res) -> (ReLU) into `out`
+    void conv1(const std::string& wname, const std::string& bn_prefix, bool has_bias, View in, View out, int ksize,
+               int stride, bool relu, const View* res = nullptr, bool res_up2 = false) {
+        const ConvLayer& L = E->conv_layer(wname, {wname}, in.C, ksize);
+        const Epilogue& e = E->bn_epilogue(wname + "|" + bn_prefix, bn_prefix, has_bias ? wname + ".bias" : "", L.cout);
+        std::vector<SegSpec> segs(1);
+        segs[0].in = in;
+        segs[0].out = out;
+        segs[0].epi = &e;
+        if (res) {
+            segs[0].res = *res;
+            segs[0].has_res = true;
+            segs[0].res_up2 = res_up2;
+        }
+        conv(L, stride, relu, segs, false);
+    }
+
+    void maxpool(View in, View out, int ksize) {
+        if (dry) return;
+        Op op;
+        op.type = Op::POOL;
+        op.in = in;
+        op.out = out;
+        op.ksize = ksize;
+        P->ops.push_back(op);
+    }
+    void relu(View in, View out) {
+        if (dry) return;
+        Op op;
+        op.type = Op::RELU;
+        op.in = in;
+        op.out = out;
+        P->ops.push_back(op);
+    }
+
+    // ---- DLA-34 -------------------------------------------------------------------------------------------
+    // BasicBlock (dla.py:24-62): conv1 -> BN -> ReLU -> conv2 -> BN -> (+residual) -> ReLU
+    void dla_block(const std::string& p, View x, int stride, View residual, View dst) {
+        const int Ho = x.H / stride, Wo = x.W / stride;
+        View t = alloc(Ho, Wo, dst.C);
+        conv1(p + ".conv1", p + ".conv1.norm", false, x, t, 3, stride, true);
+        conv1(p + ".conv2", p + ".conv2.norm", false, t, dst, 3, 1, true, &residual);
+    }
+    // Tree with levels == 1 (dla.py:170-247): `rc` is the Root's concat buffer, laid out [x2 | x1 | children...]
+    // with the children already in place; `bottom` is the (pooled) input the optional `project` acts on.
+    void dla_tree1(const std::string& p, View x, int in_ch, int out_ch, int stride, View rc, View bottom, View dst) {
+        View residual = bottom;
+        if (in_ch != out_ch) {
+            residual = alloc(bottom.H, bottom.W, out_ch);
+            conv1(p + ".project", p + ".project.norm", false, bottom, residual, 1, 1, false);
+        }
+        View x1 = slice(rc, out_ch, out_ch);
+        View x2 = slice(rc, 0, out_ch);
+        dla_block(p + ".tree1", x, stride, residual, x1);
+        dla_block(p + ".tree2", x1, 1, x1, x2);
+        conv1(p + ".root.conv", p + ".root.conv.norm", false, rc, dst, 1, 1, true);  // Root: cat -> 1x1 -> BN -> ReLU
+    }
+    // Tree with levels == 2 and level_root (level3 / level4, dla.py:309-314)
+    View dla_tree2(const std::string& p, View x, int in_ch, int out_ch) {
+        const int Ho = x.H / 2, Wo = x.W / 2;
+        View rc2 = alloc(Ho, Wo, 3 * out_ch + in_ch);  // [x2 | x1 | bottom | tree1-out]   (dla.py:235-245)
+        View bottom = slice(rc2, 2 * out_ch, in_ch);
+        View t1_out = slice(rc2, 2 * out_ch + in_ch, out_ch);
+        maxpool(x, bottom, 2);  // outer and inner Tree pool the same tensor (dla.py:235) -> computed once
+        View rc1 = alloc(Ho, Wo, 2 * out_ch);
+        dla_tree1(p + ".tree1", x, in_ch, out_ch, 2, rc1, bottom, t1_out);
+        View out = alloc(Ho, Wo, out_ch);
+        dla_tree1(p + ".tree2", t1_out, out_ch, out_ch, 1, rc2, t1_out, out);
+        return out;
+    }
+
+    void build_dla34(View input, std::vector<View>* feats) {
+        const std::string p = "backbone.bottom_up";
+        const int H = input.H, W = input.W;
+        View a0 = alloc(H, W, 16);
+        stem(p + ".base_layer", p + ".base_layer.norm", input, a0, 7, 1);
+        View a1 = alloc(H, W, 16);
+        conv1(p + ".level0.0", p + ".level0.0.norm", false, a0, a1, 3, 1, true);
+        View a2 = alloc(H / 2, W / 2, 32);
+        conv1(p + ".level1.0", p + ".level1.0.norm", false, a1, a2, 3, 2, true);
+        // level2: Tree(levels=1, 32->64, stride 2)
+        View rc = alloc(H / 4, W / 4, 128);
+        View bottom = alloc(H / 4, W / 4, 32);
+        maxpool(a2, bottom, 2);
+        View l2 = alloc(H / 4, W / 4, 64);
+        dla_tree1(p + ".level2", a2, 32, 64, 2, rc, bottom, l2);
+        View l3 = dla_tree2(p + ".level3", l2, 64, 128);
+        View l4 = dla_tree2(p + ".level4", l3, 128, 256);
+        // level5: Tree(levels=1, 256->512, stride 2, level_root) -> root input [x2 | x1 | bottom]
+        View rc5 = alloc(H / 32, W / 32, 1280);
+        View bottom5 = slice(rc5, 1024, 256);
+        maxpool(l4, bottom5, 2);
+        View l5 = alloc(H / 32, W / 32, 512);
+        dla_tree1(p + ".level5", l4, 256, 512, 2, rc5, bottom5, l5);
+        feats->assign({l3, l4, l5});
+    }
+
+    void stem(const std::string& wname, const std::string& bn, View in4, View out, int ksize, int stride) {
+        const StemLayer& S = E->stem_layer(wname, bn, ksize, stride);
+        if (dry) return;
+        Op op;
+        op.type = Op::STEM;
+        op.in = in4;
+        op.out = out;
+        op.ksize = ksize;
+        op.stride = stride;
+        op.stem = &S;
+        P->ops.push_back(op);
+    }
+
+    // ---- VoVNetV2-99-eSE ----------------------------------------------------------------------------------
+    void build_v2_99(View input, std::vector<View>* feats) {
+        const std::string p = "backbone.bottom_up";
+        const int H = input.H, W = input.W;
+        static const int stage_ch[4] = {128, 160, 192, 224};
+        static const int out_ch[4] = {256, 512, 768, 1024};
+        static const int blocks[4] = {1, 3, 9, 3};
+        View s1 = alloc(H / 2, W / 2, 64);
+        stem(p + ".stem.stem_1/conv", p + ".stem.stem_1/norm", input, s1, 3, 2);
+        View s2 = alloc(H / 2, W / 2, 64);
+        conv1(p + ".stem.stem_2/conv", p + ".stem.stem_2/norm", false, s1, s2, 3, 1, true);
+        int h = H / 4, w = W / 4;
+        int in_ch = 128;
+        View cat = alloc(h, w, in_ch + 5 * stage_ch[0]);
+        conv1(p + ".stem.stem_3/conv", p + ".stem.stem_3/norm", false, s2, slice(cat, 0, in_ch), 3, 2, true);
+        View stage_out;
+        for (int si = 0; si < 4; ++si) {
+            const int sc = stage_ch[si], oc = out_ch[si];
+            if (si > 0) {
+                const int hp = (h - 3 + 1) / 2 + 1, wp = (w - 3 + 1) / 2 + 1;  // 3x3 / s2, ceil_mode (vovnet.py:249)
+                cat = alloc(hp, wp, in_ch + 5 * sc);
+                maxpool(stage_out, slice(cat, 0, in_ch), 3);
+                h = hp;
+                w = wp;
+            }
+            for (int b = 0; b < blocks[si]; ++b) {
+                const std::string name = "OSA" + std::to_string(si + 2) + "_" + std::to_string(b + 1);
+                const std::string q = p + ".stage" + std::to_string(si + 2) + "." + name;
+                View x = slice(cat, 0, in_ch);
+                int c0 = in_ch;
+                View prev = x;
+                for (int i = 0; i < 5; ++i) {
+                    const std::string ln = q + ".layers." + std::to_string(i) + "." + name + "_" + std::to_string(i);
+                    View o = slice(cat, c0, sc);
+                    conv1(ln + "/conv", ln + "/norm", false, prev, o, 3, 1, true);
+                    prev = o;
+                    c0 += sc;
+                }
+                View xt = alloc(h, w, oc);
+                conv1(q + ".concat." + name + "_concat/conv", q + ".concat." + name + "_concat/norm", false, cat, xt, 1,
+                      1, true);
+                // eSE (always applied, vovnet.py:216,233) then identity add for non-first blocks (:235-236)
+                View dst;
+                View next_cat;
+                const bool last = (b == blocks[si] - 1);
+                if (last) {
+                    dst = alloc(h, w, oc);
+                } else {
+                    next_cat = alloc(h, w, oc + 5 * sc);
+                    dst = slice(next_cat, 0, oc);
+                }
+                ese(q + ".ese.fc", xt, b > 0 ? &x : nullptr, dst);
+                if (last) {
+                    stage_out = dst;
+                } else {
+                    cat = next_cat;
+                }
+                in_ch = oc;
+            }
+            feats->push_back(stage_out);
+        }
+    }
+
+    void ese(const std::string& fc, View xt, const View* identity, View dst) {
+        const EseLayer& L = E->ese_layer(fc, xt.C);
+        const int HW = xt.H * xt.W;
+        float* partial = alloc_f32(static_cast<size_t>(B) * ese_nsplit(HW) * xt.C);
+        float* gate = alloc_f32(static_cast<size_t>(B) * xt.C);
+        if (dry) return;
+        Op op;
+        op.type = Op::ESE;
+        op.in = xt;
+        op.out = dst;
+        op.ese = &L;
+        op.has_identity = identity != nullptr;
+        if (identity) op.identity = *identity;
+        op.f0 = partial;
+        op.f1 = gate;
+        P->ops.push_back(op);
+    }
+
+    // ---- FPN (detectron2 FPN.forward + top block) -----------------------------------------------------------
+    void build_fpn(const std::vector<View>& feats, int first_stage, std::vector<View>* outs) {
+        const std::string p = "backbone";
+        const int n = static_cast<int>(feats.size());
+        std::vector<View> res(n);
+        View prev;
+        for (int i = n - 1; i >= 0; --i) {
+            const std::string st = std::to_string(first_stage + i);
+            const View& c = feats[i];
+            View lat = alloc(c.H, c.W, 256);
+            if (i == n - 1) {
+                conv1(p + ".fpn_lateral" + st, p + ".fpn_lateral" + st + ".norm", false, c, lat, 1, 1, false);
+            } else {
+                // lateral + nearest-2x(prev): the un-smoothed `prev` is what propagates downwards
+                conv1(p + ".fpn_lateral" + st, p + ".fpn_lateral" + st + ".norm", false, c, lat, 1, 1, false, &prev,
+                      true);
+            }
+            prev = lat;
+            res[i] = alloc(c.H, c.W, 256);
+            conv1(p + ".fpn_output" + st, p + ".fpn_output" + st + ".norm", false, lat, res[i], 3, 1, false);
+        }
+        *outs = res;
+        const View& p5 = res[n - 1];
+        View p6 = alloc(p5.H / 2, p5.W / 2, 256);
+        conv1(p + ".top_block.p6", "", true, p5, p6, 3, 2, false);
+        outs->push_back(p6);
+        if (E->desc.arch == DD3D_ARCH_DLA34) {
+            View r6 = alloc(p6.H, p6.W, 256);
+            relu(p6, r6);
+            View p7 = alloc(p6.H / 2, p6.W / 2, 256);
+            conv1(p + ".top_block.p7", "", true, r6, p7, 3, 2, false);
+            outs->push_back(p7);
+        }
+    }
+
+    // ---- heads ------------------------------------------------------------------------------------------------
+    void tower(const std::string& tp, const std::vector<View>& feats, std::vector<View>* out) {
+        std::vector<View> cur = feats;
+        std::vector<View> buf[2];
+        for (int k = 0; k < 2; ++k)
+            for (auto& f : feats) buf[k].push_back(alloc(f.H, f.W, 256));
+        for (int i = 0; i < 4; ++i) {
+            const std::string wn = tp + "." + std::to_string(i);
+            const ConvLayer& L = E->conv_layer(wn, {wn}, 256, 3);
+            std::vector<SegSpec> segs(feats.size());
+            for (size_t l = 0; l < feats.size(); ++l) {
+                const std::string bn = wn + ".norm." + std::to_string(l);  // ModuleListDial: level l -> norm l
+                segs[l].in = cur[l];
+                segs[l].out = buf[i & 1][l];
+                segs[l].epi = &E->bn_epilogue(wn + "|" + bn, bn, "", 256);
+            }
+            conv(L, 1, true, segs, false);
+            cur = buf[i & 1];
+        }
+        *out = cur;
+    }
+
+    void build_heads(const std::vector<View>& feats) {
+        const int C = E->desc.num_classes;
+        const int L = static_cast<int>(feats.size());
+        const int cls_pitch = round_up(C, 16), b3d_pitch = round_up(11 * C, 16);
+        P->cls_pitch = cls_pitch;
+        P->b3d_pitch = b3d_pitch;
+        std::vector<View> cls_t, box_t, b3d_t;
+        tower("fcos2d_head.cls_tower", feats, &cls_t);
+        tower("fcos2d_head.box2d_tower", feats, &box_t);
+        tower("fcos3d_head.box3d_tower", feats, &b3d_t);
+        for (int l = 0; l < L; ++l) {
+            const size_t hw = static_cast<size_t>(B) * feats[l].H * feats[l].W;
+            P->cls_map[l] = alloc_f32(hw * cls_pitch);
+            P->box_map[l] = alloc_f32(hw * 16);
+            P->b3d_map[l] = alloc_f32(hw * b3d_pitch);
+            P->lvl_h[l] = feats[l].H;
+            P->lvl_w[l] = feats[l].W;
+        }
+        // cls_logits (fcos2d.py:96,142): bias only, shared across levels
+        {
+            const ConvLayer& Lc = E->conv_layer("fcos2d_head.cls_logits", {"fcos2d_head.cls_logits"}, 256, 3);
+            const Epilogue& e = E->bn_epilogue("fcos2d_head.cls_logits|", "", "fcos2d_head.cls_logits.bias", C);
+            std::vector<SegSpec> segs(L);
+            for (int l = 0; l < L; ++l) {
+                segs[l].in = cls_t[l];
+                segs[l].epi = &e;
+                segs[l].out_f32 = P->cls_map[l];
+                segs[l].out_pitch = cls_pitch;
+            }
+            conv(Lc, 1, false, segs, true);
+        }
+        // [box2d_reg (4) | centerness (1)] on the box2d tower: relu(scale_l * (conv + b)) / conv + b (fcos2d.py:143-152)
+        {
+            const ConvLayer& Lb = E->conv_layer("fcos2d_head.box2d_reg+centerness",
+                                                {"fcos2d_head.box2d_reg", "fcos2d_head.centerness"}, 256, 3);
+            std::vector<SegSpec> segs(L);
+            for (int l = 0; l < L; ++l) {
+                const std::string key = "fcos2d_head.box@" + std::to_string(l);
+                if (E->epis.find(key) == E->epis.end()) {
+                    const float s = E->weight("fcos2d_head.scales_box2d_reg." + std::to_string(l) + ".scale").data[0];
+                    const HostTensor& br = E->weight("fcos2d_head.box2d_reg.bias");
+                    const HostTensor& bc = E->weight("fcos2d_head.centerness.bias");
+                    std::vector<float> sc(5), bi(5), lo(5);
+                    for (int k = 0; k < 4; ++k) {
+                        sc[k] = s;
+                        bi[k] = br.data[k] * s;
+                        lo[k] = 0.0f;
+                    }
+                    sc[4] = 1.0f;
+                    bi[4] = bc.data[0];
+                    lo[4] = -INFINITY;
+                    E->epilogue(key, sc, bi, &lo);
+                }
+                segs[l].in = box_t[l];
+                segs[l].epi = &E->epis.at(key);
+                segs[l].out_f32 = P->box_map[l];
+                segs[l].out_pitch = 16;
+            }
+            conv(Lb, 1, false, segs, true);
+        }
+        // [quat 4C | ctr 2C | depth C | size 3C | conf C] on the box3d tower with the per-level Scale/Offset folded
+        // (fcos3d.py:166-180; PER_LEVEL_PREDICTORS False -> predictor index 0)
+        {
+            const ConvLayer& L3 = E->conv_layer(
+                "fcos3d_head.box3d_all",
+                {"fcos3d_head.box3d_quat.0", "fcos3d_head.box3d_ctr.0", "fcos3d_head.box3d_depth.0",
+                 "fcos3d_head.box3d_size.0", "fcos3d_head.box3d_conf.0"},
+                256, 3);
+            std::vector<SegSpec> segs(L);
+            for (int l = 0; l < L; ++l) {
+                const std::string key = "fcos3d_head.b3d@" + std::to_string(l);
+                if (E->epis.find(key) == E->epis.end()) {
+                    const std::string ls = std::to_string(l);
+                    const float s_ctr = E->weight("fcos3d_head.scales_proj_ctr." + ls + ".scale").data[0];
+                    const float s_size = E->weight("fcos3d_head.scales_size." + ls + ".scale").data[0];
+                    const float s_conf = E->weight("fcos3d_head.scales_conf." + ls + ".scale").data[0];
+                    const float s_depth = E->weight("fcos3d_head.scales_depth." + ls + ".scale").data[0];
+                    const float o_depth = E->weight("fcos3d_head.offsets_depth." + ls + ".bias").data[0];
+                    std::vector<float> sc(11 * C), bi(11 * C);
+                    auto fill = [&](int c0, int n, float s, const char* bias_name, float add) {
+                        const bool has = E->weights.find(bias_name) != E->weights.end();
+                        for (int k = 0; k < n; ++k) {
+                            sc[c0 + k] = s;
+                            bi[c0 + k] = (has ? E->weight(bias_name).data[k] : 0.0f) * s + add;
+                        }
+                    };
+                    fill(0, 4 * C, 1.0f, "fcos3d_head.box3d_quat.0.bias", 0.f);
+                    fill(4 * C, 2 * C, s_ctr, "fcos3d_head.box3d_ctr.0.bias", 0.f);
+                    fill(6 * C, C, s_depth, "fcos3d_head.box3d_depth.0.bias", o_depth);
+                    fill(7 * C, 3 * C, s_size, "fcos3d_head.box3d_size.0.bias", 0.f);
+                    fill(10 * C, C, s_conf, "fcos3d_head.box3d_conf.0.bias", 0.f);
+                    E->epilogue(key, sc, bi, nullptr);
+                }
+                segs[l].in = b3d_t[l];
+                segs[l].epi = &E->epis.at(key);
+                segs[l].out_f32 = P->b3d_map[l];
+                segs[l].out_pitch = b3d_pitch;
+            }
+            conv(L3, 1, false, segs, true);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ misc layers
+
+const StemLayer& Engine::stem_layer(const std::string& wname, const std::string& bn, int ksize, int stride) {
+    auto it = stems.find(wname);
+    if (it != stems.end()) return it->second;
+    const HostTensor& w = weight(wname + ".weight");
+    if (w.shape.size() != 4 || w.shape[1] != 3 || w.shape[2] != ksize || w.shape[0] % 16)
+        fail(DD3D_ERR_INVALID, "bad stem weight: " + wname);
+    StemLayer S;
+    S.ksize = ksize;
+    S.stride = stride;
+    S.cout = static_cast<int>(w.shape[0]);
+    // engine layout [ky][kx][c][cout] fp32, with the weights pre-rounded to bf16 like every other conv
+    std::vector<float> packed(static_cast<size_t>(ksize) * ksize * 3 * S.cout);
+    for (int co = 0; co < S.cout; ++co)
+        for (int c = 0; c < 3; ++c)
+            for (int t = 0; t < ksize * ksize; ++t) {
+                const uint32_t bits = static_cast<uint32_t>(f32_to_bf16(w.data[(static_cast<size_t>(co) * 3 + c) * ksize * ksize + t])) << 16;
+                float f;
+                memcpy(&f, &bits, 4);
+                packed[(static_cast<size_t>(t) * 3 + c) * S.cout + co] = f;
+            }
+    S.d_w = upload_f32(packed);
+    S.epi = bn_epilogue(wname + "|" + bn, bn, "", S.cout);
+    return stems.emplace(wname, S).first->second;
+}
+
+const EseLayer& Engine::ese_layer(const std::string& fc, int C) {
+    auto it = eses.find(fc);
+    if (it != eses.end()) return it->second;
+    const HostTensor& w = weight(fc + ".weight");
+    const HostTensor& b = weight(fc + ".bias");
+    if (static_cast<int>(w.data.size()) != C * C || static_cast<int>(b.data.size()) != C)
+        fail(DD3D_ERR_INVALID, "bad eSE fc shape: " + fc);
+    EseLayer L;
+    L.C = C;
+    L.d_w = upload_f32(w.data);
+    L.d_b = upload_f32(b.data);
+    return eses.emplace(fc, L).first->second;
+}
+
+// ================================================================================================ plan / forward
+
+int Engine::size_divisibility() const { return desc.arch == DD3D_ARCH_DLA34 ? 128 : 64; }
+
+size_t Engine::build(Plan* P, int B, int Hs, int Ws, void* workspace, bool dry) {
+    const int d = size_divisibility();
+    const int Hp = round_up(Hs, d), Wp = round_up(Ws, d);
+    P->B = B; P->Hs = Hs; P->Ws = Ws; P->Hp = Hp; P->Wp = Wp;
+    P->ops.clear();
+    Builder bld;
+    bld.E = this;
+    bld.P = P;
+    bld.dry = dry;
+    bld.base = static_cast<uint8_t*>(workspace);
+    bld.B = B;
+    View input;
+    input.B = B; input.H = Hp; input.W = Wp; input.C = 4; input.pitch = 4;
+    input.ptr = dry ? nullptr : reinterpret_cast<__nv_bfloat16*>(bld.base + bld.off);
+    bld.off += round_up_sz(static_cast<size_t>(B) * Hp * Wp * 4 * 2, 1024);
+    P->input = input;
+    std::vector<View> feats, fpn;
+    if (desc.arch == DD3D_ARCH_DLA34) {
+        bld.build_dla34(input, &feats);
+        bld.build_fpn(feats, 3, &fpn);
+    } else {
+        bld.build_v2_99(input, &feats);
+        bld.build_fpn(feats, 2, &fpn);
+    }
+    if (static_cast<int>(fpn.size()) != kLevels) fail(DD3D_ERR_STATE, "internal: expected 5 FPN levels");
+    for (int l = 0; l < kLevels; ++l) P->fpn[l] = fpn[l];
+    bld.build_heads(fpn);
+    // detection scratch + staging for the host-facing path
+    P->detect_scratch = bld.alloc_bytes(decode_scratch_bytes(B, desc.pre_nms_topk));
+    P->d_K = static_cast<float*>(bld.alloc_bytes(static_cast<size_t>(B) * 9 * 4));
+    P->d_sizes = static_cast<int32_t*>(bld.alloc_bytes(static_cast<size_t>(B) * 4 * 4));
+    P->d_out = static_cast<Det*>(bld.alloc_bytes(static_cast<size_t>(B) * desc.out_cap * sizeof(Det)));
+    P->d_counts = static_cast<int32_t*>(bld.alloc_bytes(static_cast<size_t>(B) * 4));
+    P->d_images = bld.alloc_bytes(static_cast<size_t>(B) * 3 * Hs * Ws * 4);
+    P->d_canon = nullptr;
+    return bld.off;
+}
+
+void Engine::finalize() {
+    if (finalized) return;
+    // dry graph walk with the smallest legal shape: creates (packs + uploads) every layer and names the first
+    // missing tensor, without needing a workspace.
+    Plan tmp;
+    build(&tmp, 1, size_divisibility(), size_divisibility(), nullptr, true);
+    std::vector<float> canon(desc.canonical_box3d_sizes, desc.canonical_box3d_sizes + DD3D_MAX_CLASSES * 3);
+    d_canon = upload_f32(canon);
+    finalized = true;
+    weights.clear();  // host copies are no longer needed
+}
+
+size_t Engine::workspace_bytes(int B, int Hs, int Ws) {
+    if (!finalized) fail(DD3D_ERR_STATE, "workspace_bytes before finalize");
+    Plan tmp;
+    return build(&tmp, B, Hs, Ws, nullptr, true);
+}
+
+void Engine::release_plan() {
+    if (plan.owned_workspace) cudaFree(plan.owned_workspace);
+    plan = Plan();
+}
+
+void Engine::make_plan(int B, int Hs, int Ws, void* workspace, size_t bytes) {
+    if (!finalized) fail(DD3D_ERR_STATE, "plan before finalize");
+    if (B < 1 || Hs < 1 || Ws < 1) fail(DD3D_ERR_INVALID, "bad plan shape");
+    cuda_check(cudaSetDevice(device), "cudaSetDevice");
+    const size_t need = workspace_bytes(B, Hs, Ws);
+    release_plan();
+    if (workspace == nullptr) {
+        cuda_check(cudaMalloc(&plan.owned_workspace, need), "cudaMalloc(workspace)");
+        workspace = plan.owned_workspace;
+    } else if (bytes < need) {
+        fail(DD3D_ERR_INVALID, "workspace too small: need " + std::to_string(need) + " bytes");
+    }
+    if (reinterpret_cast<uintptr_t>(workspace) % 1024) fail(DD3D_ERR_INVALID, "workspace must be 1024-byte aligned");
+    build(&plan, B, Hs, Ws, workspace, false);
+    plan.valid = true;
+    // decode / NMS parameter blocks
+    DecodeParams& dp = plan.decode;
+    memset(&dp, 0, sizeof(dp));
+    static const int strides_dla[5] = {8, 16, 32, 64, 128};
+    static const int strides_vov[5] = {4, 8, 16, 32, 64};
+    const int* strides = desc.arch == DD3D_ARCH_DLA34 ? strides_dla : strides_vov;
+    for (int l = 0; l < kLevels; ++l) {
+        dp.lvl[l].cls = plan.cls_map[l];
+        dp.lvl[l].box = plan.box_map[l];
+        dp.lvl[l].b3d = plan.b3d_map[l];
+        dp.lvl[l].H = plan.lvl_h[l];
+        dp.lvl[l].W = plan.lvl_w[l];
+        dp.lvl[l].stride = strides[l];
+    }
+    fill_decode_params(&dp, desc, B, plan.cls_pitch, plan.b3d_pitch, d_canon);
+    decode_bind_scratch(&dp, plan.detect_scratch);
+    decode_finalize_params(&dp);
+    fill_nms_params(&plan.nms, desc, dp, B);
+}
+
+void fill_decode_params(DecodeParams* dp, const dd3d_model_desc& desc, int B, int cls_pitch, int b3d_pitch,
+                        const float* d_canon) {
+    dp->B = B;
+    dp->C = desc.num_classes;
+    dp->cls_pitch = cls_pitch;
+    dp->b3d_pitch = b3d_pitch;
+    dp->topk = desc.pre_nms_topk;
+    dp->thresh = desc.pre_nms_thresh;
+    dp->loc_offset_half = desc.feature_locations_offset_half;
+    dp->canon = d_canon;
+    dp->min_depth = desc.min_depth;
+    dp->max_depth = desc.max_depth;
+    dp->depth_factor = desc.scale_depth_by_focal_lengths_factor;
+    dp->scale_depth_by_focal = desc.scale_depth_by_focal_lengths;
+    dp->allocentric = desc.predict_allocentric_rot;
+    dp->predict_distance = desc.predict_distance;
+}
+
+void fill_nms_params(NmsParams* np, const dd3d_model_desc& desc, const DecodeParams& dp, int B) {
+    memset(np, 0, sizeof(*np));
+    np->cand = dp.cand;
+    np->cand_count = dp.cand_count;
+    np->flags = dp.flags;
+    np->B = B;
+    np->topk = desc.pre_nms_topk;
+    np->out_cap = desc.out_cap;
+    np->do_nms = desc.do_nms;
+    np->post_topk = desc.post_nms_topk;
+    np->do_postprocess = 1;
+    np->nms_thresh = desc.nms_thresh;
+}
+
+int Engine::launches_per_forward() const {
+    int n = 1 /*preprocess*/ + 5 /*decode*/ + 1 /*nms*/;
+    for (const Op& op : plan.ops) n += (op.type == Op::ESE) ? 3 : 1;
+    return n;
+}
+
+void Engine::forward(const void* d_images, int img_dtype, const float* d_K, const int32_t* d_sizes, Det* d_out,
+                     int32_t* d_counts, cudaStream_t stream) {
+    if (!plan.valid) fail(DD3D_ERR_STATE, "forward before plan");
+    const Plan& P = plan;
+    // sizes (h, w, out_h, out_w) -> the (h, w) pairs the preprocess kernel reads are its first two columns
+    cuda_check(launch_preprocess(d_images, img_dtype == DD3D_IMG_U8, d_sizes, 4, P.input.ptr, P.B, P.Hs, P.Ws, P.Hp, P.Wp,
+                                 desc.pixel_mean, desc.pixel_std, stream),
+               "preprocess");
+    for (const Op& op : P.ops) {
+        switch (op.type) {
+            case Op::CONV:
+                cuda_check(launch_conv(op.conv, num_sms, stream), "conv");
+                break;
+            case Op::STEM:
+                cuda_check(launch_stem_conv(op.in.ptr, op.stem->d_w, op.stem->epi.d_scale, op.stem->epi.d_bias,
+                                            op.out.ptr, P.B, op.in.H, op.in.W, op.ksize, op.stride, op.stem->cout,
+                                            op.out.pitch, stream),
+                           "stem conv");
+                break;
+            case Op::POOL:
+                cuda_check(launch_maxpool(op.in.ptr, op.out.ptr, P.B, op.in.H, op.in.W, op.in.C, op.in.pitch, op.out.H,
+                                          op.out.W, op.out.pitch, op.ksize, num_sms, stream),
+                           "maxpool");
+                break;
+            case Op::ESE:
+                cuda_check(launch_ese(op.in.ptr, op.in.pitch, op.ese->d_w, op.ese->d_b,
+                                      op.has_identity ? op.identity.ptr : nullptr, op.has_identity ? op.identity.pitch : 0,
+                                      op.out.ptr, op.out.pitch, op.f0, op.f1, P.B, op.in.H * op.in.W, op.in.C, num_sms,
+                                      stream),
+                           "eSE");
+                break;
+            case Op::RELU:
+                cuda_check(launch_relu(op.in.ptr, op.out.ptr, static_cast<size_t>(P.B) * op.in.H * op.in.W * op.in.C,
+                                       num_sms, stream),
+                           "relu");
+                break;
+        }
+    }
+    DecodeParams dp = P.decode;
+    dp.K = d_K;
+    cuda_check(launch_decode(dp, stream), "decode");
+    NmsParams np = P.nms;
+    np.do_postprocess = opt_do_postprocess;
+    np.do_nms = desc.do_nms;
+    np.sizes = d_sizes;
+    np.out = d_out;
+    np.out_count = d_counts;
+    cuda_check(launch_nms(np, stream), "nms");
+}
+
+void Engine::forward_host(const void* h_images, int img_dtype, const float* h_K, const int32_t* h_sizes, Det* h_out,
+                          int32_t* h_counts, cudaStream_t stream) {
+    if (!plan.valid) fail(DD3D_ERR_STATE, "forward before plan");
+    const Plan& P = plan;
+    const size_t img_bytes = static_cast<size_t>(P.B) * 3 * P.Hs * P.Ws * (img_dtype == DD3D_IMG_U8 ? 1 : 4);
+    cuda_check(cudaMemcpyAsync(P.d_images, h_images, img_bytes, cudaMemcpyHostToDevice, stream), "H2D images");
+    cuda_check(cudaMemcpyAsync(P.d_K, h_K, static_cast<size_t>(P.B) * 36, cudaMemcpyHostToDevice, stream), "H2D K");
+    cuda_check(cudaMemcpyAsync(P.d_sizes, h_sizes, static_cast<size_t>(P.B) * 16, cudaMemcpyHostToDevice, stream),
+               "H2D sizes");
+    forward(P.d_images, img_dtype, P.d_K, P.d_sizes, P.d_out, P.d_counts, stream);
+    cuda_check(cudaMemcpyAsync(h_out, P.d_out, static_cast<size_t>(P.B) * desc.out_cap * sizeof(Det),
+                               cudaMemcpyDeviceToHost, stream),
+               "D2H dets");
+    cuda_check(cudaMemcpyAsync(h_counts, P.d_counts, static_cast<size_t>(P.B) * 4, cudaMemcpyDeviceToHost, stream),
+               "D2H counts");
+    cuda_check(cudaStreamSynchronize(stream), "sync");
+}
+
+}  // namespace dd3d

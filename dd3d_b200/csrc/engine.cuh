@@ -1,0 +1,142 @@
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dd3d_b200.h"
+#include "conv_igemm.cuh"
+#include "detect.cuh"
+#include "small_kernels.cuh"
+
+namespace dd3d {
+
+struct EngineError {
+    int status;
+    std::string msg;
+    EngineError(int s, std::string m) : status(s), msg(std::move(m)) {}
+};
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+// NHWC bf16 activation view: C channels starting at ptr, `pitch` channels per pixel in the underlying buffer.
+struct View {
+    __nv_bfloat16* ptr = nullptr;
+    int B = 0, H = 0, W = 0, C = 0, pitch = 0;
+};
+
+struct ConvLayer {
+    int cin, cout, ksize, taps, kchunks, ktot, cout_pad, block_n, n_blocks;
+    __nv_bfloat16* d_w;
+    CUtensorMap w_map;
+};
+struct Epilogue {
+    float* d_scale;
+    float* d_bias;
+    float* d_lo;
+};
+struct StemLayer {
+    float* d_w;
+    int ksize, stride, cout;
+    Epilogue epi;
+};
+struct EseLayer {
+    float* d_w;
+    float* d_b;
+    int C;
+};
+
+struct Op {
+    enum Type { CONV, STEM, POOL, ESE, RELU } type;
+    ConvParams conv;
+    View in, out, identity;
+    bool has_identity = false;
+    int ksize = 0, stride = 0;
+    const StemLayer* stem = nullptr;
+    const EseLayer* ese = nullptr;
+    float* f0 = nullptr;
+    float* f1 = nullptr;
+};
+
+struct Plan {
+    bool valid = false;
+    int B = 0, Hs = 0, Ws = 0, Hp = 0, Wp = 0;
+    void* owned_workspace = nullptr;
+    View input;
+    View fpn[kLevels];
+    float* cls_map[kLevels] = {};
+    float* box_map[kLevels] = {};
+    float* b3d_map[kLevels] = {};
+    int lvl_h[kLevels] = {}, lvl_w[kLevels] = {};
+    int cls_pitch = 0, b3d_pitch = 0;
+    std::vector<Op> ops;
+    void* detect_scratch = nullptr;
+    float* d_K = nullptr;
+    int32_t* d_sizes = nullptr;
+    Det* d_out = nullptr;
+    int32_t* d_counts = nullptr;
+    void* d_images = nullptr;
+    const float* d_canon = nullptr;
+    DecodeParams decode;
+    NmsParams nms;
+};
+
+void fill_decode_params(DecodeParams* dp, const dd3d_model_desc& desc, int B, int cls_pitch, int b3d_pitch,
+                        const float* d_canon);
+void fill_nms_params(NmsParams* np, const dd3d_model_desc& desc, const DecodeParams& dp, int B);
+
+class Engine {
+   public:
+    explicit Engine(const dd3d_model_desc& d);
+    ~Engine();
+    void load_weight(const char* name, const float* data, const int64_t* shape, int ndim);
+    void finalize();
+    int size_divisibility() const;
+    size_t workspace_bytes(int B, int Hs, int Ws);
+    void make_plan(int B, int Hs, int Ws, void* workspace, size_t bytes);
+    void forward(const void* d_images, int img_dtype, const float* d_K, const int32_t* d_sizes, Det* d_out,
+                 int32_t* d_counts, cudaStream_t stream);
+    void forward_host(const void* h_images, int img_dtype, const float* h_K, const int32_t* h_sizes, Det* h_out,
+                      int32_t* h_counts, cudaStream_t stream);
+    int launches_per_forward() const;
+
+    // layer factories (cached by key)
+    const HostTensor& weight(const std::string& name) const;
+    const ConvLayer& conv_layer(const std::string& key, const std::vector<std::string>& wnames, int cin, int ksize);
+    void bn_fold(const std::string& bn_prefix, const std::string& conv_bias_name, int cout, std::vector<float>* scale,
+                 std::vector<float>* bias) const;
+    const Epilogue& epilogue(const std::string& key, const std::vector<float>& scale, const std::vector<float>& bias,
+                             const std::vector<float>* lo);
+    const Epilogue& bn_epilogue(const std::string& key, const std::string& bn_prefix, const std::string& conv_bias_name,
+                                int cout);
+    const StemLayer& stem_layer(const std::string& wname, const std::string& bn, int ksize, int stride);
+    const EseLayer& ese_layer(const std::string& fc, int C);
+
+    dd3d_model_desc desc;
+    int device = 0;
+    int num_sms = 148;
+    bool finalized = false;
+    int opt_do_postprocess = 1;
+    std::string err;
+    std::map<std::string, HostTensor> weights;
+    std::map<std::string, ConvLayer> convs;
+    std::map<std::string, Epilogue> epis;
+    std::map<std::string, StemLayer> stems;
+    std::map<std::string, EseLayer> eses;
+    std::vector<void*> device_allocs;
+    float* d_canon = nullptr;
+    Plan plan;
+
+   private:
+    void* dev_alloc(size_t bytes);
+    float* upload_f32(const std::vector<float>& v);
+    size_t build(Plan* P, int B, int Hs, int Ws, void* workspace, bool dry);
+    void release_plan();
+};
+
+}  // namespace dd3d

@@ -1,0 +1,356 @@
+// Bandwidth-bound kernels of the DD3D backbone (NHWC bf16, 128-bit vector accesses):
+//   preprocess   : (x - mean) / std, zero pad, NCHW -> NHWC(4)        reference core.py:61-72, image_list.py:93-158
+//   stem conv    : direct conv for the Cin=3 stems (DLA 7x7 s1, VoVNet 3x3 s2) + folded BN + ReLU
+//                                                                     reference dla.py:271-280, vovnet.py:302-306
+//   max-pool     : 2x2/s2 (DLA Tree.downsample, dla.py:224-225), 3x3/s2 ceil (VoVNet, vovnet.py:248-249)
+//   eSE          : global avg-pool -> fc -> hsigmoid -> channel scale (+identity)   vovnet.py:169-185,233-236
+//   relu         : p7 input (detectron2 LastLevelP6P7)
+#include "small_kernels.cuh"
+
+#include <cuda_bf16.h>
+#include <math.h>
+
+namespace dd3d {
+
+namespace {
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+
+// ------------------------------------------------------------------------------------------ preprocess
+template <typename T>
+__global__ void preprocess_kernel(const T* __restrict__ src, const int* __restrict__ sizes, __nv_bfloat16* __restrict__ dst,
+                                  int B, int Hs, int Ws, int Hp, int Wp, int size_stride, float m0, float m1, float m2,
+                                  float s0, float s1, float s2) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int b = blockIdx.z;
+    if (x >= Wp) return;
+    const int h = sizes[size_stride * b], w = sizes[size_stride * b + 1];
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (y < h && x < w) {
+        const size_t plane = static_cast<size_t>(Hs) * Ws;
+        const T* p = src + static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(y) * Ws + x;
+        v0 = (static_cast<float>(p[0]) - m0) / s0;
+        v1 = (static_cast<float>(p[plane]) - m1) / s1;
+        v2 = (static_cast<float>(p[2 * plane]) - m2) / s2;
+    }
+    uint2 o;
+    o.x = pack2(v0, v1);
+    o.y = pack2(v2, 0.f);
+    *reinterpret_cast<uint2*>(dst + (static_cast<size_t>(b * Hp + y) * Wp + x) * 4) = o;
+}
+
+// ------------------------------------------------------------------------------------------ stem conv
+// Each thread: 2 horizontally adjacent output pixels x 16 output channels; weights broadcast from smem.
+template <int KS, int STRIDE>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+                                                        const float* __restrict__ scale, const float* __restrict__ bias,
+                                                        __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo,
+                                                        int Cout, int out_pitch) {
+    constexpr int TY = 16, TX = 32, PAD = (KS - 1) / 2;
+    constexpr int PH = (TY - 1) * STRIDE + KS, PW = (TX - 1) * STRIDE + KS;
+    __shared__ uint2 patch[PH][PW];
+    __shared__ float4 wsm[KS * KS * 3][4];
+    const int groups = Cout / 16;
+    const int b = blockIdx.z / groups, cg = blockIdx.z - b * groups;
+    const int oy0 = blockIdx.y * TY, ox0 = blockIdx.x * TX;
+    const int tid = threadIdx.y * 16 + threadIdx.x;
+    const int iy0 = oy0 * STRIDE - PAD, ix0 = ox0 * STRIDE - PAD;
+    for (int i = tid; i < PH * PW; i += 256) {
+        const int py = i / PW, px = i - py * PW;
+        const int iy = iy0 + py, ix = ix0 + px;
+        uint2 v = make_uint2(0u, 0u);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+            v = *reinterpret_cast<const uint2*>(in + (static_cast<size_t>(b * H + iy) * W + ix) * 4);
+        patch[py][px] = v;
+    }
+    for (int i = tid; i < KS * KS * 3 * 4; i += 256) {
+        const int k = i >> 2, j = i & 3;
+        wsm[k][j] = *reinterpret_cast<const float4*>(w + static_cast<size_t>(k) * Cout + cg * 16 + j * 4);
+    }
+    __syncthreads();
+    float acc[2][16];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[p][c] = 0.f;
+    const int ly = threadIdx.y * STRIDE, lx = threadIdx.x * 2 * STRIDE;
+#pragma unroll 1
+    for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+            float xin[2][3];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const uint2 v = patch[ly + ky][lx + p * STRIDE + kx];
+                const float2 a = unpack2(v.x), c2 = unpack2(v.y);
+                xin[p][0] = a.x;
+                xin[p][1] = a.y;
+                xin[p][2] = c2.x;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int k = (ky * KS + kx) * 3 + c;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 wv = wsm[k][j];
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        acc[p][4 * j + 0] = fmaf(xin[p][c], wv.x, acc[p][4 * j + 0]);
+                        acc[p][4 * j + 1] = fmaf(xin[p][c], wv.y, acc[p][4 * j + 1]);
+                        acc[p][4 * j + 2] = fmaf(xin[p][c], wv.z, acc[p][4 * j + 2]);
+                        acc[p][4 * j + 3] = fmaf(xin[p][c], wv.w, acc[p][4 * j + 3]);
+                    }
+                }
+            }
+        }
+    }
+    const int oy = oy0 + threadIdx.y;
+    if (oy >= Ho) return;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int ox = ox0 + threadIdx.x * 2 + p;
+        if (ox >= Wo) continue;
+        uint32_t o[8];
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+            const int n = cg * 16 + c;
+            const float y0 = fmaxf(fmaf(acc[p][c], scale[n], bias[n]), 0.f);
+            const float y1 = fmaxf(fmaf(acc[p][c + 1], scale[n + 1], bias[n + 1]), 0.f);
+            o[c >> 1] = pack2(y0, y1);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b * Ho + oy) * Wo + ox) * out_pitch + cg * 16);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ max-pool
+__device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
+    uint4 r;
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+    return r;
+}
+
+__global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                               int C, int in_pitch, int Ho, int Wo, int out_pitch, int ksize) {
+    const int vc = C >> 3;
+    const size_t total = static_cast<size_t>(B) * Ho * Wo * vc;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(i % vc);
+        size_t pix = i / vc;
+        const int ox = static_cast<int>(pix % Wo);
+        pix /= Wo;
+        const int oy = static_cast<int>(pix % Ho);
+        const int b = static_cast<int>(pix / Ho);
+        uint4 m;
+        bool first = true;
+        for (int dy = 0; dy < ksize; ++dy) {
+            const int iy = oy * 2 + dy;
+            if (iy >= H) break;  // ceil_mode: windows are clipped to the input
+            for (int dx = 0; dx < ksize; ++dx) {
+                const int ix = ox * 2 + dx;
+                if (ix >= W) break;
+                const uint4 x = __ldg(reinterpret_cast<const uint4*>(
+                    in + (static_cast<size_t>(b * H + iy) * W + ix) * in_pitch + v * 8));
+                m = first ? x : max8(m, x);
+                first = false;
+            }
+        }
+        *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b * Ho + oy) * Wo + ox) * out_pitch + v * 8) = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ eSE
+// partial[b][split][c] = sum over the split's pixels (fixed order -> deterministic).
+__global__ void ese_pool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C,
+                                int pitch, int nsplit, int rows) {
+    extern __shared__ float red[];  // [rows][C]
+    const int vc = C >> 3;
+    const int b = blockIdx.y, split = blockIdx.x;
+    const int v = threadIdx.x % vc, r = threadIdx.x / vc;
+    const int per = (HW + nsplit - 1) / nsplit;
+    const int p0 = split * per, p1 = min(HW, p0 + per);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+        for (int p = p0 + r; p < p1; p += rows) {
+            const uint4 u =
+                __ldg(reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * HW + p) * pitch + v * 8));
+            const float2 a = unpack2(u.x), c = unpack2(u.y), d = unpack2(u.z), e = unpack2(u.w);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += c.x; acc[3] += c.y;
+            acc[4] += d.x; acc[5] += d.y; acc[6] += e.x; acc[7] += e.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[r * C + v * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int rr = 0; rr < rows; ++rr) s += red[rr * C + c];
+        partial[(static_cast<size_t>(b) * nsplit + split) * C + c] = s;
+    }
+}
+
+// gate[b][co] = relu6(W[co,:] . mean[b,:] + bias[co] + 3) / 6      (one warp per output channel)
+__global__ void ese_fc_kernel(const float* __restrict__ partial, const float* __restrict__ w, const float* __restrict__ bias,
+                              float* __restrict__ gate, int C, int nsplit, float inv_hw) {
+    extern __shared__ float mean[];  // [C]
+    const int b = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nsplit; ++k) s += partial[(static_cast<size_t>(b) * nsplit + k) * C + c];
+        mean[c] = s * inv_hw;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int co = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (co >= C) return;
+    float s = 0.f;
+    for (int ci = lane; ci < C; ci += 32) s = fmaf(w[static_cast<size_t>(co) * C + ci], mean[ci], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const float y = s + bias[co] + 3.0f;
+        gate[static_cast<size_t>(b) * C + co] = fminf(fmaxf(y, 0.f), 6.f) / 6.0f;
+    }
+}
+
+// out = bf16(x * gate[b][c] (+ identity))
+__global__ void ese_scale_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gate,
+                                 const __nv_bfloat16* __restrict__ identity, __nv_bfloat16* __restrict__ out, int B, int HW,
+                                 int C, int x_pitch, int id_pitch, int out_pitch) {
+    const int vc = C >> 3;
+    const size_t total = static_cast<size_t>(B) * HW * vc;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(i % vc);
+        const size_t pix = i / vc;
+        const int b = static_cast<int>(pix / HW);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pix * x_pitch + v * 8));
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * C + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * C + v * 8 + 4));
+        float f[8];
+        float2 t;
+        t = unpack2(u.x); f[0] = t.x * g0.x; f[1] = t.y * g0.y;
+        t = unpack2(u.y); f[2] = t.x * g0.z; f[3] = t.y * g0.w;
+        t = unpack2(u.z); f[4] = t.x * g1.x; f[5] = t.y * g1.y;
+        t = unpack2(u.w); f[6] = t.x * g1.z; f[7] = t.y * g1.w;
+        if (identity != nullptr) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(identity + pix * id_pitch + v * 8));
+            t = unpack2(q.x); f[0] += t.x; f[1] += t.y;
+            t = unpack2(q.y); f[2] += t.x; f[3] += t.y;
+            t = unpack2(q.z); f[4] += t.x; f[5] += t.y;
+            t = unpack2(q.w); f[6] += t.x; f[7] += t.y;
+        }
+        uint4 o;
+        o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(out + pix * out_pitch + v * 8) = o;
+    }
+}
+
+__global__ void relu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t nvec) {
+    const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + i);
+        __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = __hmax2(p[j], z);
+        reinterpret_cast<uint4*>(out)[i] = u;
+    }
+}
+
+inline int grid_for(size_t total, int block, int num_sms) {
+    size_t g = (total + block - 1) / block;
+    size_t cap = static_cast<size_t>(num_sms) * 8;
+    return static_cast<int>(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace
+
+cudaError_t launch_preprocess(const void* src, int src_is_u8, const int* d_sizes, int size_stride, __nv_bfloat16* dst,
+                              int B, int Hs, int Ws, int Hp, int Wp, const float mean[3], const float std[3],
+                              cudaStream_t stream) {
+    dim3 block(256), grid((Wp + 255) / 256, Hp, B);
+    if (src_is_u8) {
+        preprocess_kernel<uint8_t><<<grid, block, 0, stream>>>(static_cast<const uint8_t*>(src), d_sizes, dst, B, Hs,
+                                                               Ws, Hp, Wp, size_stride, mean[0], mean[1], mean[2], std[0],
+                                                               std[1], std[2]);
+    } else {
+        preprocess_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(src), d_sizes, dst, B, Hs, Ws,
+                                                             Hp, Wp, size_stride, mean[0], mean[1], mean[2], std[0], std[1],
+                                                             std[2]);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stem_conv(const __nv_bfloat16* in, const float* w, const float* scale, const float* bias,
+                             __nv_bfloat16* out, int B, int H, int W, int ksize, int stride, int Cout, int out_pitch,
+                             cudaStream_t stream) {
+    const int pad = (ksize - 1) / 2;
+    const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+    dim3 block(16, 16), grid((Wo + 31) / 32, (Ho + 15) / 16, B * (Cout / 16));
+    if (ksize == 7 && stride == 1) {
+        stem_conv_kernel<7, 1><<<grid, block, 0, stream>>>(in, w, scale, bias, out, H, W, Ho, Wo, Cout, out_pitch);
+    } else if (ksize == 3 && stride == 2) {
+        stem_conv_kernel<3, 2><<<grid, block, 0, stream>>>(in, w, scale, bias, out, H, W, Ho, Wo, Cout, out_pitch);
+    } else {
+        return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_maxpool(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, int in_pitch,
+                           int Ho, int Wo, int out_pitch, int ksize, int num_sms, cudaStream_t stream) {
+    const size_t total = static_cast<size_t>(B) * Ho * Wo * (C / 8);
+    maxpool_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, out, B, H, W, C, in_pitch, Ho, Wo, out_pitch,
+                                                                    ksize);
+    return cudaGetLastError();
+}
+
+int ese_nsplit(int HW) {
+    int n = HW / 512;
+    if (n < 1) n = 1;
+    if (n > 64) n = 64;
+    return n;
+}
+
+cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, const float* fc_b,
+                       const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out, int out_pitch, float* partial,
+                       float* gate, int B, int HW, int C, int num_sms, cudaStream_t stream) {
+    const int vc = C / 8;
+    int rows = 256 / vc;
+    if (rows < 1) rows = 1;
+    const int nsplit = ese_nsplit(HW);
+    ese_pool_kernel<<<dim3(nsplit, B), vc * rows, static_cast<size_t>(rows) * C * sizeof(float), stream>>>(
+        x, partial, HW, C, x_pitch, nsplit, rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ese_fc_kernel<<<dim3((C + 7) / 8, B), 256, C * sizeof(float), stream>>>(partial, fc_w, fc_b, gate, C, nsplit,
+                                                                          1.0f / static_cast<float>(HW));
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t total = static_cast<size_t>(B) * HW * vc;
+    ese_scale_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
+                                                                      id_pitch, out_pitch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_relu(const __nv_bfloat16* x, __nv_bfloat16* out, size_t n_elems, int num_sms, cudaStream_t stream) {
+    const size_t nvec = n_elems / 8;
+    relu_kernel<<<grid_for(nvec, 256, num_sms), 256, 0, stream>>>(x, out, nvec);
+    return cudaGetLastError();
+}
+
+}  // namespace dd3d

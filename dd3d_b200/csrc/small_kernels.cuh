@@ -1,0 +1,31 @@
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace dd3d {
+
+// images: [B][3][Hs][Ws] uint8 or fp32 (each image top-left aligned, valid size sizes[b] = (h, w));
+// dst: [B][Hp][Wp][4] bf16, zero outside the valid region (pad AFTER normalisation, image_list.py:124-148).
+cudaError_t launch_preprocess(const void* src, int src_is_u8, const int* d_sizes, int size_stride, __nv_bfloat16* dst,
+                              int B, int Hs, int Ws, int Hp, int Wp, const float mean[3], const float std[3],
+                              cudaStream_t stream);
+
+// in: [B][H][W][4] bf16; w: [ksize*ksize*3][Cout] fp32; out NHWC bf16 with `out_pitch` channels per pixel.
+cudaError_t launch_stem_conv(const __nv_bfloat16* in, const float* w, const float* scale, const float* bias,
+                             __nv_bfloat16* out, int B, int H, int W, int ksize, int stride, int Cout, int out_pitch,
+                             cudaStream_t stream);
+
+cudaError_t launch_maxpool(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, int in_pitch,
+                           int Ho, int Wo, int out_pitch, int ksize, int num_sms, cudaStream_t stream);
+
+int ese_nsplit(int HW);
+// partial: [B][ese_nsplit(HW)][C] fp32 scratch, gate: [B][C] fp32 scratch.
+cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, const float* fc_b,
+                       const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out, int out_pitch, float* partial,
+                       float* gate, int B, int HW, int C, int num_sms, cudaStream_t stream);
+
+cudaError_t launch_relu(const __nv_bfloat16* x, __nv_bfloat16* out, size_t n_elems, int num_sms, cudaStream_t stream);
+
+}  // namespace dd3d

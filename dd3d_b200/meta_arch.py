@@ -1,0 +1,278 @@
+"""DD3DB200 -- drop-in mirror of the reference meta-architecture for inference.
+
+Same constructor and call contract as ``tridet.modeling.dd3d.core.DD3D`` (core.py:18-164):
+``DD3DB200(cfg)``, ``.to(device)``, ``load_state_dict(reference_state_dict)``,
+``forward(batched_inputs: list[dict]) -> list[{"instances": Instances}]`` with the attributes callers toggle
+(``postprocess_in_inference``, ``do_nms``, ``only_box2d``, ``num_classes``, ``device``,
+``backbone.size_divisibility``).  All arithmetic runs in libdd3d_b200.so (hand-written sm_100a kernels) through the
+C ABI in include/dd3d_b200.h; torch is used for device memory and streams only.  No CPU fallback exists.
+"""
+import ctypes as C
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from . import lib as _lib
+from .arch import arch_of, param_specs, size_divisibility
+from .structures import Boxes, Boxes3D, Instances
+
+try:  # register next to the reference's DD3D when detectron2 is present (scripts/train.py:48 build_model)
+    from detectron2.modeling.meta_arch.build import META_ARCH_REGISTRY  # type: ignore
+except Exception:  # noqa: BLE001
+    META_ARCH_REGISTRY = None
+
+
+class DD3DB200(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.arch = arch_of(cfg)  # raises KeyError for an unknown FE.BUILDER like the reference registry
+        if not cfg.MODEL.BOX3D_ON:
+            raise NotImplementedError("DD3DB200 implements the BOX3D_ON configuration")
+        self.only_box2d = False
+        self.num_classes = cfg.DD3D.NUM_CLASSES
+        self.postprocess_in_inference = cfg.DD3D.INFERENCE.DO_POSTPROCESS
+        self.do_nms = cfg.DD3D.INFERENCE.DO_NMS
+        self.do_bev_nms = cfg.DD3D.INFERENCE.DO_BEV_NMS
+        self.bev_nms_iou_thresh = cfg.DD3D.INFERENCE.BEV_NMS_IOU_THRESH
+        self.backbone = SimpleNamespace(size_divisibility=size_divisibility(cfg))
+        self._specs = param_specs(cfg)
+        self._state = None  # reference-keyed fp32 CPU tensors
+        self._device = torch.device("cpu")
+        self._desc = _lib.desc_from_cfg(cfg)
+        self._handle = None
+        self._plan_key = None
+        self._host_bufs = None
+        self.training = False
+
+    # ------------------------------------------------------------------ nn.Module surface the callers use
+    @property
+    def device(self):
+        return self._device
+
+    def to(self, device=None, *args, **kwargs):  # noqa: D401 - mirrors nn.Module.to for the device move
+        if device is not None and not isinstance(device, torch.dtype):
+            self._device = torch.device(device)
+            if self._device.type == "cuda" and self._device.index is None:
+                self._device = torch.device("cuda", torch.cuda.current_device())
+        return self
+
+    def cuda(self, device=None):
+        return self.to("cuda" if device is None else device)
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("DD3DB200 is an inference engine; training uses the reference DD3D")
+        return self
+
+    def eval(self):
+        return self
+
+    def state_dict(self, *args, **kwargs):
+        if self._state is None:
+            return {k: torch.zeros(shape) for k, (shape, _) in self._specs.items()}
+        return dict(self._state)
+
+    def load_state_dict(self, state_dict, strict=True):
+        """Accepts the reference DD3D state_dict (fvcore Checkpointer: ``{"model": state_dict}`` unwrapped)."""
+        missing = [k for k in self._specs if k not in state_dict and not k.endswith("num_batches_tracked")]
+        unexpected = [k for k in state_dict if k not in self._specs]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict for DD3DB200: missing {missing[:5]}, "
+                               f"unexpected {unexpected[:5]}")
+        for k, (shape, _) in self._specs.items():
+            if k in state_dict and tuple(state_dict[k].shape) != tuple(shape):
+                raise RuntimeError(f"size mismatch for {k}: {tuple(state_dict[k].shape)} vs {tuple(shape)}")
+        self._state = {k: v.detach().to("cpu") for k, v in state_dict.items() if k in self._specs}
+        self._release()
+        return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
+
+    # ------------------------------------------------------------------ engine lifetime
+    def _release(self):
+        if self._handle is not None:
+            _lib.load().dd3d_destroy(self._handle)
+        self._handle = None
+        self._plan_key = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _engine(self):
+        if self._handle is not None:
+            return self._handle
+        if self._state is None:
+            raise RuntimeError("DD3DB200: load_state_dict() must be called before forward()")
+        if self._device.type != "cuda":
+            raise RuntimeError("DD3DB200 runs on CUDA sm_100a only (model.to('cuda')); there is no CPU path")
+        L = _lib.load()
+        # pixel mean/std travel in the state_dict like in the reference (core.py:54-55)
+        for i in range(3):
+            self._desc.pixel_mean[i] = float(self._state["pixel_mean"].reshape(-1)[i])
+            self._desc.pixel_std[i] = float(self._state["pixel_std"].reshape(-1)[i])
+        self._desc.do_nms = int(self.do_nms)
+        handle = C.c_void_p()
+        with torch.cuda.device(self._device):
+            _lib.check(L.dd3d_create(C.byref(self._desc), C.byref(handle)))
+            for name, t in self._state.items():
+                if not t.is_floating_point():
+                    continue
+                t = t.to(torch.float32).contiguous()
+                shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+                _lib.check(L.dd3d_load_weight(handle, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()), handle)
+            _lib.check(L.dd3d_finalize(handle), handle)
+        self._handle = handle
+        return handle
+
+    def _plan(self, B, Hs, Ws):
+        key = (B, Hs, Ws)
+        if self._plan_key != key:
+            L = _lib.load()
+            with torch.cuda.device(self._device):
+                _lib.check(L.dd3d_plan(self._engine(), B, Hs, Ws, None, 0), self._handle)
+            self._plan_key = key
+            self._host_bufs = None
+
+    # ------------------------------------------------------------------ forward
+    def _gather_inputs(self, batched_inputs, device):
+        images = [x["image"] for x in batched_inputs]
+        B = len(images)
+        sizes_hw = [(int(im.shape[-2]), int(im.shape[-1])) for im in images]
+        Hs, Ws = max(s[0] for s in sizes_hw), max(s[1] for s in sizes_hw)
+        is_u8 = all(im.dtype == torch.uint8 for im in images)
+        dtype = torch.uint8 if is_u8 else torch.float32
+        if all(s == (Hs, Ws) for s in sizes_hw):
+            batch = torch.stack([im.to(dtype) for im in images], 0)
+        else:
+            batch = torch.zeros((B, 3, Hs, Ws), dtype=dtype)
+            for i, im in enumerate(images):
+                batch[i, :, :im.shape[-2], :im.shape[-1]] = im.to(dtype)
+        if "intrinsics" not in batched_inputs[0]:
+            raise ValueError("DD3DB200 needs 'intrinsics' in every input (BOX3D_ON)")
+        K = torch.stack([x["intrinsics"].to(torch.float32) for x in batched_inputs], 0)
+        if torch.allclose(K[0].cpu(), torch.eye(3)):  # image_list.py:57-62
+            raise ValueError("Intrinsics is Identity.")
+        sizes = torch.empty((B, 4), dtype=torch.int32)
+        for i, (x, (h, w)) in enumerate(zip(batched_inputs, sizes_hw)):
+            if self.postprocess_in_inference:
+                oh, ow = int(x.get("height", h)), int(x.get("width", w))
+            else:
+                oh, ow = h, w
+            sizes[i] = torch.tensor([h, w, oh, ow], dtype=torch.int32)
+        return batch, K.reshape(B, 9).contiguous(), sizes, (B, Hs, Ws), is_u8
+
+    def _wrap(self, out, counts, K, sizes, device):
+        """[B][cap][24] fp32 words + counts -> list[{"instances": Instances}] (fields: fcos2d.py:331-335, fcos3d.py:398)."""
+        inv_K = torch.linalg.inv(K.reshape(-1, 3, 3).to(torch.float64)).to(torch.float32).to(device)
+        results = []
+        ints = out.view(torch.int32)
+        for b, n in enumerate(counts.tolist()):
+            d, di = out[b, :n], ints[b, :n]
+            h, w, oh, ow = sizes[b].tolist()
+            inst = Instances((oh, ow) if self.postprocess_in_inference else (h, w))
+            inst.pred_boxes = Boxes(d[:, 0:4].clone())
+            inst.scores = d[:, 4].clone()
+            inst.pred_classes = di[:, 6].to(torch.int64)
+            inst.locations = d[:, 18:20].clone()
+            inst.fpn_levels = di[:, 7].to(torch.int64)
+            inst.pred_boxes3d = Boxes3D(d[:, 8:12].clone(), d[:, 12:14].clone(), d[:, 14:15].clone(),
+                                        d[:, 15:18].clone(), inv_K[b][None].expand(n, 3, 3))
+            inst.scores_3d = d[:, 5].clone()
+            results.append({"instances": inst})
+        return results
+
+    @torch.no_grad()
+    def forward(self, batched_inputs):
+        """Device path: inputs are moved to the GPU with torch, one small D2H (per-image counts) at the end."""
+        if self.do_bev_nms:
+            raise NotImplementedError("BEV NMS (DD3D.INFERENCE.DO_BEV_NMS) is not implemented yet (SURVEY.md 8f)")
+        device = self._device
+        batch, K, sizes, shape, is_u8 = self._gather_inputs(batched_inputs, device)
+        self._plan(*shape)
+        L = _lib.load()
+        B = shape[0]
+        cap = self._desc.out_cap
+        with torch.cuda.device(device):
+            d_batch = batch.to(device, non_blocking=True)
+            d_K = K.to(device, non_blocking=True)
+            d_sizes = sizes.to(device, non_blocking=True)
+            out = torch.empty((B, cap, _lib.DET_WORDS), dtype=torch.float32, device=device)
+            counts = torch.empty((B, ), dtype=torch.int32, device=device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(L.dd3d_set_option(self._handle, b"do_postprocess", int(self.postprocess_in_inference)),
+                       self._handle)
+            _lib.check(L.dd3d_set_option(self._handle, b"do_nms", int(self.do_nms)), self._handle)
+            _lib.check(
+                L.dd3d_forward(self._handle, C.c_void_p(d_batch.data_ptr()), _lib.IMG_U8 if is_u8 else _lib.IMG_F32,
+                               C.c_void_p(d_K.data_ptr()), C.c_void_p(d_sizes.data_ptr()), C.c_void_p(out.data_ptr()),
+                               C.c_void_p(counts.data_ptr()), C.c_void_p(stream)), self._handle)
+            counts_h = counts.cpu()  # the only synchronisation
+        return self._wrap(out, counts_h, K, sizes, device)
+
+    __call__ = forward
+
+    @torch.no_grad()
+    def forward_host(self, batched_inputs):
+        """End-to-end path through HOST buffers: pinned staging -> dd3d_forward_host (H2D, kernels, D2H, sync)."""
+        batch, K, sizes, shape, is_u8 = self._gather_inputs(batched_inputs, self._device)
+        self._plan(*shape)
+        L = _lib.load()
+        B = shape[0]
+        cap = self._desc.out_cap
+        hb = self._host_bufs
+        if hb is None or hb["img"].shape != batch.shape or hb["img"].dtype != batch.dtype:
+            hb = dict(img=torch.empty_like(batch).pin_memory(), K=torch.empty_like(K).pin_memory(),
+                      sizes=torch.empty_like(sizes).pin_memory(),
+                      out=torch.empty((B, cap, _lib.DET_WORDS), dtype=torch.float32).pin_memory(),
+                      counts=torch.empty((B, ), dtype=torch.int32).pin_memory())
+            self._host_bufs = hb
+        hb["img"].copy_(batch)
+        hb["K"].copy_(K)
+        hb["sizes"].copy_(sizes)
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            _lib.check(L.dd3d_set_option(self._handle, b"do_postprocess", int(self.postprocess_in_inference)),
+                       self._handle)
+            _lib.check(
+                L.dd3d_forward_host(self._handle, C.c_void_p(hb["img"].data_ptr()),
+                                    _lib.IMG_U8 if is_u8 else _lib.IMG_F32, C.c_void_p(hb["K"].data_ptr()),
+                                    C.c_void_p(hb["sizes"].data_ptr()), C.c_void_p(hb["out"].data_ptr()),
+                                    C.c_void_p(hb["counts"].data_ptr()), C.c_void_p(stream)), self._handle)
+        return self._wrap(hb["out"], hb["counts"], K, sizes, torch.device("cpu"))
+
+    # ------------------------------------------------------------------ introspection (stage-level parity tests)
+    def get_tensor(self, name):
+        """Device tensor of an engine-internal map after a forward: 'p0'..'p4', 'cls0'.., 'box0'.., 'b3d0'.., 'input'."""
+        L = _lib.load()
+        ptr = C.c_void_p()
+        dims = (C.c_int32 * 6)()
+        _lib.check(L.dd3d_get_tensor(self._handle, name.encode(), C.byref(ptr), C.byref(dims)), self._handle)
+        B, H, W, Cc, pitch, eb = list(dims)
+        dtype = torch.bfloat16 if eb == 2 else torch.float32
+        # wrap device memory without copying through the CUDA array interface
+        t = torch.as_tensor(_DevArray(ptr.value, (B, H, W, pitch), "<f4" if eb == 4 else "<i2"), device=self._device)
+        if eb == 2:
+            t = t.view(torch.bfloat16)
+        return t[..., :Cc]
+
+    def launches_per_forward(self):
+        return _lib.load().dd3d_launches_per_forward(self._handle)
+
+    def overflow_flags(self):
+        flags = C.c_int32(0)
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        _lib.check(_lib.load().dd3d_overflow_flags(self._handle, C.c_void_p(stream), C.byref(flags)), self._handle)
+        return flags.value
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch can alias engine-owned device memory."""
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+if META_ARCH_REGISTRY is not None:  # pragma: no cover
+    META_ARCH_REGISTRY.register(DD3DB200)

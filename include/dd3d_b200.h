@@ -1,0 +1,155 @@
+/*
+ * dd3d_b200 -- C ABI of the B200-native DD3D inference path.
+ *
+ * Drop-in boundary for ONE reference call: the eval-mode DD3D.forward()
+ *   /root/reference/tridet/modeling/dd3d/core.py:64-164
+ * (backbone + FPN: feature_extractor/dla.py:346-355, vovnet.py:357-367, detectron2 FPN; heads: fcos2d.py:130-156,
+ * fcos3d.py:160-188; decode: fcos2d.py:270-344, fcos3d.py:328-399; NMS/top-k: fcos2d.py:346-367; rescale:
+ * detectron2 detector_postprocess, core.py:153-160).  The Python mirror of the meta-arch
+ * (dd3d_b200/meta_arch.py::DD3DB200) binds these symbols with ctypes and keeps the reference's
+ * forward(batched_inputs) -> [{"instances": Instances}] contract; see INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 on success or a negative dd3d_status; dd3d_last_error() gives the text.
+ * Pointers prefixed d_ are device pointers, h_ host pointers.  A handle is bound to the CUDA device that was
+ * current at dd3d_create and is not thread-safe.  There is no CPU fallback: without a CUDA device every entry
+ * point that needs one fails with DD3D_ERR_CUDA.
+ */
+#ifndef DD3D_B200_H_
+#define DD3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dd3d_engine* dd3d_handle;
+typedef void* dd3d_stream; /* cudaStream_t */
+
+enum dd3d_status {
+    DD3D_OK = 0,
+    DD3D_ERR_INVALID = -1,  /* bad argument / unknown weight name / shape mismatch */
+    DD3D_ERR_STATE = -2,    /* call order (e.g. forward before finalize) */
+    DD3D_ERR_CUDA = -3,     /* CUDA runtime / driver error */
+    DD3D_ERR_MISSING = -4   /* a weight the architecture needs was never loaded */
+};
+
+enum dd3d_arch { DD3D_ARCH_DLA34 = 0, DD3D_ARCH_V2_99 = 1 };
+enum dd3d_image_dtype { DD3D_IMG_U8 = 0, DD3D_IMG_F32 = 1 };
+
+#define DD3D_MAX_CLASSES 16
+#define DD3D_NUM_LEVELS 5
+
+/* Mirrors the cfg values DD3D.__init__ / FCOS2DInference / FCOS3DInference read
+ * (core.py:20-55, fcos2d.py:242-249, fcos3d.py:302-313; defaults configs/models/dd3d.yaml). */
+typedef struct dd3d_model_desc {
+    int32_t arch;        /* dd3d_arch: FE.BUILDER build_fcos_dla_fpn_backbone_p67 / build_fcos_vovnet_fpn_backbone_p6 */
+    int32_t num_classes; /* DD3D.NUM_CLASSES (<= DD3D_MAX_CLASSES) */
+    float pixel_mean[3]; /* MODEL.PIXEL_MEAN (BGR) */
+    float pixel_std[3];  /* MODEL.PIXEL_STD */
+    int32_t feature_locations_offset_half; /* DD3D.FEATURE_LOCATIONS_OFFSET == "half" */
+    float pre_nms_thresh;   /* FCOS2D.INFERENCE.PRE_NMS_THRESH (applied to sigmoid(cls)*sigmoid(ctr)) */
+    int32_t pre_nms_topk;   /* PRE_NMS_TOPK (<= 1638 so that 5 levels fit the NMS sort) */
+    int32_t post_nms_topk;  /* POST_NMS_TOPK */
+    float nms_thresh;       /* NMS_THRESH (<= 0 disables suppression) */
+    int32_t do_nms;         /* DD3D.INFERENCE.DO_NMS */
+    float min_depth, max_depth;             /* FCOS3D.MIN_DEPTH / MAX_DEPTH */
+    int32_t scale_depth_by_focal_lengths;   /* FCOS3D.SCALE_DEPTH_BY_FOCAL_LENGTHS */
+    float scale_depth_by_focal_lengths_factor;
+    int32_t predict_allocentric_rot;        /* FCOS3D.PREDICT_ALLOCENTRIC_ROT */
+    int32_t predict_distance;               /* FCOS3D.PREDICT_DISTANCE */
+    float canonical_box3d_sizes[DD3D_MAX_CLASSES * 3]; /* FCOS3D.CANONICAL_BOX3D_SIZES rows 0..num_classes-1 (W,L,H) */
+    int32_t out_cap;        /* detection slots per image in the output buffer (>= post_nms_topk; ties may exceed it) */
+} dd3d_model_desc;
+
+/* One detection = the fields the reference returns in Instances (fcos2d.py:331-335,263; fcos3d.py:398-399). */
+typedef struct dd3d_det {
+    float box[4];      /* pred_boxes (x1, y1, x2, y2) */
+    float score;       /* scores */
+    float score_3d;    /* scores_3d */
+    int32_t cls;       /* pred_classes */
+    int32_t level;     /* fpn_levels */
+    float quat[4];     /* pred_boxes3d.quat (w, x, y, z), egocentric */
+    float proj_ctr[2]; /* pred_boxes3d.proj_ctr */
+    float depth;       /* pred_boxes3d.depth */
+    float size[3];     /* pred_boxes3d.size (W, L, H) */
+    float loc[2];      /* locations */
+    int32_t index;     /* pixel * num_classes + class at its level */
+    int32_t pad[3];
+} dd3d_det;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+int dd3d_create(const dd3d_model_desc* h_desc, dd3d_handle* out);
+void dd3d_destroy(dd3d_handle h);
+const char* dd3d_last_error(dd3d_handle h); /* h may be NULL: error of the last failed dd3d_create */
+int dd3d_size_divisibility(dd3d_handle h);  /* backbone.size_divisibility: 128 (DLA p67) / 64 (V2-99 p6) */
+
+/* ---- weights: one call per tensor of the reference state_dict (Checkpointer.load, scripts/train.py:52) ----- */
+/* h_data: host fp32, contiguous, `ndim` dims in h_shape.  Unknown names are ignored (return DD3D_OK, e.g.
+ * num_batches_tracked); known names with a wrong shape return DD3D_ERR_INVALID. */
+int dd3d_load_weight(dd3d_handle h, const char* h_name, const float* h_data, const int64_t* h_shape, int ndim);
+/* Folds BN / Scale / Offset into per-channel epilogue vectors, repacks conv weights to bf16 [Cout][tap][Cin]
+ * and uploads them.  DD3D_ERR_MISSING names the first absent tensor. */
+int dd3d_finalize(dd3d_handle h);
+
+/* ---- planning: buffers + TMA descriptors for one (batch, source height, source width) --------------------- */
+/* Hs, Ws: height/width of the source batch tensor [B][3][Hs][Ws]; the padded size is rounded up to the size
+ * divisibility.  Returns the workspace bytes the plan needs. */
+int64_t dd3d_workspace_bytes(dd3d_handle h, int B, int Hs, int Ws);
+/* d_workspace may be NULL: the engine then allocates (and owns) the workspace. */
+int dd3d_plan(dd3d_handle h, int B, int Hs, int Ws, void* d_workspace, int64_t workspace_bytes);
+
+/* ---- the hot path ---------------------------------------------------------------------------------------- */
+/* d_images: [B][3][Hs][Ws] (dd3d_image_dtype), image b valid in its top-left (h_b, w_b) corner.
+ * d_intrinsics: [B][9] fp32 row-major K.  d_sizes: [B][4] int32 = (h_b, w_b, out_h, out_w): valid image size and
+ * the size boxes are rescaled to (input["height"/"width"], core.py:156-158).
+ * d_out: [B][out_cap] dd3d_det, d_counts: [B] int32.  Enqueues on `stream`; no host sync, no allocation. */
+int dd3d_forward(dd3d_handle h, const void* d_images, int img_dtype, const float* d_intrinsics,
+                 const int32_t* d_sizes, dd3d_det* d_out, int32_t* d_counts, dd3d_stream stream);
+/* Same through HOST buffers (pinned recommended): copies inputs H2D, runs, copies detections and counts D2H,
+ * then synchronises `stream`. */
+int dd3d_forward_host(dd3d_handle h, const void* h_images, int img_dtype, const float* h_intrinsics,
+                      const int32_t* h_sizes, dd3d_det* h_out, int32_t* h_counts, dd3d_stream stream);
+/* bit 0: more candidates tied at the k-th pre-NMS score than the boundary buffer holds; bit 1: more than
+ * out_cap detections survived.  Reads a device word (synchronises `stream`). */
+int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags);
+/* Runtime switches the reference's callers toggle on the meta-arch: "do_postprocess" (postprocess_in_inference,
+ * scripts/train.py:206-209, test_time_augmentation.py:107) and "do_nms" (core.py:134). */
+int dd3d_set_option(dd3d_handle h, const char* name, int value);
+/* Number of kernel launches one dd3d_forward enqueues (for the bench's gpu_launches claim). */
+int dd3d_launches_per_forward(dd3d_handle h);
+
+/* ---- introspection for stage-level parity tests ---------------------------------------------------------- */
+/* name: "p0".."p4" (FPN outputs, bf16 NHWC), "cls0".."cls4", "box0".."box4", "b3d0".."b3d4" (fp32 NHWC head maps),
+ * "input" (bf16 [B][Hp][Wp][4]).  Returns the device pointer and fills dims = {B, H, W, C, pitch, elem_bytes}. */
+int dd3d_get_tensor(dd3d_handle h, const char* name, void** d_ptr, int32_t dims[6]);
+
+/* ---- single operators (same kernels the engine launches; used by the kernel-level parity tests) ----------- */
+/* NHWC bf16 conv via the tcgen05 implicit-GEMM kernel.  d_w: bf16 [cout_pad][ksize*ksize][cin_pad64];
+ * d_scale/d_bias: fp32 [cout_pad]; d_residual (optional) NHWC bf16 with res_pitch channels, res_up2: residual is
+ * the 2x coarser map; out: bf16 (out_f32 == 0, pitch out_pitch) or fp32. */
+int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch, const void* d_w, int cout, int ksize,
+                   int stride, const float* d_scale, const float* d_bias, int relu, const void* d_residual,
+                   int res_pitch, int res_up2, void* d_out, int out_pitch, int out_f32, dd3d_stream stream);
+int dd3d_op_stem_conv(const void* d_in4, const float* d_w, const float* d_scale, const float* d_bias, void* d_out,
+                      int B, int H, int W, int ksize, int stride, int cout, int out_pitch, dd3d_stream stream);
+int dd3d_op_preprocess(const void* d_images, int img_dtype, const int32_t* d_sizes2, void* d_out4, int B, int Hs, int Ws,
+                       int Hp, int Wp, const float* h_mean, const float* h_std, dd3d_stream stream);
+int dd3d_op_maxpool(const void* d_in, void* d_out, int B, int H, int W, int C, int in_pitch, int out_pitch, int ksize,
+                    dd3d_stream stream);
+int dd3d_op_ese(const void* d_x, int x_pitch, const float* d_fc_w, const float* d_fc_b, const void* d_identity,
+                int id_pitch, void* d_out, int out_pitch, float* d_scratch, int B, int HW, int C, dd3d_stream stream);
+int64_t dd3d_op_ese_scratch_bytes(int B, int HW, int C);
+/* decode + NMS on caller-provided head maps (layout documented in csrc/detect.cuh). */
+int64_t dd3d_op_detect_scratch_bytes(int B, int pre_nms_topk);
+int dd3d_op_detect(const dd3d_model_desc* h_desc, int B, const int32_t* h_level_hw /*[5][2]*/,
+                   const int32_t* h_strides /*[5]*/, const float* const* d_cls /*[5]*/, const float* const* d_box,
+                   const float* const* d_b3d, int cls_pitch, int b3d_pitch, const float* d_intrinsics,
+                   const int32_t* d_sizes, void* d_scratch, dd3d_det* d_pre_nms /* [B][5*topk] or NULL */,
+                   int32_t* d_pre_counts /* [B][5] or NULL */, dd3d_det* d_out, int32_t* d_counts, dd3d_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DD3D_B200_H_ */
