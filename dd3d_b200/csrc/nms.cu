@@ -276,11 +276,15 @@ cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream) {
     if (cap > kMaxCand || p.B <= 0) return cudaErrorInvalidValue;
     const size_t smem = static_cast<size_t>(kMaxCand) * 8 + static_cast<size_t>(cap) * 16 +
                         static_cast<size_t>(cap) * 8 + static_cast<size_t>(kMaxCand) * 2 + static_cast<size_t>(cap) * 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+    static size_t attr_smem = 0;  // the limit is 227 KiB minus the kernel's static shared memory: ask for what we use
+    if (smem > attr_smem) {
+        cudaError_t e =
+            cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return e;
+        }
+        attr_smem = smem;
     }
     nms_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);
     return cudaGetLastError();

@@ -1,0 +1,167 @@
+"""End-to-end parity (-m gpu): DD3DB200.forward (C ABI -> sm_100a kernels) vs the CPU oracle on identical inputs.
+
+Tolerances (see DESIGN.md "Numerics"): the engine stores activations in bf16, so it is compared
+  (a) tightly with the oracle run in bf16-storage emulation (same rounding points; differences come only from
+      fp32 accumulation order -> isolated 1-ulp bf16 flips): relative L2 error of every FPN / head map <= 1e-2 and
+      matched detections within 2e-2 (boxes relative to box size, scores absolute);
+  (b) loosely with the committed fp32 golden vectors of the REAL reference: >= 60 % of the reference detections
+      are reproduced (same level, location, class) with boxes within 10 % of the box size.
+The fp32 decode / NMS kernels themselves are held to <= 1e-4 in tests/test_kernels_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+from dd3d_b200.config import get_cfg
+from dd3d_b200.meta_arch import DD3DB200
+from dd3d_b200.synthetic import make_inputs, make_state_dict
+from oracle.dd3d_oracle import DD3DOracle  # checker only
+from oracle.gen_golden import CASES, case_inputs
+from util import det_key, match_by_key, quat_dist
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp(min=1e-12)).item()
+
+
+def _model(arch):
+    cfg = get_cfg(arch, CASES[arch][0])
+    sd = make_state_dict(cfg)
+    m = DD3DB200(cfg).to("cuda")
+    m.load_state_dict(sd)
+    return cfg, sd, m
+
+
+def _keys_inst(inst):
+    return [det_key(l, p, c) for l, p, c in zip(inst.fpn_levels.cpu(), inst.locations.cpu(), inst.pred_classes.cpu())]
+
+
+@pytest.mark.parametrize("arch", ["dla34", "v2_99"])
+def test_forward_vs_emulating_oracle(arch):
+    cfg, sd, model = _model(arch)
+    inputs = case_inputs(arch)
+    out = model(inputs)
+    torch.cuda.synchronize()
+    assert model.overflow_flags() == 0
+    ref, inter = DD3DOracle(cfg, sd, emulate_bf16=True).forward(inputs, return_intermediates=True)
+    C = cfg.DD3D.NUM_CLASSES
+    # ---- stage level: preprocessed input (bit exact), FPN outputs, head maps
+    x = model.get_tensor("input")[..., :3].float().cpu().permute(0, 3, 1, 2)
+    assert torch.equal(x, inter["batch"])
+    for l in range(5):
+        f = model.get_tensor(f"p{l}").float().cpu().permute(0, 3, 1, 2)
+        e = _rel_l2(f, inter["features"][l])
+        assert e < 1e-2, f"FPN level {l}: rel L2 {e}"
+        cls = model.get_tensor(f"cls{l}").cpu().permute(0, 3, 1, 2)
+        box = model.get_tensor(f"box{l}").cpu().permute(0, 3, 1, 2)
+        b3d = model.get_tensor(f"b3d{l}").cpu().permute(0, 3, 1, 2)
+        m = inter["maps"]
+        ref3d = torch.cat([m["quat"][l], m["ctr"][l], m["depth"][l], m["size"][l], m["conf"][l]], 1)
+        for name, got, want in (("cls", cls, m["logits"][l]), ("reg", box[:, :4], m["box2d_reg"][l]),
+                                ("ctr", box[:, 4:5], m["centerness"][l]), ("b3d", b3d, ref3d)):
+            e = _rel_l2(got, want)
+            assert e < 1.5e-2, f"{name} level {l}: rel L2 {e}"
+    # ---- detections
+    for b, (o, r) in enumerate(zip(out, ref)):
+        inst = o["instances"]
+        kr = [det_key(l, p, c) for l, p, c in zip(r["level"], r["loc"], r["cls"])]
+        ia, ib = match_by_key(_keys_inst(inst), kr)
+        assert len(ib) >= 0.8 * len(kr), f"image {b}: matched {len(ib)} of {len(kr)}"
+        if len(ia) == 0:
+            continue
+        gb, rb = inst.pred_boxes.tensor.cpu()[ia], r["box2d"][ib]
+        size = torch.stack([rb[:, 2] - rb[:, 0], rb[:, 3] - rb[:, 1]], 1).clamp(min=1.0).repeat(1, 2)
+        assert ((gb - rb).abs() / size).max() < 2e-2
+        assert (inst.scores_3d.cpu()[ia] - r["score3d"][ib]).abs().max() < 2e-2
+        assert (inst.scores.cpu()[ia] - r["score"][ib]).abs().max() < 2e-2
+        b3 = inst.pred_boxes3d
+        assert quat_dist(b3.quat.cpu()[ia], r["quat"][ib]).max() < 3e-2
+        assert ((b3.size.cpu()[ia] - r["size"][ib]).abs() / r["size"][ib]).max() < 3e-2
+        assert ((b3.depth.cpu()[ia, 0] - r["depth"][ib]).abs() / r["depth"][ib]).max() < 3e-2
+        assert (b3.tvec.cpu()[ia] - r["tvec"][ib]).abs().max() < 0.05 * r["tvec"][ib].abs().max()
+
+
+@pytest.mark.parametrize("arch", ["dla34", "v2_99"])
+def test_forward_vs_reference_golden(arch):
+    g = np.load(os.path.join(GOLDEN_DIR, f"golden_{arch}.npz"))
+    _, _, model = _model(arch)
+    out = model(case_inputs(arch))
+    for b, o in enumerate(out):
+        inst = o["instances"]
+        assert tuple(inst.image_size) == tuple(g[f"image_size{b}"].tolist())
+        kg = [det_key(l, p, c) for l, p, c in zip(g[f"levels{b}"], g[f"locations{b}"], g[f"classes{b}"])]
+        ia, ib = match_by_key(_keys_inst(inst), kg)
+        assert len(ib) >= 0.6 * len(kg), f"image {b}: matched {len(ib)} of {len(kg)}"
+        gb, rb = inst.pred_boxes.tensor.cpu()[ia], torch.tensor(g[f"boxes{b}"])[ib]
+        size = torch.stack([rb[:, 2] - rb[:, 0], rb[:, 3] - rb[:, 1]], 1).clamp(min=1.0).repeat(1, 2)
+        assert ((gb - rb).abs() / size).max() < 0.1
+
+
+def test_host_path_equals_device_path_and_is_deterministic():
+    _, _, model = _model("dla34")
+    inputs = case_inputs("dla34")
+    a = model(inputs)
+    b = model.forward_host(inputs)
+    c = model(inputs)
+    for x, y, z in zip(a, b, c):
+        ix, iy, iz = x["instances"], y["instances"], z["instances"]
+        assert len(ix) == len(iy) == len(iz)
+        assert torch.equal(ix.pred_boxes.tensor.cpu(), iy.pred_boxes.tensor.cpu())
+        assert torch.equal(ix.pred_boxes.tensor.cpu(), iz.pred_boxes.tensor.cpu())
+        assert torch.equal(ix.scores_3d.cpu(), iy.scores_3d.cpu())
+        assert torch.equal(ix.pred_boxes3d.quat.cpu(), iz.pred_boxes3d.quat.cpu())
+
+
+def test_postprocess_toggle_and_no_nms():
+    cfg, sd, model = _model("dla34")
+    inputs = case_inputs("dla34")
+    full = model(inputs)
+    model.postprocess_in_inference = False
+    raw = model(inputs)
+    # image 1 is rescaled x2 by postprocess: raw boxes * 2 (then clipped) == processed boxes for surviving detections
+    assert tuple(raw[1]["instances"].image_size) == (171, 286)
+    n = min(len(raw[1]["instances"]), len(full[1]["instances"]))
+    if n and len(raw[1]["instances"]) == len(full[1]["instances"]):
+        rb = raw[1]["instances"].pred_boxes.tensor * 2
+        rb[:, 0::2].clamp_(0, 572)
+        rb[:, 1::2].clamp_(0, 342)
+        assert torch.allclose(rb, full[1]["instances"].pred_boxes.tensor, atol=1e-3)
+    cfg2 = get_cfg("dla34", "kitti_3d")  # out_cap is sized for the no-NMS case at construction
+    cfg2.DD3D.INFERENCE.DO_NMS = False
+    model2 = DD3DB200(cfg2).to("cuda")
+    model2.load_state_dict(sd)
+    allc = model2(inputs)
+    assert len(allc[0]["instances"]) >= len(full[0]["instances"])
+
+
+def test_full_size_properties_v2_99():
+    """BASELINE shape (900x1600 -> 960x1600), size-independent properties: batch independence (image i of a batch ==
+    the same image alone, bit for bit), determinism, sortedness by scores_3d, <= POST_NMS_TOPK (+ties), boxes clipped."""
+    cfg, sd, model = _model("v2_99")
+    inputs = make_inputs(2, 900, 1600, 1266.4)
+    both = model(inputs)
+    again = model(inputs)
+    single = model(inputs[1:])
+    assert model.overflow_flags() == 0
+    for x, y in zip(both, again):
+        assert torch.equal(x["instances"].pred_boxes.tensor, y["instances"].pred_boxes.tensor)
+    a, s = both[1]["instances"], single[0]["instances"]
+    assert len(a) == len(s)
+    assert torch.equal(a.pred_boxes.tensor, s.pred_boxes.tensor) and torch.equal(a.scores_3d, s.scores_3d)
+    for o in both:
+        inst = o["instances"]
+        assert 0 < len(inst) <= 128
+        s3 = inst.scores_3d
+        assert (s3[:-1] >= s3[1:]).all()
+        bx = inst.pred_boxes.tensor
+        assert (bx[:, 0] >= 0).all() and (bx[:, 2] <= 1600).all() and (bx[:, 1] >= 0).all() and (bx[:, 3] <= 900).all()
+        assert ((bx[:, 2] - bx[:, 0]) > 0).all() and ((bx[:, 3] - bx[:, 1]) > 0).all()
+        q = inst.pred_boxes3d.quat
+        assert (q.norm(dim=1) - 1).abs().max() < 1e-3
+        d = inst.pred_boxes3d.depth
+        assert (d >= 0.1).all() and (d <= 80.0).all()
