@@ -130,6 +130,8 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value) {
             e.opt_do_postprocess = value ? 1 : 0;
         } else if (n == "do_nms") {
             e.desc.do_nms = value ? 1 : 0;
+        } else if (n == "profile") {
+            e.opt_profile = value ? 1 : 0;
         } else {
             throw EngineError(DD3D_ERR_INVALID, "unknown option: " + n);
         }
@@ -140,6 +142,11 @@ int dd3d_launches_per_forward(dd3d_handle h) {
     int n = 0;
     int st = guarded(h, [&](Engine& e) { n = e.launches_per_forward(); });
     return st == DD3D_OK ? n : st;
+}
+
+int dd3d_get_profile(dd3d_handle h, double* h_ms, double* h_flops, double* h_bytes, int32_t* h_launches) {
+    if (!h_ms || !h_flops || !h_bytes || !h_launches) return DD3D_ERR_INVALID;
+    return guarded(h, [&](Engine& e) { e.get_profile(h_ms, h_flops, h_bytes, h_launches); });
 }
 
 int dd3d_get_tensor(dd3d_handle h, const char* name, void** d_ptr, int32_t dims[6]) {

@@ -298,6 +298,8 @@ struct Builder {
             }
         }
         conv_finalize_params(&p);
+        for (int s = 0; s < p.nseg; ++s)
+            op.flops += 2.0 * B * p.seg[s].H * p.seg[s].W * static_cast<double>(L.cout) * L.cin * L.taps;
         P->ops.push_back(op);
     }
 
@@ -835,10 +837,24 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
                      int32_t* d_counts, cudaStream_t stream) {
     if (!plan.valid) fail(DD3D_ERR_STATE, "forward before plan");
     const Plan& P = plan;
+    size_t ev_i = 0;
+    auto mark = [&](int cat) {  // opt_profile: CUDA events on the launch stream around every op
+        if (!opt_profile) return;
+        if (ev_i >= prof_ev.size()) {
+            cudaEvent_t e;
+            cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+            prof_ev.push_back(e);
+            prof_cat.push_back(cat);
+        }
+        prof_cat[ev_i] = cat;
+        cuda_check(cudaEventRecord(prof_ev[ev_i++], stream), "cudaEventRecord");
+    };
+    mark(-1);
     // sizes (h, w, out_h, out_w) -> the (h, w) pairs the preprocess kernel reads are its first two columns
     cuda_check(launch_preprocess(d_images, img_dtype == DD3D_IMG_U8, d_sizes, 4, P.input.ptr, P.B, P.Hs, P.Ws, P.Hp, P.Wp,
                                  desc.pixel_mean, desc.pixel_std, stream),
                "preprocess");
+    mark(0);
     for (const Op& op : P.ops) {
         switch (op.type) {
             case Op::CONV:
@@ -868,10 +884,12 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
                            "relu");
                 break;
         }
+        mark(op.type == Op::STEM ? 1 : op.type == Op::CONV ? 2 : op.type == Op::POOL ? 3 : op.type == Op::ESE ? 4 : 5);
     }
     DecodeParams dp = P.decode;
     dp.K = d_K;
     cuda_check(launch_decode(dp, stream), "decode");
+    mark(6);
     NmsParams np = P.nms;
     np.do_postprocess = opt_do_postprocess;
     np.do_nms = desc.do_nms;
@@ -879,6 +897,55 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
     np.out = d_out;
     np.out_count = d_counts;
     cuda_check(launch_nms(np, stream), "nms");
+    mark(7);
+    if (opt_profile) prof_used = ev_i;
+}
+
+void Engine::get_profile(double* ms, double* flops, double* bytes, int32_t* launches) {
+    if (!plan.valid) fail(DD3D_ERR_STATE, "no plan");
+    for (int c = 0; c < 8; ++c) ms[c] = flops[c] = bytes[c] = 0.0, launches[c] = 0;
+    if (prof_used >= 2) {
+        cuda_check(cudaEventSynchronize(prof_ev[prof_used - 1]), "cudaEventSynchronize");
+        for (size_t i = 1; i < prof_used; ++i) {
+            float t = 0.f;
+            cuda_check(cudaEventElapsedTime(&t, prof_ev[i - 1], prof_ev[i]), "cudaEventElapsedTime");
+            ms[prof_cat[i]] += t;
+        }
+    }
+    const Plan& P = plan;
+    const double C = desc.num_classes;
+    launches[0] = 1;
+    bytes[0] = static_cast<double>(P.B) * 3 * P.Hs * P.Ws + static_cast<double>(P.B) * P.Hp * P.Wp * 8;
+    for (const Op& op : P.ops) {
+        const double in_px = static_cast<double>(P.B) * op.in.H * op.in.W, out_px = static_cast<double>(P.B) * op.out.H * op.out.W;
+        switch (op.type) {
+            case Op::STEM:
+                launches[1] += 1;
+                flops[1] += 2.0 * out_px * op.stem->cout * 3 * op.ksize * op.ksize;
+                bytes[1] += in_px * 8 + out_px * op.stem->cout * 2;
+                break;
+            case Op::CONV:
+                launches[2] += 1;
+                flops[2] += op.flops;
+                break;
+            case Op::POOL:
+                launches[3] += 1;
+                bytes[3] += (in_px + out_px) * op.in.C * 2;
+                break;
+            case Op::ESE:
+                launches[4] += 3;
+                bytes[4] += in_px * op.in.C * 2 * (op.has_identity ? 4 : 3);
+                break;
+            case Op::RELU:
+                launches[5] += 1;
+                bytes[5] += in_px * op.in.C * 4;
+                break;
+        }
+    }
+    launches[6] = 5;
+    launches[7] = 1;
+    for (int l = 0; l < kLevels; ++l)  // two dense passes over the fp32 logits + centerness
+        bytes[6] += 2.0 * P.B * P.lvl_h[l] * P.lvl_w[l] * (C + 1) * 4;
 }
 
 void Engine::forward_host(const void* h_images, int img_dtype, const float* h_K, const int32_t* h_sizes, Det* h_out,

@@ -61,6 +61,8 @@ struct Op {
     const EseLayer* ese = nullptr;
     float* f0 = nullptr;
     float* f1 = nullptr;
+    double flops = 0.0;  // algorithmic FLOPs (2*MACs over the real, unpadded channels)
+    double bytes = 0.0;  // algorithmic HBM bytes for the bandwidth-bound ops
 };
 
 struct Plan {
@@ -104,6 +106,8 @@ class Engine {
     void forward_host(const void* h_images, int img_dtype, const float* h_K, const int32_t* h_sizes, Det* h_out,
                       int32_t* h_counts, cudaStream_t stream);
     int launches_per_forward() const;
+    // categories: 0 preprocess, 1 stem, 2 conv (tcgen05), 3 pool, 4 eSE, 5 relu, 6 decode, 7 nms
+    void get_profile(double* ms, double* flops, double* bytes, int32_t* launches);
 
     // layer factories (cached by key)
     const HostTensor& weight(const std::string& name) const;
@@ -122,6 +126,10 @@ class Engine {
     int num_sms = 148;
     bool finalized = false;
     int opt_do_postprocess = 1;
+    int opt_profile = 0;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_cat;
+    size_t prof_used = 0;
     std::string err;
     std::map<std::string, HostTensor> weights;
     std::map<std::string, ConvLayer> convs;

@@ -258,6 +258,19 @@ class DD3DB200(nn.Module):
             t = t.view(torch.bfloat16)
         return t[..., :Cc]
 
+    PROFILE_CATEGORIES = ("preprocess", "stem_conv", "conv_igemm", "maxpool", "ese", "relu", "decode", "nms")
+
+    def set_profile(self, on):
+        """Record CUDA events around every engine op of the following forwards (dd3d_get_profile)."""
+        _lib.check(_lib.load().dd3d_set_option(self._engine(), b"profile", int(on)), self._handle)
+
+    def get_profile(self):
+        """{category: {ms, flops, bytes, launches}} of the last profiled forward."""
+        ms, fl, by = (C.c_double * 8)(), (C.c_double * 8)(), (C.c_double * 8)()
+        ln = (C.c_int32 * 8)()
+        _lib.check(_lib.load().dd3d_get_profile(self._handle, ms, fl, by, ln), self._handle)
+        return {n: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=ln[i]) for i, n in enumerate(self.PROFILE_CATEGORIES)}
+
     def launches_per_forward(self):
         return _lib.load().dd3d_launches_per_forward(self._handle)
 

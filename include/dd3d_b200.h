@@ -115,10 +115,17 @@ int dd3d_forward_host(dd3d_handle h, const void* h_images, int img_dtype, const 
  * out_cap detections survived.  Reads a device word (synchronises `stream`). */
 int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags);
 /* Runtime switches the reference's callers toggle on the meta-arch: "do_postprocess" (postprocess_in_inference,
- * scripts/train.py:206-209, test_time_augmentation.py:107) and "do_nms" (core.py:134). */
+ * scripts/train.py:206-209, test_time_augmentation.py:107), "do_nms" (core.py:134), and "profile" (see
+ * dd3d_get_profile). */
 int dd3d_set_option(dd3d_handle h, const char* name, int value);
 /* Number of kernel launches one dd3d_forward enqueues (for the bench's gpu_launches claim). */
 int dd3d_launches_per_forward(dd3d_handle h);
+
+/* Per-category device time of the LAST dd3d_forward issued with option "profile" = 1 (CUDA events recorded on the
+ * launch stream around every op), with the algorithmic FLOPs / HBM bytes and launch counts of one forward.
+ * Categories (arrays of 8): 0 preprocess, 1 stem conv, 2 tcgen05 implicit-GEMM conv, 3 max-pool, 4 eSE, 5 relu,
+ * 6 decode, 7 NMS. */
+int dd3d_get_profile(dd3d_handle h, double* h_ms, double* h_flops, double* h_bytes, int32_t* h_launches);
 
 /* ---- introspection for stage-level parity tests ---------------------------------------------------------- */
 /* name: "p0".."p4" (FPN outputs, bf16 NHWC), "cls0".."cls4", "box0".."box4", "b3d0".."b3d4" (fp32 NHWC head maps),
