@@ -149,6 +149,13 @@ int dd3d_get_profile(dd3d_handle h, double* h_ms, double* h_flops, double* h_byt
     return guarded(h, [&](Engine& e) { e.get_profile(h_ms, h_flops, h_bytes, h_launches); });
 }
 
+int dd3d_get_op_times(dd3d_handle h, float* h_ms, int32_t* h_cats, double* h_flops, int max_ops) {
+    if (!h_ms || !h_cats || !h_flops || max_ops < 1) return DD3D_ERR_INVALID;
+    int n = 0;
+    int st = guarded(h, [&](Engine& e) { n = e.get_op_times(h_ms, h_cats, h_flops, max_ops); });
+    return st == DD3D_OK ? n : st;
+}
+
 int dd3d_get_tensor(dd3d_handle h, const char* name, void** d_ptr, int32_t dims[6]) {
     return guarded(h, [&](Engine& e) {
         if (!e.plan.valid) throw EngineError(DD3D_ERR_STATE, "no plan");
@@ -220,7 +227,12 @@ int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch,
     g.W = Wo;
     choose_tile(Ho, Wo, &g.th, &g.tw);
     bool ok = make_weight_map(&p.w_map, d_w, taps * kchunks * kBlockK, cout_pad, block_n);
-    if (stride == 1) {
+    p.halo = conv_prefer_halo(taps, stride, block_n, 1, &Ho, &Wo) ? conv_halo_mode() : 0;
+    if (p.halo) {
+        g.th = kHaloTh;
+        g.tw = kHaloTw;
+        ok = ok && make_act_map_halo(&g.in_map[0], d_in, B, H, W, cin, in_pitch);
+    } else if (stride == 1) {
         ok = ok && make_act_map(&g.in_map[0], d_in, B, H, W, cin, in_pitch, g.th, g.tw);
     } else {
         ok = ok && make_act_map_s2(&g.in_map[0], d_in, 0, B, H, W, cin, in_pitch, g.th, g.tw) &&

@@ -21,6 +21,7 @@
 #include "conv_igemm.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -36,6 +37,14 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kStagingBytes = kBlockM * 128;    // one 64-channel bf16 output chunk
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
+// halo variant: per 64-channel block the A operand is ONE (16+2)x(8+2)-pixel patch stored as 8 planes
+// [8-channel group][180 pixels][8 ch = 16 B]; plane stride padded to a multiple of 128 B (TMA destination alignment)
+constexpr int kHaloPW = kHaloTw + 2, kHaloPH = kHaloTh + 2;
+constexpr int kHaloPlaneTx = kHaloPW * kHaloPH * 16;          // 2880 bytes delivered per TMA box
+constexpr int kHaloPlane = (kHaloPlaneTx + 127) / 128 * 128;  // 2944
+constexpr int kHaloABytes = 8 * kHaloPlane;                    // 23552 = 23 KiB (keeps 1024-byte alignment)
+constexpr int kHaloAStages = 3;
+constexpr int kBarBytes = 512;
 
 struct TileCoord {
     int seg, img, y0, x0, n_blk;
@@ -68,20 +77,39 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// elect.sync: exactly one lane of the (converged) warp gets true.  Keeping the role loops warp-converged and
+// predicating only the issue instructions on the elected lane lets the compiler keep TMA / UMMA operands in
+// uniform registers; a `lane == 0` branch instead forces an R2UR + election loop around every UTMALDG / UTCHMMA
+// (measured: ~220 ns per TMA box and ~245 ns per MMA from a single divergent thread).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+template <bool HALO>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = kABytes + p.block_n * 128;
-    uint8_t* staging = smem + p.num_stages * stage_bytes;
+    // generic: num_stages x [A 16 KiB | B block_n*128].  halo: num_stages x [B block_n*128], then 3 x [A patch 23 KiB]
+    const int stage_bytes = (HALO ? 0 : kABytes) + p.block_n * 128;
+    uint8_t* halo_a = smem + p.num_stages * stage_bytes;
+    uint8_t* staging = halo_a + (HALO ? kHaloAStages * kHaloABytes : 0);
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
     uint64_t* full_bar = bars;                     // [kMaxStages]
     uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
     uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
     uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* afull_bar = tempty_bar + 2;          // [kHaloAStages]
+    uint64_t* aempty_bar = afull_bar + kHaloAStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + kHaloAStages);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -91,12 +119,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             if (p.out_mode == 0) ptx::prefetch_tensormap(&p.seg[s].out_map);
         }
         for (int i = 0; i < p.num_stages; ++i) {
-            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&full_bar[i], HALO ? 1 : 2);  // generic: A (warp 0) + B (warp 6) each arrive.expect_tx
             ptx::mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
             ptx::mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+        }
+        for (int i = 0; i < kHaloAStages; ++i) {
+            ptx::mbar_init(&afull_bar[i], 1);
+            ptx::mbar_init(&aempty_bar[i], 1);
         }
         ptx::fence_barrier_init();
     }
@@ -112,22 +144,39 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const int kblocks = p.taps * p.kchunks;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------------------ TMA producer
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t tx_bytes = kABytes + p.block_n * 128;
-            for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
-                const TileCoord t = decode_tile(p, work);
-                const ConvSeg& g = p.seg[t.seg];
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    const int r = (p.taps == 9) ? tap / 3 : 1;
-                    const int s = (p.taps == 9) ? tap - 3 * (tap / 3) : 1;
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
+        // ---------------------------------------------------------------- warp 0: activation (A) producer in the
+        // generic variant, weight (B) producer in the halo variant.  Whole warp runs the loop; one elected lane issues.
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+            const TileCoord t = decode_tile(p, work);
+            const ConvSeg& g = p.seg[t.seg];
+            if (HALO) {
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int tap = 0; tap < 9; ++tap) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                        if (elect_one()) {
+                            ptx::mbar_expect_tx(&full_bar[stage], p.block_n * 128);
+                            ptx::tma_load_2d(smem + stage * stage_bytes, &p.w_map, &full_bar[stage],
+                                             (tap * p.kchunks + kc) * kBlockK, t.n_blk * p.block_n);
+                        }
+                        __syncwarp();
+                        if (++stage == p.num_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+                continue;
+            }
+            for (int tap = 0; tap < p.taps; ++tap) {
+                const int r = (p.taps == 9) ? tap / 3 : 1;
+                const int s = (p.taps == 9) ? tap - 3 * (tap / 3) : 1;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    if (elect_one()) {
                         uint8_t* a_dst = smem + stage * stage_bytes;
-                        uint8_t* b_dst = a_dst + kABytes;
-                        ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        ptx::mbar_expect_tx(&full_bar[stage], kABytes);  // the weight tile is armed + issued by warp 6
                         if (p.stride == 1) {
                             ptx::tma_load_4d(a_dst, &g.in_map[0], &full_bar[stage], kc * kBlockK, t.x0 + s - 1,
                                              t.y0 + r - 1, t.img);
@@ -140,50 +189,139 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                             ptx::tma_load_5d(a_dst, &g.in_map[wp], &full_bar[stage], kc * kBlockK, t.x0 + dw, hp,
                                              t.y0 + dh, t.img);
                         }
-                        ptx::tma_load_2d(b_dst, &p.w_map, &full_bar[stage], (tap * p.kchunks + kc) * kBlockK,
-                                         t.n_blk * p.block_n);
-                        if (++stage == p.num_stages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
                     }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------------------ MMA issuer
-            const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, p.block_n);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
-                ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * p.block_n;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase, 3);
-                    ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(smem + stage * stage_bytes);
-                    const uint32_t b_addr = a_addr + kABytes;
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint64_t adesc = ptx::make_sw128_desc(a_addr + k * 32);
-                        const uint64_t bdesc = ptx::make_sw128_desc(b_addr + k * 32);
-                        ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
-                    }
-                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    __syncwarp();
                     if (++stage == p.num_stages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1;
+            }
+        }
+    } else if (warp == 6) {
+        if (!HALO) {
+            // ------------------------------------------------------------ warp 6: weight-tile (B) producer (generic)
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t b_bytes = p.block_n * 128;
+            for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+                const int n0 = (work % p.n_blocks) * p.block_n;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 7);
+                    if (elect_one()) {
+                        ptx::mbar_expect_tx(&full_bar[stage], b_bytes);
+                        ptx::tma_load_2d(smem + stage * stage_bytes + kABytes, &p.w_map, &full_bar[stage], kb * kBlockK,
+                                         n0);
+                    }
+                    __syncwarp();
+                    if (++stage == p.num_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
+            }
+        } else {
+            // ------------------------------------------------------------ warp 6: halo A-patch producer: one box
+            // [18][10][64 ch] (180 rows of 128 B, 128B-swizzled, zero-filled outside the image) per 64-channel block
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+                const TileCoord t = decode_tile(p, work);
+                const ConvSeg& g = p.seg[t.seg];
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(&aempty_bar[as], aphase ^ 1, 5);
+                    if (elect_one()) {
+                        ptx::mbar_expect_tx(&afull_bar[as], kHaloPW * kHaloPH * 128);
+                        ptx::tma_load_4d(halo_a + as * kHaloABytes, &g.in_map[0], &afull_bar[as], kc * kBlockK,
+                                         t.x0 - 1, t.y0 - 1, t.img);
+                    }
+                    __syncwarp();
+                    if (++as == kHaloAStages) {
+                        as = 0;
+                        aphase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------------------- warp 1: tcgen05.mma issuer
+        // Descriptor high word is constant; the low word is (addr >> 4) | LBO, advanced by 2 (= 32 bytes) per K=16 step.
+        const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, p.block_n);
+        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);                   // SBO 1024, v1, SW128
+        constexpr uint32_t kHaloDescHi = ((kHaloPW * 128u) >> 4) | (1u << 14) | (2u << 29);     // SBO = 10 pixels
+        const uint32_t lo0 = (ptx::smem_u32(smem) >> 4) | (1u << 16);
+        const uint32_t halo_lo0 = (ptx::smem_u32(halo_a) >> 4) | (1u << 16);
+        const uint32_t stage_units = static_cast<uint32_t>(stage_bytes) >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+            ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * p.chains * p.block_n;  // chain c lives at + c * block_n
+            if (HALO) {
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(&afull_bar[as], aphase, 6);
+                    const uint32_t a_lo = halo_lo0 + static_cast<uint32_t>(as) * (kHaloABytes >> 4);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ptx::mbar_wait(&full_bar[stage], phase, 3);
+                        ptx::tc_fence_after();
+                        const int r = tap / 3, s = tap - 3 * r;
+                        const uint32_t a_tap = a_lo + (r * kHaloPW + s) * 8;  // whole pixels: 128 B = 8 x 16 B
+                        const uint32_t b_lo = lo0 + static_cast<uint32_t>(stage) * stage_units;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                const uint64_t adesc = (static_cast<uint64_t>(kHaloDescHi) << 32) | (a_tap + 2 * k);
+                                const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
+                                ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                            }
+                            ptx::umma_commit(&empty_bar[stage]);
+                            if (tap == 8) ptx::umma_commit(&aempty_bar[as]);  // patch free once its 36 MMAs retire
+                        }
+                        __syncwarp();
+                        if (++stage == p.num_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    if (++as == kHaloAStages) {
+                        as = 0;
+                        aphase ^= 1;
+                    }
+                }
+            } else {
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase, 3);
+                    ptx::tc_fence_after();
+                    const uint32_t a_lo = lo0 + static_cast<uint32_t>(stage) * stage_units;
+                    const uint32_t b_lo = a_lo + (kABytes >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t adesc = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2 * k);
+                            const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
+                            const int j = kb * (kBlockK / 16) + k;  // MMA index within the tile
+                            const int chain = j & (p.chains - 1);   // optional split-K accumulator chains
+                            ptx::umma_bf16(d_tmem + chain * p.block_n, adesc, bdesc, idesc, j >= p.chains ? 1u : 0u);
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    }
+                    __syncwarp();
+                    if (++stage == p.num_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+            if (elect_one()) ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+            __syncwarp();
+            if (++acc == p.acc_stages) {
+                acc = 0;
+                acc_phase ^= 1;
             }
         }
     } else {
@@ -216,7 +354,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
             ptx::mbar_wait(&tfull_bar[acc], acc_phase, 4);
             ptx::tc_fence_after();
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.chains * p.block_n;
 
             for (int c0 = 0; c0 < p.block_n; c0 += 64) {
                 const int chunk_cols = min(64, p.block_n - c0);
@@ -235,6 +373,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         ptx::tmem_ld16(t_addr + c0 + h, v);
                     }
                     ptx::tmem_ld_wait();
+                    for (int ch = 1; ch < p.chains; ++ch) {  // add the other split-K chains (fp32)
+                        uint32_t w[32];
+                        if (cols == 32) {
+                            ptx::tmem_ld32(t_addr + ch * p.block_n + c0 + h, w);
+                        } else {
+                            ptx::tmem_ld16(t_addr + ch * p.block_n + c0 + h, w);
+                        }
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < cols) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+                    }
                     const int n0 = n_base + c0 + h;  // absolute output channel of v[0]
                     float y[32];
 #pragma unroll
@@ -311,7 +461,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) {
+            if (++acc == p.acc_stages) {
                 acc = 0;
                 acc_phase ^= 1;
             }
@@ -351,12 +501,12 @@ EncodeTiledFn get_encode_fn() {
 }
 
 bool encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-            const cuuint32_t* box, CUtensorMapL2promotion promo) {
+            const cuuint32_t* box, CUtensorMapL2promotion promo, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) return false;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[256];
@@ -392,6 +542,35 @@ bool make_act_map_s2(CUtensorMap* map, const void* base, int wp, int B, int H, i
     return encode(map, b, 5, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
+int conv_halo_mode() { return 2; }  // one 128B-swizzled [18][10][64ch] box per 64-channel block
+
+bool make_act_map_halo(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kHaloPW, (cuuint32_t)kHaloPH, 1};
+    return encode(map, base, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+}
+
+bool conv_prefer_halo(int taps, int stride, int block_n, int nseg, const int* Hs, const int* Ws) {
+    if (taps != 9 || stride != 1) return false;
+    (void)block_n;
+    static int mode = -1;  // 0 auto, 1 generic, 2 halo
+    if (mode < 0) {
+        const char* e = getenv("DD3D_CONV_MODE");
+        mode = (e && !strcmp(e, "generic")) ? 1 : (e && !strcmp(e, "halo")) ? 2 : 0;
+    }
+    if (mode == 1) return false;
+    if (mode == 2) return true;
+    long halo_tiles = 0, gen_tiles = 0;
+    for (int s = 0; s < nseg; ++s) {
+        int th, tw;
+        choose_tile(Hs[s], Ws[s], &th, &tw);
+        gen_tiles += (long)((Hs[s] + th - 1) / th) * ((Ws[s] + tw - 1) / tw);
+        halo_tiles += (long)((Hs[s] + kHaloTh - 1) / kHaloTh) * ((Ws[s] + kHaloTw - 1) / kHaloTw);
+    }
+    return halo_tiles * 100 <= gen_tiles * 110;  // fixed 16x8 tiling may cost at most 10 % more tiles
+}
+
 bool make_weight_map(CUtensorMap* map, const void* base, int ktot, int cout_pad, int block_n) {
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout_pad};
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
@@ -423,28 +602,52 @@ void conv_finalize_params(ConvParams* p) {
         tile += g.tiles_x * g.tiles_y * p->B;
     }
     p->total_work = tile * p->n_blocks;
-    const int stage_bytes = kABytes + p->block_n * 128;
-    const int fixed = 2 * kStagingBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    const int stage_bytes = (p->halo ? 0 : kABytes) + p->block_n * 128;
+    const int fixed = 2 * kStagingBytes + 1024 /*alignment slack*/ + kBarBytes +
+                      (p->halo ? kHaloAStages * kHaloABytes : 0);
     int stages = (kSmemBudget - fixed) / stage_bytes;
     p->num_stages = std::max(2, std::min(kMaxStages, stages));
+    // split-K chains: enough independent accumulators to cover the ~160-cycle dependent-MMA latency
+    // (one MMA of N columns occupies the pipe for N/2 cycles), within 512 TMEM columns.
+    static int force_chains = -1;
+    if (force_chains < 0) {
+        const char* e = getenv("DD3D_CONV_CHAINS");
+        force_chains = e ? atoi(e) : 0;
+    }
+    int chains = 1;
+    if (!p->halo) {
+        if (force_chains > 0) chains = force_chains;  // default 1: no measured benefit
+        while (chains > 1 && chains * p->block_n > 512) chains /= 2;
+        const int kmmas = p->taps * p->kchunks * (kBlockK / 16);
+        while (chains > 1 && chains > kmmas) chains /= 2;
+    }
+    p->chains = chains;
+    p->acc_stages = (2 * chains * p->block_n <= 512) ? 2 : 1;
     int cols = 32;
-    while (cols < 2 * p->block_n) cols *= 2;
+    while (cols < p->acc_stages * chains * p->block_n) cols *= 2;
     p->tmem_cols = cols;
 }
 
 cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
-    const int stage_bytes = kABytes + p.block_n * 128;
-    const int smem_bytes = p.num_stages * stage_bytes + 2 * kStagingBytes + 1024 + 256;
+    const int stage_bytes = (p.halo ? 0 : kABytes) + p.block_n * 128;
+    const int smem_bytes = p.num_stages * stage_bytes + 2 * kStagingBytes + 1024 + kBarBytes +
+                           (p.halo ? kHaloAStages * kHaloABytes : 0);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
-            cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+            cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     if (p.total_work <= 0) return cudaSuccess;
     const int grid = std::min(p.total_work, num_sms);
-    conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(p);
+    if (p.halo) {
+        conv_igemm_kernel<true><<<grid, kConvThreads, smem_bytes, stream>>>(p);
+    } else {
+        conv_igemm_kernel<false><<<grid, kConvThreads, smem_bytes, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

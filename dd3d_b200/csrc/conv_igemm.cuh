@@ -14,7 +14,7 @@ namespace dd3d {
 constexpr int kMaxSeg = 5;
 constexpr int kBlockM = 128;  // output pixels per tile (th * tw)
 constexpr int kBlockK = 64;   // bf16 channels per k-block = one 128-byte swizzle row
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 224;  // warps: 0 TMA, 1 MMA, 2-5 epilogue, 6 halo A-patch producer
 
 struct ConvSeg {
     CUtensorMap in_map[2];  // NHWC bf16 input.  stride 1: [0] (4-D).  stride 2: [w-parity] (5-D parity split)
@@ -47,6 +47,9 @@ struct ConvParams {
     int total_work;  // (sum of M-tiles) * n_blocks
     int num_stages;
     int tmem_cols;
+    int chains;      // split-K accumulator chains per tile (independent TMEM accumulators, summed in the epilogue)
+    int acc_stages;  // 2: accumulators double-buffered against the epilogue, 1: single-buffered
+    int halo;  // 1: 3x3 stride-1 halo-reuse variant (tile 16x8, A patch loaded once per 64-channel block)
 };
 
 // Host helpers (conv_igemm.cu)
@@ -56,6 +59,13 @@ bool make_act_map_s2(CUtensorMap* map, const void* base, int wp, int B, int H, i
                      int tw);
 bool make_weight_map(CUtensorMap* map, const void* base, int ktot, int cout_pad, int block_n);
 void choose_tile(int H, int W, int* th, int* tw);
+// Halo variant (3x3, stride 1): non-swizzled [8-channel group][18x10 pixels][8 ch] patch loads.
+constexpr int kHaloTh = 16, kHaloTw = 8;
+int conv_halo_mode();
+bool make_act_map_halo(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch);
+// Policy: use the halo variant when its fixed 16x8 tiling costs at most ~15 % more tiles than the best generic
+// tiling over all segments (env DD3D_CONV_MODE=generic|halo overrides, for tests).
+bool conv_prefer_halo(int taps, int stride, int block_n, int nseg, const int* Hs, const int* Ws);
 // Fills num_stages / tmem_cols / total_work / tile bookkeeping from the already-set fields.
 void conv_finalize_params(ConvParams* p);
 cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream);

@@ -256,6 +256,14 @@ struct Builder {
         p.block_n = L.block_n;
         p.relu = relu ? 1 : 0;
         p.out_mode = f32_out ? 1 : 0;
+        {
+            int hs[kMaxSeg], ws[kMaxSeg];
+            for (int s = 0; s < p.nseg; ++s) {
+                hs[s] = segs[s].in.H / stride;
+                ws[s] = segs[s].in.W / stride;
+            }
+            p.halo = conv_prefer_halo(L.taps, stride, L.block_n, p.nseg, hs, ws) ? conv_halo_mode() : 0;
+        }
         for (int s = 0; s < p.nseg; ++s) {
             SegSpec& sp = segs[s];
             ConvSeg& g = p.seg[s];
@@ -270,7 +278,11 @@ struct Builder {
             g.W = Wo;
             choose_tile(Ho, Wo, &g.th, &g.tw);
             bool ok;
-            if (stride == 1) {
+            if (p.halo) {
+                g.th = kHaloTh;
+                g.tw = kHaloTw;
+                ok = make_act_map_halo(&g.in_map[0], sp.in.ptr, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch);
+            } else if (stride == 1) {
                 ok = make_act_map(&g.in_map[0], sp.in.ptr, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, g.th, g.tw);
             } else {
                 ok = make_act_map_s2(&g.in_map[0], sp.in.ptr, 0, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, g.th, g.tw) &&
@@ -899,6 +911,20 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
     cuda_check(launch_nms(np, stream), "nms");
     mark(7);
     if (opt_profile) prof_used = ev_i;
+}
+
+// per-op device time of the last profiled forward: entry 0 = preprocess, then plan.ops in order, then decode, nms
+int Engine::get_op_times(float* ms, int32_t* cats, double* flops, int max_ops) {
+    if (!plan.valid) fail(DD3D_ERR_STATE, "no plan");
+    if (prof_used < 2) return 0;
+    cuda_check(cudaEventSynchronize(prof_ev[prof_used - 1]), "cudaEventSynchronize");
+    int n = 0;
+    for (size_t i = 1; i < prof_used && n < max_ops; ++i, ++n) {
+        cuda_check(cudaEventElapsedTime(&ms[n], prof_ev[i - 1], prof_ev[i]), "cudaEventElapsedTime");
+        cats[n] = prof_cat[i];
+        flops[n] = (i >= 2 && i - 2 < plan.ops.size()) ? plan.ops[i - 2].flops : 0.0;
+    }
+    return n;
 }
 
 void Engine::get_profile(double* ms, double* flops, double* bytes, int32_t* launches) {

@@ -108,6 +108,7 @@ class Engine {
     int launches_per_forward() const;
     // categories: 0 preprocess, 1 stem, 2 conv (tcgen05), 3 pool, 4 eSE, 5 relu, 6 decode, 7 nms
     void get_profile(double* ms, double* flops, double* bytes, int32_t* launches);
+    int get_op_times(float* ms, int32_t* cats, double* flops, int max_ops);
 
     // layer factories (cached by key)
     const HostTensor& weight(const std::string& name) const;

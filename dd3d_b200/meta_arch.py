@@ -271,6 +271,12 @@ class DD3DB200(nn.Module):
         _lib.check(_lib.load().dd3d_get_profile(self._handle, ms, fl, by, ln), self._handle)
         return {n: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=ln[i]) for i, n in enumerate(self.PROFILE_CATEGORIES)}
 
+    def get_op_times(self, max_ops=1024):
+        """[(category, ms, algorithmic flops)] per engine op of the last profiled forward, in launch order."""
+        ms, cats, fl = (C.c_float * max_ops)(), (C.c_int32 * max_ops)(), (C.c_double * max_ops)()
+        n = _lib.check(_lib.load().dd3d_get_op_times(self._handle, ms, cats, fl, max_ops), self._handle)
+        return [(self.PROFILE_CATEGORIES[cats[i]], ms[i], fl[i]) for i in range(n)]
+
     def launches_per_forward(self):
         return _lib.load().dd3d_launches_per_forward(self._handle)
 

@@ -126,6 +126,9 @@ int dd3d_launches_per_forward(dd3d_handle h);
  * Categories (arrays of 8): 0 preprocess, 1 stem conv, 2 tcgen05 implicit-GEMM conv, 3 max-pool, 4 eSE, 5 relu,
  * 6 decode, 7 NMS. */
 int dd3d_get_profile(dd3d_handle h, double* h_ms, double* h_flops, double* h_bytes, int32_t* h_launches);
+/* Same events, per op in launch order (entry 0 = preprocess, then every engine op, then decode, NMS): device ms,
+ * category and algorithmic FLOPs.  Returns the number of entries written (<= max_ops). */
+int dd3d_get_op_times(dd3d_handle h, float* h_ms, int32_t* h_cats, double* h_flops, int max_ops);
 
 /* ---- introspection for stage-level parity tests ---------------------------------------------------------- */
 /* name: "p0".."p4" (FPN outputs, bf16 NHWC), "cls0".."cls4", "box0".."box4", "b3d0".."b3d4" (fp32 NHWC head maps),
