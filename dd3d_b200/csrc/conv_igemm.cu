@@ -454,6 +454,44 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         ptx::tma_store_4d(&g.out_map, stag, n_base + c0, t.x0, t.y0, t.img);
                         ptx::tma_store_commit();
                     }
+                    if (g.pool_partial != nullptr) {
+                        // eSE global-average-pool, fused: per-tile channel sums of the bf16 tile just staged (exactly the
+                        // values the reference pools, vovnet.py:181).  Thread e covers channels 8*(e&7).. of rows
+                        // (e>>3) + 16*i; the 4 row-groups of a warp are shuffle-reduced; one fp32 partial per
+                        // (tile, warp, channel) -> deterministic reduction later (no atomics).
+                        const int e = threadIdx.x - 64;
+                        const int cg = e & 7;
+                        float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = (e >> 3) + 16 * i;
+                            const int ry = t.y0 + (r >> g.tw_shift), rx = t.x0 + (r & (g.tw - 1));
+                            if (ry < g.H && rx < g.W) {
+                                const uint4 u = *reinterpret_cast<const uint4*>(stag + r * 128 + ((cg ^ (r & 7)) << 4));
+                                const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 f = __bfloat1622float2(b2[j]);
+                                    ps[2 * j] += f.x;
+                                    ps[2 * j + 1] += f.y;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            ps[j] += __shfl_xor_sync(0xffffffffu, ps[j], 8);
+                            ps[j] += __shfl_xor_sync(0xffffffffu, ps[j], 16);
+                        }
+                        if (lane < 8 && c0 + cg * 8 < p.block_n) {
+                            const int tile_in_img = (t.y0 / g.th) * g.tiles_x + (t.x0 / g.tw);
+                            float* dst = g.pool_partial +
+                                         ((static_cast<size_t>(t.img) * (g.tiles_x * g.tiles_y) + tile_in_img) * 4 + (warp - 2)) *
+                                             g.pool_pitch +
+                                         n_base + c0 + cg * 8;
+                            *reinterpret_cast<float4*>(dst) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+                            *reinterpret_cast<float4*>(dst + 4) = make_float4(ps[4], ps[5], ps[6], ps[7]);
+                        }
+                    }
                     sbuf ^= 1;
                 }
             }
@@ -592,10 +630,18 @@ void choose_tile(int H, int W, int* th, int* tw) {
     }
 }
 
+int conv_tiles_per_image(int H, int W) {
+    int th, tw;
+    choose_tile(H, W, &th, &tw);
+    return ((H + th - 1) / th) * ((W + tw - 1) / tw);
+}
+
 void conv_finalize_params(ConvParams* p) {
     int tile = 0;
     for (int s = 0; s < p->nseg; ++s) {
         ConvSeg& g = p->seg[s];
+        g.tw_shift = 0;
+        while ((1 << g.tw_shift) < g.tw) ++g.tw_shift;
         g.tiles_x = (g.W + g.tw - 1) / g.tw;
         g.tiles_y = (g.H + g.th - 1) / g.th;
         g.tile_begin = tile;

@@ -30,6 +30,9 @@ struct ConvSeg {
     int th, tw;       // tile shape, th * tw == 128
     int tiles_x, tiles_y;
     int tile_begin;   // index of this segment's first M-tile
+    int tw_shift;     // log2(tw)
+    float* pool_partial;  // optional [B][tiles_per_image][4][pool_pitch] per-tile channel sums (eSE avg-pool), or nullptr
+    int pool_pitch;
 };
 
 struct ConvParams {
@@ -59,6 +62,7 @@ bool make_act_map_s2(CUtensorMap* map, const void* base, int wp, int B, int H, i
                      int tw);
 bool make_weight_map(CUtensorMap* map, const void* base, int ktot, int cout_pad, int block_n);
 void choose_tile(int H, int W, int* th, int* tw);
+int conv_tiles_per_image(int H, int W);  // M-tiles per image of the generic tiling
 // Halo variant (3x3, stride 1): non-swizzled [8-channel group][18x10 pixels][8 ch] patch loads.
 constexpr int kHaloTh = 16, kHaloTw = 8;
 int conv_halo_mode();

@@ -490,10 +490,18 @@ struct Builder {
 
     void ese(const std::string& fc, View xt, const View* identity, View dst) {
         const EseLayer& L = E->ese_layer(fc, xt.C);
-        const int HW = xt.H * xt.W;
-        float* partial = alloc_f32(static_cast<size_t>(B) * ese_nsplit(HW) * xt.C);
+        // The concat conv (the op just emitted) writes per-tile channel sums from its epilogue: [B][T][C], T = 4 * tiles
+        const int T = 4 * conv_tiles_per_image(xt.H, xt.W);
+        float* tile_partial = alloc_f32(static_cast<size_t>(B) * T * xt.C);
+        float* sums = alloc_f32(static_cast<size_t>(B) * xt.C);
         float* gate = alloc_f32(static_cast<size_t>(B) * xt.C);
         if (dry) return;
+        Op& cv = P->ops.back();
+        if (cv.type != Op::CONV || cv.conv.nseg != 1 || cv.conv.halo || cv.conv.out_mode != 0 ||
+            4 * cv.conv.seg[0].tiles_x * cv.conv.seg[0].tiles_y != T)
+            fail(DD3D_ERR_STATE, "internal: eSE must follow its concat conv");
+        cv.conv.seg[0].pool_partial = tile_partial;
+        cv.conv.seg[0].pool_pitch = xt.C;
         Op op;
         op.type = Op::ESE;
         op.in = xt;
@@ -501,8 +509,10 @@ struct Builder {
         op.ese = &L;
         op.has_identity = identity != nullptr;
         if (identity) op.identity = *identity;
-        op.f0 = partial;
+        op.f0 = sums;
         op.f1 = gate;
+        op.f2 = tile_partial;
+        op.ksize = T;
         P->ops.push_back(op);
     }
 
@@ -884,10 +894,10 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
                            "maxpool");
                 break;
             case Op::ESE:
-                cuda_check(launch_ese(op.in.ptr, op.in.pitch, op.ese->d_w, op.ese->d_b,
-                                      op.has_identity ? op.identity.ptr : nullptr, op.has_identity ? op.identity.pitch : 0,
-                                      op.out.ptr, op.out.pitch, op.f0, op.f1, P.B, op.in.H * op.in.W, op.in.C, num_sms,
-                                      stream),
+                cuda_check(launch_ese_fused(op.in.ptr, op.in.pitch, op.f2, op.ksize, op.ese->d_w, op.ese->d_b,
+                                            op.has_identity ? op.identity.ptr : nullptr,
+                                            op.has_identity ? op.identity.pitch : 0, op.out.ptr, op.out.pitch, op.f0, op.f1,
+                                            P.B, op.in.H * op.in.W, op.in.C, num_sms, stream),
                            "eSE");
                 break;
             case Op::RELU:
@@ -960,7 +970,7 @@ void Engine::get_profile(double* ms, double* flops, double* bytes, int32_t* laun
                 break;
             case Op::ESE:
                 launches[4] += 3;
-                bytes[4] += in_px * op.in.C * 2 * (op.has_identity ? 4 : 3);
+                bytes[4] += in_px * op.in.C * 2 * (op.has_identity ? 3 : 2);  // pooling is fused into the concat conv
                 break;
             case Op::RELU:
                 launches[5] += 1;

@@ -61,6 +61,7 @@ struct Op {
     const EseLayer* ese = nullptr;
     float* f0 = nullptr;
     float* f1 = nullptr;
+    float* f2 = nullptr;
     double flops = 0.0;  // algorithmic FLOPs (2*MACs over the real, unpadded channels)
     double bytes = 0.0;  // algorithmic HBM bytes for the bandwidth-bound ops
 };

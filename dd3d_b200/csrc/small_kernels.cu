@@ -202,6 +202,31 @@ __global__ void ese_pool_kernel(const __nv_bfloat16* __restrict__ x, float* __re
     }
 }
 
+// sums[b][c] = sum over the T per-tile/per-warp partial rows written by the concat-conv epilogue (fixed order).
+__global__ void ese_reduce_kernel(const float* __restrict__ tile_partial, float* __restrict__ sums, int T, int C,
+                                  int pitch) {
+    __shared__ float red[4][64];
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int grp = threadIdx.x >> 6;  // 4 row groups
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (c < C) {
+        const float* p = tile_partial + static_cast<size_t>(b) * T * pitch + c;
+        int t = grp;
+        for (; t + 12 < T; t += 16) {
+            s0 += p[static_cast<size_t>(t) * pitch];
+            s1 += p[static_cast<size_t>(t + 4) * pitch];
+            s2 += p[static_cast<size_t>(t + 8) * pitch];
+            s3 += p[static_cast<size_t>(t + 12) * pitch];
+        }
+        for (; t < T; t += 4) s0 += p[static_cast<size_t>(t) * pitch];
+    }
+    red[grp][threadIdx.x & 63] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (grp == 0 && c < C)
+        sums[static_cast<size_t>(b) * C + c] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
 // gate[b][co] = relu6(W[co,:] . mean[b,:] + bias[co] + 3) / 6      (one warp per output channel)
 __global__ void ese_fc_kernel(const float* __restrict__ partial, const float* __restrict__ w, const float* __restrict__ bias,
                               float* __restrict__ gate, int C, int nsplit, float inv_hw) {
@@ -342,6 +367,24 @@ cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, c
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t total = static_cast<size_t>(B) * HW * vc;
+    ese_scale_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
+                                                                      id_pitch, out_pitch);
+    return cudaGetLastError();
+}
+
+// eSE with the pooling partials produced by the conv epilogue: reduce -> fc -> scale (2 tensor passes instead of 3)
+cudaError_t launch_ese_fused(const __nv_bfloat16* x, int x_pitch, const float* tile_partial, int T, const float* fc_w,
+                             const float* fc_b, const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out,
+                             int out_pitch, float* sums, float* gate, int B, int HW, int C, int num_sms,
+                             cudaStream_t stream) {
+    ese_reduce_kernel<<<dim3((C + 63) / 64, B), 256, 0, stream>>>(tile_partial, sums, T, C, C);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ese_fc_kernel<<<dim3((C + 7) / 8, B), 256, C * sizeof(float), stream>>>(sums, fc_w, fc_b, gate, C, 1,
+                                                                          1.0f / static_cast<float>(HW));
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t total = static_cast<size_t>(B) * HW * (C / 8);
     ese_scale_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
                                                                       id_pitch, out_pitch);
     return cudaGetLastError();
