@@ -217,6 +217,7 @@ int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch,
     p.taps = taps;
     p.stride = stride;
     p.kchunks = kchunks;
+    p.cin = cin;
     p.n_blocks = cout_pad / block_n;
     p.block_n = block_n;
     p.relu = relu;
@@ -259,12 +260,11 @@ int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch,
     return cuda_status(launch_conv(p, device_sms(), static_cast<cudaStream_t>(stream)), nullptr);
 }
 
-int dd3d_op_stem_conv(const void* d_in4, const float* d_w, const float* d_scale, const float* d_bias, void* d_out, int B,
+int dd3d_op_stem_conv(const void* d_in4, const void* d_w, const float* d_scale, const float* d_bias, void* d_out, int B,
                       int H, int W, int ksize, int stride, int cout, int out_pitch, dd3d_stream stream) {
-    if (cout % 16) return DD3D_ERR_INVALID;
-    return cuda_status(launch_stem_conv(static_cast<const __nv_bfloat16*>(d_in4), d_w, d_scale, d_bias,
-                                        static_cast<__nv_bfloat16*>(d_out), B, H, W, ksize, stride, cout, out_pitch,
-                                        static_cast<cudaStream_t>(stream)),
+    return cuda_status(launch_stem_tc(static_cast<const __nv_bfloat16*>(d_in4), static_cast<const __nv_bfloat16*>(d_w),
+                                      d_scale, d_bias, static_cast<__nv_bfloat16*>(d_out), B, H, W, ksize, stride, cout,
+                                      out_pitch, device_sms(), static_cast<cudaStream_t>(stream)),
                        nullptr);
 }
 

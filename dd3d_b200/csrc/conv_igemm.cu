@@ -13,11 +13,17 @@
 // beyond C (ragged C such as 160/224).  Stride-2 convs read a parity-split 5-D view of the same tensor.
 // Concats are free: producers TMA-store into channel slices of one wide NHWC buffer, the 1x1 reads it whole.
 //
-// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0 lane 0 : TMA producer      (full/empty mbarrier ring, num_stages deep)
-//   warp 1 lane 0 : tcgen05.mma issuer (accumulators double-buffered in TMEM: 2 x block_n columns)
-//   warps 2..5    : epilogue           (tcgen05.ld -> scale/bias/residual/ReLU -> bf16 -> swizzled smem -> TMA store,
-//                                       or fp32 direct stores for the predictor heads)
+// Halo variant (3x3, stride 1): the A operand of a 64-channel block is ONE box [18][10][64ch] (tile + halo); the nine
+// taps are descriptor views of it shifted by whole 128-byte pixel rows, so A is fetched once instead of nine times.
+//
+// Warp roles (224 threads, 1 CTA/SM, persistent over tiles); every role loop is warp-converged and only the issue
+// instructions are predicated on elect.sync, which keeps TMA / UMMA operands in uniform registers:
+//   warp 0 : TMA producer of the activation tiles (generic) / of the weight tiles (halo)
+//   warp 6 : TMA producer of the weight tiles (generic) / of the halo patches (halo)
+//   warp 1 : tcgen05.mma issuer (accumulators double-buffered in TMEM: 2 x block_n columns)
+//   warps 2..5 : epilogue (tcgen05.ld -> scale/bias/residual/ReLU -> bf16 -> swizzled smem -> TMA store, optional eSE
+//                pooling partial sums; or fp32 direct stores for the predictor heads)
+// Launched with programmatic dependent launch: the prologue overlaps the previous kernel's tail.
 #include "conv_igemm.cuh"
 
 #include <math.h>
@@ -140,6 +146,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the
+    // tail of the previous kernel in the stream; from here on we touch its outputs, so wait for it, and let the next
+    // kernel start its own prologue as our CTAs retire.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int kblocks = p.taps * p.kchunks;
 
@@ -272,12 +283,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         const int r = tap / 3, s = tap - 3 * r;
                         const uint32_t a_tap = a_lo + (r * kHaloPW + s) * 8;  // whole pixels: 128 B = 8 x 16 B
                         const uint32_t b_lo = lo0 + static_cast<uint32_t>(stage) * stage_units;
+                        const int ksteps = (kc == p.kchunks - 1) ? p.last_ksteps : kBlockK / 16;
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) {
-                                const uint64_t adesc = (static_cast<uint64_t>(kHaloDescHi) << 32) | (a_tap + 2 * k);
-                                const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
-                                ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                                if (k < ksteps) {  // channels beyond cin are zero padding: skip their K steps
+                                    const uint64_t adesc = (static_cast<uint64_t>(kHaloDescHi) << 32) | (a_tap + 2 * k);
+                                    const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
+                                    ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                                }
                             }
                             ptx::umma_commit(&empty_bar[stage]);
                             if (tap == 8) ptx::umma_commit(&aempty_bar[as]);  // patch free once its 36 MMAs retire
@@ -294,19 +308,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     }
                 }
             } else {
+                int kc_gen = 0;  // channel block of k-block kb (k-blocks run tap-major: kb = tap * kchunks + kc)
                 for (int kb = 0; kb < kblocks; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase, 3);
                     ptx::tc_fence_after();
                     const uint32_t a_lo = lo0 + static_cast<uint32_t>(stage) * stage_units;
                     const uint32_t b_lo = a_lo + (kABytes >> 4);
+                    if (++kc_gen == p.kchunks) kc_gen = 0;
+                    const int ksteps = (kc_gen == 0) ? p.last_ksteps : kBlockK / 16;  // kc_gen == 0: this was the last block
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
-                            const uint64_t adesc = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2 * k);
-                            const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
-                            const int j = kb * (kBlockK / 16) + k;  // MMA index within the tile
-                            const int chain = j & (p.chains - 1);   // optional split-K accumulator chains
-                            ptx::umma_bf16(d_tmem + chain * p.block_n, adesc, bdesc, idesc, j >= p.chains ? 1u : 0u);
+                            if (k < ksteps) {  // channels beyond cin are zero padding: skip their K steps
+                                const uint64_t adesc = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2 * k);
+                                const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
+                                const int j = kb * (kBlockK / 16) + k;  // MMA index within the tile
+                                const int chain = j & (p.chains - 1);   // optional split-K accumulator chains
+                                ptx::umma_bf16(d_tmem + chain * p.block_n, adesc, bdesc, idesc, j >= p.chains ? 1u : 0u);
+                            }
                         }
                         ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
                     }
@@ -669,6 +688,10 @@ void conv_finalize_params(ConvParams* p) {
     }
     p->chains = chains;
     p->acc_stages = (2 * chains * p->block_n <= 512) ? 2 : 1;
+    {
+        const int rem = p->cin - kBlockK * (p->kchunks - 1);
+        p->last_ksteps = (p->cin > 0 && rem > 0 && chains == 1) ? std::min(kBlockK / 16, (rem + 15) / 16) : kBlockK / 16;
+    }
     int cols = 32;
     while (cols < p->acc_stages * chains * p->block_n) cols *= 2;
     p->tmem_cols = cols;
@@ -689,12 +712,24 @@ cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
     }
     if (p.total_work <= 0) return cudaSuccess;
     const int grid = std::min(p.total_work, num_sms);
-    if (p.halo) {
-        conv_igemm_kernel<true><<<grid, kConvThreads, smem_bytes, stream>>>(p);
-    } else {
-        conv_igemm_kernel<false><<<grid, kConvThreads, smem_bytes, stream>>>(p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char* e = getenv("DD3D_NO_PDL");
+        use_pdl = (e && atoi(e)) ? 0 : 1;
     }
-    return cudaGetLastError();
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    return p.halo ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, p)
+                  : cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, p);
 }
 
 }  // namespace dd3d

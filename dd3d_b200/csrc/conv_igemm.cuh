@@ -52,6 +52,8 @@ struct ConvParams {
     int tmem_cols;
     int chains;      // split-K accumulator chains per tile (independent TMEM accumulators, summed in the epilogue)
     int acc_stages;  // 2: accumulators double-buffered against the epilogue, 1: single-buffered
+    int cin;          // real input channels (the zero-padded K steps of the last 64-channel block are skipped)
+    int last_ksteps;  // K=16 steps of the last channel block: ceil((cin - 64*(kchunks-1)) / 16)
     int halo;  // 1: 3x3 stride-1 halo-reuse variant (tile 16x8, A patch loaded once per 64-channel block)
 };
 

@@ -252,6 +252,7 @@ struct Builder {
         p.taps = L.taps;
         p.stride = stride;
         p.kchunks = L.kchunks;
+        p.cin = L.cin;
         p.n_blocks = L.n_blocks;
         p.block_n = L.block_n;
         p.relu = relu ? 1 : 0;
@@ -688,17 +689,16 @@ const StemLayer& Engine::stem_layer(const std::string& wname, const std::string&
     S.ksize = ksize;
     S.stride = stride;
     S.cout = static_cast<int>(w.shape[0]);
-    // engine layout [ky][kx][c][cout] fp32, with the weights pre-rounded to bf16 like every other conv
-    std::vector<float> packed(static_cast<size_t>(ksize) * ksize * 3 * S.cout);
+    // tensor-core stem layout: bf16 [cout][kpad], k = (ky*ksize + kx)*4 + c, zero padded (4th channel and K tail)
+    const int kpad = stem_tc_kpad(ksize);
+    std::vector<uint16_t> packed(static_cast<size_t>(S.cout) * kpad, 0);
     for (int co = 0; co < S.cout; ++co)
         for (int c = 0; c < 3; ++c)
-            for (int t = 0; t < ksize * ksize; ++t) {
-                const uint32_t bits = static_cast<uint32_t>(f32_to_bf16(w.data[(static_cast<size_t>(co) * 3 + c) * ksize * ksize + t])) << 16;
-                float f;
-                memcpy(&f, &bits, 4);
-                packed[(static_cast<size_t>(t) * 3 + c) * S.cout + co] = f;
-            }
-    S.d_w = upload_f32(packed);
+            for (int t = 0; t < ksize * ksize; ++t)
+                packed[static_cast<size_t>(co) * kpad + t * 4 + c] =
+                    f32_to_bf16(w.data[(static_cast<size_t>(co) * 3 + c) * ksize * ksize + t]);
+    S.d_w = static_cast<__nv_bfloat16*>(dev_alloc(packed.size() * 2));
+    cuda_check(cudaMemcpy(S.d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice), "upload stem weights");
     S.epi = bn_epilogue(wname + "|" + bn, bn, "", S.cout);
     return stems.emplace(wname, S).first->second;
 }
@@ -883,9 +883,9 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
                 cuda_check(launch_conv(op.conv, num_sms, stream), "conv");
                 break;
             case Op::STEM:
-                cuda_check(launch_stem_conv(op.in.ptr, op.stem->d_w, op.stem->epi.d_scale, op.stem->epi.d_bias,
-                                            op.out.ptr, P.B, op.in.H, op.in.W, op.ksize, op.stride, op.stem->cout,
-                                            op.out.pitch, stream),
+                cuda_check(launch_stem_tc(op.in.ptr, op.stem->d_w, op.stem->epi.d_scale, op.stem->epi.d_bias, op.out.ptr,
+                                          P.B, op.in.H, op.in.W, op.ksize, op.stride, op.stem->cout, op.out.pitch, num_sms,
+                                          stream),
                            "stem conv");
                 break;
             case Op::POOL:

@@ -41,7 +41,7 @@ struct Epilogue {
     float* d_lo;
 };
 struct StemLayer {
-    float* d_w;
+    __nv_bfloat16* d_w;
     int ksize, stride, cout;
     Epilogue epi;
 };

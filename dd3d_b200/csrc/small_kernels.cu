@@ -1,7 +1,6 @@
 // Bandwidth-bound kernels of the DD3D backbone (NHWC bf16, 128-bit vector accesses):
 //   preprocess   : (x - mean) / std, zero pad, NCHW -> NHWC(4)        reference core.py:61-72, image_list.py:93-158
-//   stem conv    : direct conv for the Cin=3 stems (DLA 7x7 s1, VoVNet 3x3 s2) + folded BN + ReLU
-//                                                                     reference dla.py:271-280, vovnet.py:302-306
+//   (the Cin=3 stem convs live in stem_tc.cu)
 //   max-pool     : 2x2/s2 (DLA Tree.downsample, dla.py:224-225), 3x3/s2 ceil (VoVNet, vovnet.py:248-249)
 //   eSE          : global avg-pool -> fc -> hsigmoid -> channel scale (+identity)   vovnet.py:169-185,233-236
 //   relu         : p7 input (detectron2 LastLevelP6P7)
@@ -44,91 +43,6 @@ __global__ void preprocess_kernel(const T* __restrict__ src, const int* __restri
     o.x = pack2(v0, v1);
     o.y = pack2(v2, 0.f);
     *reinterpret_cast<uint2*>(dst + (static_cast<size_t>(b * Hp + y) * Wp + x) * 4) = o;
-}
-
-// ------------------------------------------------------------------------------------------ stem conv
-// Each thread: 2 horizontally adjacent output pixels x 16 output channels; weights broadcast from smem.
-template <int KS, int STRIDE>
-__global__ void __launch_bounds__(256) stem_conv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
-                                                        const float* __restrict__ scale, const float* __restrict__ bias,
-                                                        __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo,
-                                                        int Cout, int out_pitch) {
-    constexpr int TY = 16, TX = 32, PAD = (KS - 1) / 2;
-    constexpr int PH = (TY - 1) * STRIDE + KS, PW = (TX - 1) * STRIDE + KS;
-    __shared__ uint2 patch[PH][PW];
-    __shared__ float4 wsm[KS * KS * 3][4];
-    const int groups = Cout / 16;
-    const int b = blockIdx.z / groups, cg = blockIdx.z - b * groups;
-    const int oy0 = blockIdx.y * TY, ox0 = blockIdx.x * TX;
-    const int tid = threadIdx.y * 16 + threadIdx.x;
-    const int iy0 = oy0 * STRIDE - PAD, ix0 = ox0 * STRIDE - PAD;
-    for (int i = tid; i < PH * PW; i += 256) {
-        const int py = i / PW, px = i - py * PW;
-        const int iy = iy0 + py, ix = ix0 + px;
-        uint2 v = make_uint2(0u, 0u);
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-            v = *reinterpret_cast<const uint2*>(in + (static_cast<size_t>(b * H + iy) * W + ix) * 4);
-        patch[py][px] = v;
-    }
-    for (int i = tid; i < KS * KS * 3 * 4; i += 256) {
-        const int k = i >> 2, j = i & 3;
-        wsm[k][j] = *reinterpret_cast<const float4*>(w + static_cast<size_t>(k) * Cout + cg * 16 + j * 4);
-    }
-    __syncthreads();
-    float acc[2][16];
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-#pragma unroll
-        for (int c = 0; c < 16; ++c) acc[p][c] = 0.f;
-    const int ly = threadIdx.y * STRIDE, lx = threadIdx.x * 2 * STRIDE;
-#pragma unroll 1
-    for (int ky = 0; ky < KS; ++ky) {
-#pragma unroll
-        for (int kx = 0; kx < KS; ++kx) {
-            float xin[2][3];
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                const uint2 v = patch[ly + ky][lx + p * STRIDE + kx];
-                const float2 a = unpack2(v.x), c2 = unpack2(v.y);
-                xin[p][0] = a.x;
-                xin[p][1] = a.y;
-                xin[p][2] = c2.x;
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int k = (ky * KS + kx) * 3 + c;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 wv = wsm[k][j];
-#pragma unroll
-                    for (int p = 0; p < 2; ++p) {
-                        acc[p][4 * j + 0] = fmaf(xin[p][c], wv.x, acc[p][4 * j + 0]);
-                        acc[p][4 * j + 1] = fmaf(xin[p][c], wv.y, acc[p][4 * j + 1]);
-                        acc[p][4 * j + 2] = fmaf(xin[p][c], wv.z, acc[p][4 * j + 2]);
-                        acc[p][4 * j + 3] = fmaf(xin[p][c], wv.w, acc[p][4 * j + 3]);
-                    }
-                }
-            }
-        }
-    }
-    const int oy = oy0 + threadIdx.y;
-    if (oy >= Ho) return;
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const int ox = ox0 + threadIdx.x * 2 + p;
-        if (ox >= Wo) continue;
-        uint32_t o[8];
-#pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-            const int n = cg * 16 + c;
-            const float y0 = fmaxf(fmaf(acc[p][c], scale[n], bias[n]), 0.f);
-            const float y1 = fmaxf(fmaf(acc[p][c + 1], scale[n + 1], bias[n + 1]), 0.f);
-            o[c >> 1] = pack2(y0, y1);
-        }
-        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b * Ho + oy) * Wo + ox) * out_pitch + cg * 16);
-        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-    }
 }
 
 // ------------------------------------------------------------------------------------------ max-pool
@@ -316,22 +230,6 @@ cudaError_t launch_preprocess(const void* src, int src_is_u8, const int* d_sizes
         preprocess_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(src), d_sizes, dst, B, Hs, Ws,
                                                              Hp, Wp, size_stride, mean[0], mean[1], mean[2], std[0], std[1],
                                                              std[2]);
-    }
-    return cudaGetLastError();
-}
-
-cudaError_t launch_stem_conv(const __nv_bfloat16* in, const float* w, const float* scale, const float* bias,
-                             __nv_bfloat16* out, int B, int H, int W, int ksize, int stride, int Cout, int out_pitch,
-                             cudaStream_t stream) {
-    const int pad = (ksize - 1) / 2;
-    const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
-    dim3 block(16, 16), grid((Wo + 31) / 32, (Ho + 15) / 16, B * (Cout / 16));
-    if (ksize == 7 && stride == 1) {
-        stem_conv_kernel<7, 1><<<grid, block, 0, stream>>>(in, w, scale, bias, out, H, W, Ho, Wo, Cout, out_pitch);
-    } else if (ksize == 3 && stride == 2) {
-        stem_conv_kernel<3, 2><<<grid, block, 0, stream>>>(in, w, scale, bias, out, H, W, Ho, Wo, Cout, out_pitch);
-    } else {
-        return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }

@@ -12,10 +12,12 @@ cudaError_t launch_preprocess(const void* src, int src_is_u8, const int* d_sizes
                               int B, int Hs, int Ws, int Hp, int Wp, const float mean[3], const float std[3],
                               cudaStream_t stream);
 
-// in: [B][H][W][4] bf16; w: [ksize*ksize*3][Cout] fp32; out NHWC bf16 with `out_pitch` channels per pixel.
-cudaError_t launch_stem_conv(const __nv_bfloat16* in, const float* w, const float* scale, const float* bias,
-                             __nv_bfloat16* out, int B, int H, int W, int ksize, int stride, int Cout, int out_pitch,
-                             cudaStream_t stream);
+// Stem conv (Cin = 3) on tensor cores (stem_tc.cu).  in: bf16 [B][H][W][4]; w: bf16 [cout][stem_tc_kpad(ksize)] with
+// k = (ky*ksize + kx)*4 + c (zero padded); out NHWC bf16 with `out_pitch` channels per pixel.
+int stem_tc_kpad(int ksize);
+cudaError_t launch_stem_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const float* scale, const float* bias,
+                           __nv_bfloat16* out, int B, int H, int W, int ksize, int stride, int cout, int out_pitch,
+                           int num_sms, cudaStream_t stream);
 
 cudaError_t launch_maxpool(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, int in_pitch,
                            int Ho, int Wo, int out_pitch, int ksize, int num_sms, cudaStream_t stream);

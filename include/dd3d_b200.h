@@ -136,13 +136,16 @@ int dd3d_get_op_times(dd3d_handle h, float* h_ms, int32_t* h_cats, double* h_flo
 int dd3d_get_tensor(dd3d_handle h, const char* name, void** d_ptr, int32_t dims[6]);
 
 /* ---- single operators (same kernels the engine launches; used by the kernel-level parity tests) ----------- */
+/* dd3d_op_stem_conv: Cin=3 stem conv on tensor cores; d_in4 = bf16 [B][H][W][4] (dd3d_op_preprocess output), d_w =
+ * bf16 [cout][kpad] with k = (ky*ksize + kx)*4 + c, kpad = ksize*ksize*4 rounded up to 64; (ksize, stride, cout) in
+ * {(7,1,16), (3,2,64)}. */
 /* NHWC bf16 conv via the tcgen05 implicit-GEMM kernel.  d_w: bf16 [cout_pad][ksize*ksize][cin_pad64];
  * d_scale/d_bias: fp32 [cout_pad]; d_residual (optional) NHWC bf16 with res_pitch channels, res_up2: residual is
  * the 2x coarser map; out: bf16 (out_f32 == 0, pitch out_pitch) or fp32. */
 int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch, const void* d_w, int cout, int ksize,
                    int stride, const float* d_scale, const float* d_bias, int relu, const void* d_residual,
                    int res_pitch, int res_up2, void* d_out, int out_pitch, int out_f32, dd3d_stream stream);
-int dd3d_op_stem_conv(const void* d_in4, const float* d_w, const float* d_scale, const float* d_bias, void* d_out,
+int dd3d_op_stem_conv(const void* d_in4, const void* d_w, const float* d_scale, const float* d_bias, void* d_out,
                       int B, int H, int W, int ksize, int stride, int cout, int out_pitch, dd3d_stream stream);
 int dd3d_op_preprocess(const void* d_images, int img_dtype, const int32_t* d_sizes2, void* d_out4, int B, int Hs, int Ws,
                        int Hp, int Wp, const float* h_mean, const float* h_std, dd3d_stream stream);

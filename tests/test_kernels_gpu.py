@@ -145,7 +145,10 @@ def test_stem_conv_and_preprocess():
         wq = w.to(torch.bfloat16).float()
         scale = 0.5 + torch.rand(cout, generator=g)
         bias = torch.randn(cout, generator=g) * 0.2
-        wpk = wq.permute(2, 3, 1, 0).reshape(ksize * ksize * 3, cout).contiguous().cuda()
+        kpad = (ksize * ksize * 4 + 63) // 64 * 64  # engine layout: bf16 [cout][kpad], k = (ky*ksize + kx)*4 + c
+        wpk = torch.zeros(cout, kpad)
+        wpk[:, :ksize * ksize * 4].view(cout, ksize * ksize, 4)[:, :, :3] = wq.permute(0, 2, 3, 1).reshape(cout, -1, 3)
+        wpk = wpk.to(torch.bfloat16).cuda()
         Ho, Wo = Hp // stride, Wp // stride
         out = torch.empty(B, Ho, Wo, cout, dtype=torch.bfloat16, device="cuda")
         d_scale, d_bias = scale.cuda(), bias.cuda()
