@@ -150,30 +150,47 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         // ---- 2. greedy NMS, 64 sorted boxes per step
         for (int c0 = 0; c0 < n; c0 += 64) {
             const int cn = min(64, n - c0);
-            // diagonal block: thread t < 64*64 computes one pair
-            for (int t = threadIdx.x; t < 64; t += blockDim.x) s_diag[t] = 0ull;
-            __syncthreads();
-            for (int t = threadIdx.x; t < cn * cn; t += blockDim.x) {
-                const int i = t / cn, j = t - i * cn;
-                if (j > i && cls[c0 + i] == cls[c0 + j] && iou_tv(boxes[c0 + i], boxes[c0 + j]) > p.nms_thresh)
-                    atomicOr(&s_diag[i], 1ull << j);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned long long removed = 0ull, kept = 0ull;
-                for (int i = 0; i < cn; ++i) {
-                    if (flag[c0 + i]) removed |= (1ull << i);
-                }
-                for (int i = 0; i < cn; ++i) {
-                    if (!((removed >> i) & 1ull)) {
-                        kept |= (1ull << i);
-                        removed |= s_diag[i];
+            // (A) diagonal block: 16 threads per row, 4 columns each; OR-reduce the 4-bit pieces with shuffles
+            {
+                const int i = threadIdx.x >> 4, part = threadIdx.x & 15;
+                unsigned long long m = 0ull;
+                if (i < cn) {
+                    const float4 bi = boxes[c0 + i];
+                    const uint8_t ci = cls[c0 + i];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = part * 4 + u;
+                        if (j > i && j < cn && cls[c0 + j] == ci && iou_tv(bi, boxes[c0 + j]) > p.nms_thresh) m |= 1ull << j;
                     }
                 }
-                s_kept_mask = kept;
-                for (int i = 0; i < cn; ++i) flag[c0 + i] = ((kept >> i) & 1ull) ? 0 : 1;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+                if (part == 0) s_diag[i] = m;
             }
             __syncthreads();
+            // (B) warp 0 resolves the 64 boxes serially in registers (diag rows via shuffles)
+            if (threadIdx.x < 32) {
+                const int l = threadIdx.x;
+                const unsigned long long d_lo = s_diag[l], d_hi = s_diag[l + 32];
+                const unsigned r_lo = __ballot_sync(0xffffffffu, l < cn && flag[c0 + l]);
+                const unsigned r_hi = __ballot_sync(0xffffffffu, l + 32 < cn && flag[c0 + l + 32]);
+                unsigned long long removed = (static_cast<unsigned long long>(r_hi) << 32) | r_lo;
+                if (cn < 64) removed |= ~0ull << cn;
+                unsigned long long kept = 0ull;
+#pragma unroll 8
+                for (int i = 0; i < 64; ++i) {
+                    const unsigned long long di = __shfl_sync(0xffffffffu, i < 32 ? d_lo : d_hi, i & 31);
+                    if (!((removed >> i) & 1ull)) {
+                        kept |= 1ull << i;
+                        removed |= di;
+                    }
+                }
+                if (l == 0) s_kept_mask = kept;
+                if (l < cn) flag[c0 + l] = ((kept >> l) & 1ull) ? 0 : 1;
+                if (l + 32 < cn) flag[c0 + l + 32] = ((kept >> (l + 32)) & 1ull) ? 0 : 1;
+            }
+            __syncthreads();
+            // (C) every later box is tested against the step's survivors
             const unsigned long long kept = s_kept_mask;
             for (int k = c0 + cn + threadIdx.x; k < n; k += blockDim.x) {
                 if (flag[k]) continue;
