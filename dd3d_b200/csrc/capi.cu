@@ -302,6 +302,16 @@ int dd3d_op_ese(const void* d_x, int x_pitch, const float* d_fc_w, const float* 
                        nullptr);
 }
 
+int dd3d_op_bev_nms(dd3d_det* d_dets, int32_t* d_counts, const float* d_intrinsics, const float* d_poses,
+                    const int32_t* d_sizes, int32_t* d_flags, int B, int cap, float iou_thresh, int do_postprocess,
+                    dd3d_stream stream) {
+    if (!d_dets || !d_counts || !d_intrinsics || !d_poses || !d_sizes || !d_flags || B < 1 || cap < 1)
+        return DD3D_ERR_INVALID;
+    return cuda_status(launch_bev_nms(reinterpret_cast<Det*>(d_dets), d_counts, d_intrinsics, d_poses, d_sizes, d_flags, B,
+                                      cap, iou_thresh, do_postprocess, static_cast<cudaStream_t>(stream)),
+                       nullptr);
+}
+
 int64_t dd3d_op_detect_scratch_bytes(int B, int pre_nms_topk) {
     return static_cast<int64_t>(decode_scratch_bytes(B, pre_nms_topk)) + DD3D_MAX_CLASSES * 3 * 4 + 256;
 }

@@ -77,5 +77,8 @@ void decode_bind_scratch(DecodeParams* p, void* scratch);
 void decode_finalize_params(DecodeParams* p);
 cudaError_t launch_decode(const DecodeParams& p, cudaStream_t stream);
 cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream);
+// BEV rotated NMS on the (already 2-D-NMSed, score-sorted) detections, in place; poses: [B][7] (w,x,y,z, tx,ty,tz).
+cudaError_t launch_bev_nms(Det* dets, int32_t* counts, const float* K, const float* poses, const int32_t* sizes,
+                           int32_t* flags, int B, int cap, float thr, int do_postprocess, cudaStream_t stream);
 
 }  // namespace dd3d

@@ -164,6 +164,24 @@ class DD3DB200(nn.Module):
             sizes[i] = torch.tensor([h, w, oh, ow], dtype=torch.int32)
         return batch, K.reshape(B, 9).contiguous(), sizes, (B, Hs, Ws), is_u8
 
+    @staticmethod
+    def _gather_poses(batched_inputs):
+        """[B][7] sensor->global poses (w, x, y, z, tx, ty, tz) from input["pose"] / input["extrinsics"]
+        (core.py:141-144): a tridet Pose (pyquaternion .quat.elements + .tvec), a (quat, tvec) pair, or a 4x4 matrix."""
+        rows = []
+        for x in batched_inputs:
+            p = x["pose"] if "pose" in x else x["extrinsics"]
+            if hasattr(p, "quat") and hasattr(p, "tvec"):
+                q, t = [float(v) for v in p.quat.elements], [float(v) for v in p.tvec]
+            elif isinstance(p, (tuple, list)) and len(p) == 2:
+                q, t = [float(v) for v in p[0]], [float(v) for v in p[1]]
+            else:
+                m = torch.as_tensor(p, dtype=torch.float64)
+                from .structures import matrix_to_quaternion_wxyz
+                q, t = matrix_to_quaternion_wxyz(m[:3, :3]), [float(v) for v in m[:3, 3]]
+            rows.append(q + t)
+        return torch.tensor(rows, dtype=torch.float32)
+
     def _wrap(self, out, counts, K, sizes, device):
         """[B][cap][24] fp32 words + counts -> list[{"instances": Instances}] (fields: fcos2d.py:331-335, fcos3d.py:398)."""
         inv_K = torch.linalg.inv(K.reshape(-1, 3, 3).to(torch.float64)).to(torch.float32).to(device)
@@ -187,8 +205,6 @@ class DD3DB200(nn.Module):
     @torch.no_grad()
     def forward(self, batched_inputs):
         """Device path: inputs are moved to the GPU with torch, one small D2H (per-image counts) at the end."""
-        if self.do_bev_nms:
-            raise NotImplementedError("BEV NMS (DD3D.INFERENCE.DO_BEV_NMS) is not implemented yet (SURVEY.md 8f)")
         device = self._device
         batch, K, sizes, shape, is_u8 = self._gather_inputs(batched_inputs, device)
         self._plan(*shape)
@@ -202,13 +218,22 @@ class DD3DB200(nn.Module):
             out = torch.empty((B, cap, _lib.DET_WORDS), dtype=torch.float32, device=device)
             counts = torch.empty((B, ), dtype=torch.int32, device=device)
             stream = torch.cuda.current_stream(device).cuda_stream
-            _lib.check(L.dd3d_set_option(self._handle, b"do_postprocess", int(self.postprocess_in_inference)),
-                       self._handle)
+            # with BEV NMS the rescale/clip happens after it (core.py:137-160): the BEV kernel applies it then
+            post_in_fwd = self.postprocess_in_inference and not self.do_bev_nms
+            _lib.check(L.dd3d_set_option(self._handle, b"do_postprocess", int(post_in_fwd)), self._handle)
             _lib.check(L.dd3d_set_option(self._handle, b"do_nms", int(self.do_nms)), self._handle)
             _lib.check(
                 L.dd3d_forward(self._handle, C.c_void_p(d_batch.data_ptr()), _lib.IMG_U8 if is_u8 else _lib.IMG_F32,
                                C.c_void_p(d_K.data_ptr()), C.c_void_p(d_sizes.data_ptr()), C.c_void_p(out.data_ptr()),
                                C.c_void_p(counts.data_ptr()), C.c_void_p(stream)), self._handle)
+            if self.do_bev_nms:
+                d_poses = self._gather_poses(batched_inputs).to(device, non_blocking=True)
+                self._bev_flags = torch.zeros(1, dtype=torch.int32, device=device)
+                _lib.check(
+                    L.dd3d_op_bev_nms(C.c_void_p(out.data_ptr()), C.c_void_p(counts.data_ptr()), C.c_void_p(d_K.data_ptr()),
+                                      C.c_void_p(d_poses.data_ptr()), C.c_void_p(d_sizes.data_ptr()),
+                                      C.c_void_p(self._bev_flags.data_ptr()), B, cap, float(self.bev_nms_iou_thresh),
+                                      int(self.postprocess_in_inference), C.c_void_p(stream)), self._handle)
             counts_h = counts.cpu()  # the only synchronisation
         return self._wrap(out, counts_h, K, sizes, device)
 

@@ -191,3 +191,22 @@ except Exception:  # noqa: BLE001
                 return cls(torch.empty(0), torch.empty(0), torch.empty(0), torch.empty(0), torch.empty(0))
             return cls(*[torch.cat([getattr(b, f) for b in boxes_list], dim=dim)
                          for f in ("quat", "proj_ctr", "depth", "size", "inv_intrinsics")])
+
+
+def matrix_to_quaternion_wxyz(R):
+    """3x3 rotation (tensor) -> [w, x, y, z] (host-side helper for 4x4 pose inputs)."""
+    m = torch.as_tensor(R, dtype=torch.float64)
+    tr = float(m[0, 0] + m[1, 1] + m[2, 2])
+    if tr > 0:
+        s = (tr + 1.0)**0.5 * 2
+        q = [0.25 * s, float(m[2, 1] - m[1, 2]) / s, float(m[0, 2] - m[2, 0]) / s, float(m[1, 0] - m[0, 1]) / s]
+    elif m[0, 0] > m[1, 1] and m[0, 0] > m[2, 2]:
+        s = float(1.0 + m[0, 0] - m[1, 1] - m[2, 2])**0.5 * 2
+        q = [float(m[2, 1] - m[1, 2]) / s, 0.25 * s, float(m[0, 1] + m[1, 0]) / s, float(m[0, 2] + m[2, 0]) / s]
+    elif m[1, 1] > m[2, 2]:
+        s = float(1.0 + m[1, 1] - m[0, 0] - m[2, 2])**0.5 * 2
+        q = [float(m[0, 2] - m[2, 0]) / s, float(m[0, 1] + m[1, 0]) / s, 0.25 * s, float(m[1, 2] + m[2, 1]) / s]
+    else:
+        s = float(1.0 + m[2, 2] - m[0, 0] - m[1, 1])**0.5 * 2
+        q = [float(m[1, 0] - m[0, 1]) / s, float(m[0, 2] + m[2, 0]) / s, float(m[1, 2] + m[2, 1]) / s, 0.25 * s]
+    return q

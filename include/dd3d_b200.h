@@ -154,6 +154,14 @@ int dd3d_op_maxpool(const void* d_in, void* d_out, int B, int H, int W, int C, i
 int dd3d_op_ese(const void* d_x, int x_pitch, const float* d_fc_w, const float* d_fc_b, const void* d_identity,
                 int id_pitch, void* d_out, int out_pitch, float* d_scratch, int B, int HW, int C, dd3d_stream stream);
 int64_t dd3d_op_ese_scratch_bytes(int B, int HW, int C);
+/* Bird's-eye-view rotated NMS (reference DO_BEV_NMS branch, core.py:137-151 -> postprocessing.py:22-108 ->
+ * tridet/layers/bev_nms.py:51-133 -> detectron2 batched_nms_rotated), in place on the detections a dd3d_forward run
+ * with option "do_postprocess" = 0 produced: d_dets [B][cap], d_counts [B].  d_poses: [B][7] sensor->global pose of
+ * each image (quaternion w,x,y,z + translation; input["pose"] / input["extrinsics"]).  Applies detector_postprocess
+ * afterwards when do_postprocess != 0.  d_flags: one int32 word, bit 2 set if an image had more than 256 boxes. */
+int dd3d_op_bev_nms(dd3d_det* d_dets, int32_t* d_counts, const float* d_intrinsics, const float* d_poses,
+                    const int32_t* d_sizes, int32_t* d_flags, int B, int cap, float iou_thresh, int do_postprocess,
+                    dd3d_stream stream);
 /* decode + NMS on caller-provided head maps (layout documented in csrc/detect.cuh). */
 int64_t dd3d_op_detect_scratch_bytes(int B, int pre_nms_topk);
 int dd3d_op_detect(const dd3d_model_desc* h_desc, int B, const int32_t* h_level_hw /*[5][2]*/,

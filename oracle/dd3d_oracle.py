@@ -316,19 +316,25 @@ class DD3DOracle:
             keep = torch.nonzero(det["score"] >= thr).squeeze(1)
             det = {k: v[keep] for k, v in det.items()}
         if do_postprocess:
-            sx = out_size[1] / image_size[1]
-            sy = out_size[0] / image_size[0]
-            b = det["box2d"].clone()
-            b[:, 0::2] *= sx
-            b[:, 1::2] *= sy
-            b[:, 0].clamp_(0, out_size[1])
-            b[:, 2].clamp_(0, out_size[1])
-            b[:, 1].clamp_(0, out_size[0])
-            b[:, 3].clamp_(0, out_size[0])
-            det["box2d"] = b
-            ne = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
-            det = {k: v[ne] for k, v in det.items()}
+            det = self.postprocess(det, image_size, out_size)
         return det
+
+    @staticmethod
+    def postprocess(det, image_size, out_size):
+        """detectron2 detector_postprocess: scale to the output size, clip, drop empty boxes."""
+        sx = out_size[1] / image_size[1]
+        sy = out_size[0] / image_size[0]
+        b = det["box2d"].clone()
+        b[:, 0::2] *= sx
+        b[:, 1::2] *= sy
+        b[:, 0].clamp_(0, out_size[1])
+        b[:, 2].clamp_(0, out_size[1])
+        b[:, 1].clamp_(0, out_size[0])
+        b[:, 3].clamp_(0, out_size[0])
+        det = dict(det)
+        det["box2d"] = b
+        ne = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+        return {k: v[ne] for k, v in det.items()}
 
     # ------------------------------------------------------------------------------------------
     # whole forward
@@ -349,10 +355,27 @@ class DD3DOracle:
             det = {k: torch.cat([d[k] for d in per_level], 0) for k in per_level[0]}
             pre_nms.append(det)
             out_size = (batched_inputs[b].get("height", sizes[b][0]), batched_inputs[b].get("width", sizes[b][1]))
-            results.append(self.nms_topk_postprocess(dict(det), sizes[b], out_size, do_postprocess))
+            if self.cfg.DD3D.INFERENCE.DO_BEV_NMS:
+                # core.py:134-160: 2-D NMS + top-k, then BEV NMS (per image = its own dummy group), then postprocess
+                from oracle.bev_nms_oracle import bev_nms_image
+                d = self.nms_topk_postprocess(dict(det), sizes[b], sizes[b], do_postprocess=False)
+                pq, pt = pose_of(batched_inputs[b])
+                keep = bev_nms_image(d, pq, pt, self.cfg.DD3D.INFERENCE.BEV_NMS_IOU_THRESH)
+                d = {k: v[keep] for k, v in d.items()}
+                results.append(self.postprocess(d, sizes[b], out_size) if do_postprocess else d)
+            else:
+                results.append(self.nms_topk_postprocess(dict(det), sizes[b], out_size, do_postprocess))
         if return_intermediates:
             return results, dict(batch=batch, features=feats, maps=maps, pre_nms=pre_nms, inv_K=inv_K, sizes=sizes)
         return results
+
+
+def pose_of(inp):
+    """(quat wxyz, tvec) of input["pose"] / input["extrinsics"] (core.py:141-144): Pose-like object or a (quat, tvec) pair."""
+    p = inp["pose"] if "pose" in inp else inp["extrinsics"]
+    if hasattr(p, "quat"):
+        return [float(v) for v in p.quat.elements], [float(v) for v in p.tvec]
+    return [float(v) for v in p[0]], [float(v) for v in p[1]]
 
 
 # ----------------------------------------------------------------------------------------------

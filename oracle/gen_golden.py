@@ -40,6 +40,38 @@ def case_inputs(arch):
     return inputs
 
 
+def reference_bev_keep(det, pose_quat, pose_tvec, thr):
+    """Runs the reference's own nuscenes_sample_aggregate (postprocessing.py:58-108, one dummy group per image, as
+    core.py:137-151 does) on one image's detections; returns (sorted kept indices, BEV rotated boxes)."""
+    ref_standin.install()
+    from tridet.layers.bev_nms import boxes3d_to_rotated_boxes
+    from tridet.modeling.dd3d.postprocessing import nuscenes_sample_aggregate
+    from tridet.structures.boxes3d import GenericBoxes3D
+    from tridet.structures.pose import Pose
+
+    class _B3(GenericBoxes3D):  # pred_boxes3d stand-in: only vectorize()/indexing/cat are used
+        def __getitem__(self, i):
+            return _B3(self.quat[i], self.tvec[i], self.size[i])
+
+        def __len__(self):
+            return self.quat.shape[0]
+
+        @classmethod
+        def cat(cls, l):
+            return _B3(torch.cat([b.quat for b in l]), torch.cat([b.tvec for b in l]), torch.cat([b.size for b in l]))
+
+    n = det["quat"].shape[0]
+    inst = ref_standin.Instances((100, 100))
+    inst.pred_boxes3d = _B3(det["quat"], det["tvec"], det["size"])
+    inst.pred_classes = det["cls"]
+    inst.scores_3d = det["score3d"]
+    inst.orig_index = torch.arange(n)
+    pose = Pose(wxyz=np.float32(pose_quat), tvec=np.float32(pose_tvec))
+    out = nuscenes_sample_aggregate([inst], {0: [0]}, 3, [pose], iou_threshold=thr, include_boxes3d_global=True)[0]
+    rot = boxes3d_to_rotated_boxes(out.pred_boxes3d_global, pose_cam_global=Pose()).tensor if len(out) else None
+    return out.orig_index, rot
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -64,6 +96,24 @@ def main():
             })
             print(arch, "image", b, "detections", len(inst))
         np.savez_compressed(os.path.join(out_dir, f"golden_{arch}.npz"), **blob)
+
+    # BEV rotated NMS: reference nuscenes_sample_aggregate on seeded random boxes / poses
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_bev_nms import _random_case
+    from oracle import bev_nms_oracle
+    blob = {"num_cases": 4, "thr": 0.3}
+    for c in range(4):
+        det, pq, pt = _random_case(100 + c, 30 + 10 * c)
+        keep, _ = reference_bev_keep(det, pq, pt, 0.3)
+        q, t = bev_nms_oracle.to_global(det["quat"], det["tvec"], pq, pt)
+        from tridet.structures.boxes3d import GenericBoxes3D
+        from tridet.layers.bev_nms import boxes3d_to_rotated_boxes
+        from tridet.structures.pose import Pose
+        blob[f"n{c}"] = 30 + 10 * c
+        blob[f"keep{c}"] = keep.numpy()
+        blob[f"rot{c}"] = boxes3d_to_rotated_boxes(GenericBoxes3D(q, t, det["size"]), pose_cam_global=Pose()).tensor.numpy()
+        print("bev case", c, "kept", len(keep), "of", 30 + 10 * c)
+    np.savez_compressed(os.path.join(out_dir, "bev_nms.npz"), **blob)
 
     # known-answer test for the 3-D decode, inputs from SURVEY.md 8c (reference function called verbatim)
     ref_standin.install()

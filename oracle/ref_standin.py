@@ -115,8 +115,20 @@ def batched_nms(boxes, scores, idxs, iou_threshold):
     return _nms_greedy(boxes_for_nms, scores, iou_threshold)
 
 
-def batched_nms_rotated(*args, **kwargs):
-    raise NotImplementedError("rotated NMS is outside the round-1 scope (SURVEY.md 8f)")
+def batched_nms_rotated(boxes, scores, idxs, iou_threshold):
+    """detectron2.layers.nms.batched_nms_rotated: shift the centres by a per-class offset so that boxes of different
+    classes never overlap, then greedy rotated NMS (restated in oracle/bev_nms_oracle.py)."""
+    assert boxes.shape[-1] == 5
+    if boxes.numel() == 0:
+        return torch.empty((0, ), dtype=torch.int64, device=boxes.device)
+    from oracle.bev_nms_oracle import nms_rotated
+    boxes = boxes.float()
+    max_coordinate = (torch.max(boxes[:, 0], boxes[:, 1]) + torch.max(boxes[:, 2], boxes[:, 3]) / 2).max()
+    min_coordinate = (torch.min(boxes[:, 0], boxes[:, 1]) - torch.max(boxes[:, 2], boxes[:, 3]) / 2).min()
+    offsets = idxs.to(boxes) * (max_coordinate - min_coordinate + 1)
+    boxes_for_nms = boxes.clone()
+    boxes_for_nms[:, :2] += offsets[:, None]
+    return nms_rotated(boxes_for_nms, scores, torch.zeros_like(idxs), iou_threshold)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -179,8 +191,17 @@ class Boxes:
         return self.tensor.device
 
 
-class RotatedBoxes(Boxes):
-    pass
+class RotatedBoxes:
+    """detectron2.structures.RotatedBoxes subset: (N, 5) = (cx, cy, w, h, angle_degrees)."""
+    def __init__(self, tensor):
+        tensor = torch.as_tensor(tensor, dtype=torch.float32)
+        if tensor.numel() == 0:
+            tensor = tensor.reshape((0, 5))
+        assert tensor.dim() == 2 and tensor.size(-1) == 5, tensor.size()
+        self.tensor = tensor
+
+    def __len__(self):
+        return self.tensor.shape[0]
 
 
 class Instances:
@@ -214,6 +235,9 @@ class Instances:
 
     def has(self, name):
         return name in self._fields
+
+    def remove(self, name):
+        del self._fields[name]
 
     def get(self, name):
         return self._fields[name]
@@ -509,6 +533,62 @@ def matrix_to_quaternion(matrix):
     return quat_candidates[F.one_hot(q_abs.argmax(dim=-1), num_classes=4) > 0.5, :].reshape(batch_dim + (4, ))
 
 
+class Quaternion:
+    """Minimal pyquaternion.Quaternion (w, x, y, z) -- the subset tridet/structures/pose.py uses."""
+    def __init__(self, *args, matrix=None):
+        import numpy as np
+        if matrix is not None:
+            m = np.asarray(matrix, dtype=np.float64)[:3, :3]
+            q = matrix_to_quaternion(torch.tensor(m, dtype=torch.float64)[None])[0].numpy()
+            if q[0] < 0:
+                q = -q
+            self.q = q / np.linalg.norm(q)
+        elif len(args) == 1 and isinstance(args[0], Quaternion):
+            self.q = args[0].q.copy()
+        elif len(args) == 1:
+            self.q = np.asarray(args[0], dtype=np.float64).copy()
+        else:
+            self.q = np.array([1.0, 0.0, 0.0, 0.0])
+
+    @property
+    def elements(self):
+        return self.q
+
+    @property
+    def rotation_matrix(self):
+        return quaternion_to_matrix(torch.tensor(self.q)[None])[0].numpy()
+
+    @property
+    def transformation_matrix(self):
+        import numpy as np
+        m = np.eye(4)
+        m[:3, :3] = self.rotation_matrix
+        return m
+
+    @property
+    def inverse(self):
+        import numpy as np
+        return Quaternion(self.q * np.array([1.0, -1.0, -1.0, -1.0]) / np.dot(self.q, self.q))
+
+    def rotate(self, v):
+        import numpy as np
+        return self.rotation_matrix @ np.asarray(v, dtype=np.float64)
+
+    def __mul__(self, o):
+        import numpy as np
+        a, b = self.q, o.q
+        return Quaternion(np.array([
+            a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+            a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]]))
+
+    def __eq__(self, o):
+        import numpy as np
+        return bool(np.allclose(self.q, o.q))
+
+    def __repr__(self):
+        return "%.3f %+.3fi %+.3fj %+.3fk" % tuple(self.q)
+
+
 class _Transform3d:
     """Row-vector convention: p' = [p, 1] @ M. compose(a, b) applies a then b."""
     def __init__(self, matrix):
@@ -530,7 +610,14 @@ class _Transform3d:
         return out[..., :3] / out[..., 3:]
 
 
+def Transform3d(matrix=None, device="cpu", dtype=torch.float32):
+    m = matrix if matrix.dim() == 3 else matrix[None]
+    return _Transform3d(m)
+
+
 def Rotate(R, device="cpu", dtype=torch.float32):
+    if R.dim() == 2:
+        R = R[None]
     n = R.shape[0]
     m = torch.eye(4, dtype=R.dtype, device=R.device).repeat(n, 1, 1)
     m[:, :3, :3] = R
@@ -593,13 +680,10 @@ def install(reference_root=REFERENCE_ROOT):
 
     rc = _mod("pytorch3d.transforms.rotation_conversions", quaternion_to_matrix=quaternion_to_matrix,
               matrix_to_quaternion=matrix_to_quaternion)
-    t3d = _mod("pytorch3d.transforms.transform3d", Rotate=Rotate, Translate=Translate)
+    t3d = _mod("pytorch3d.transforms.transform3d", Rotate=Rotate, Translate=Translate, Transform3d=Transform3d)
     _mod("pytorch3d")
     _mod("pytorch3d.transforms", rotation_conversions=rc, transform3d=t3d,
          quaternion_to_matrix=quaternion_to_matrix, matrix_to_quaternion=matrix_to_quaternion)
-
-    class Quaternion:  # pyquaternion: only used for isinstance checks on the hot path
-        pass
 
     _mod("pyquaternion", Quaternion=Quaternion)
     _mod("mpi4py", MPI=types.SimpleNamespace(COMM_WORLD=None))
@@ -616,12 +700,12 @@ def install(reference_root=REFERENCE_ROOT):
         m.__spec__ = importlib.machinery.ModuleSpec(pkg, None, is_package=True)
         sys.modules[pkg] = m
     # tridet.layers.__init__ exports (bev_nms needs detectron2 rotated NMS: stubbed above)
-    _mod("tridet.structures.pose", Pose=type("Pose", (), {}))
     from tridet.layers.iou_loss import IOULoss  # noqa: E402
     from tridet.layers.smooth_l1_loss import smooth_l1_loss  # noqa: E402
     sys.modules["tridet.layers"].IOULoss = IOULoss
     sys.modules["tridet.layers"].smooth_l1_loss = smooth_l1_loss
-    sys.modules["tridet.layers"].bev_nms = _noop
+    from tridet.layers.bev_nms import bev_nms  # noqa: E402  (the reference's own BEV NMS, rotated IoU from the stand-in)
+    sys.modules["tridet.layers"].bev_nms = bev_nms
     _mod("tridet.utils.comm", reduce_sum=lambda x: x, get_world_size=lambda: 1)
 
 
