@@ -134,7 +134,17 @@ def param_specs(cfg):
         specs[f"fcos3d_head.scales_conf.{l}.scale"] = ((1, ), "scalar:one")
         specs[f"fcos3d_head.scales_depth.{l}.scale"] = ((1, ), "scalar:depth")
         specs[f"fcos3d_head.offsets_depth.{l}.bias"] = ((1, ), "scalar:depth_offset")
+    if is_nuscenes_arch(cfg):  # nuscenes_dd3d.py:311-312 (appended last: the synthetic generator stream of the rest is unchanged)
+        _conv(specs, "attr_logits", MAX_NUM_ATTRIBUTES, 256, 3, bias=True, role="attr")
+        _conv(specs, "speed", 1, 256, 3, bias=True, role="speed")
     return specs
+
+
+MAX_NUM_ATTRIBUTES = 3  # tridet/data/datasets/nuscenes/build.py:77
+
+
+def is_nuscenes_arch(cfg):
+    return cfg.MODEL.META_ARCHITECTURE == "NuscenesDD3D"
 
 
 def arch_of(cfg):

@@ -83,8 +83,9 @@ _FEATURE_EXTRACTORS = {
 }
 
 
-def get_cfg(backbone="dla34", dataset="kitti_3d", nms_thresh=0.75):
-    """backbone in {"dla34", "v2_99"}; dataset in {"kitti_3d", "nuscenes"} (head constants only)."""
+def get_cfg(backbone="dla34", dataset="kitti_3d", nms_thresh=0.75, meta_arch="DD3D"):
+    """backbone in {"dla34", "v2_99"}; dataset in {"kitti_3d", "nuscenes"} (head constants only); meta_arch in
+    {"DD3D", "NuscenesDD3D"} (configs/experiments/dd3d_nusc_{dla34,v99}.yaml:9,30-36)."""
     ds = _DATASETS[dataset]
     fe = copy.deepcopy(_FEATURE_EXTRACTORS[backbone])
     fe["FPN"] = dict(IN_FEATURES=list(fe["BACKBONE"]["OUT_FEATURES"]), OUT_FEATURES=None, OUT_CHANNELS=256,
@@ -94,7 +95,7 @@ def get_cfg(backbone="dla34", dataset="kitti_3d", nms_thresh=0.75):
         INPUT=dict(FORMAT="BGR"),
         MODEL=dict(
             DEVICE="cuda",
-            META_ARCHITECTURE="DD3D",
+            META_ARCHITECTURE=meta_arch,
             PIXEL_MEAN=[103.530, 116.280, 123.675],
             PIXEL_STD=[57.375, 57.120, 58.395],
             CKPT="",
@@ -144,6 +145,11 @@ def get_cfg(backbone="dla34", dataset="kitti_3d", nms_thresh=0.75):
                           WEIGHT_BOX3D=2.0, WEIGHT_CONF3D=1.0),
                 PREPARE_TARGET=dict(CENTER_SAMPLE=True, POS_RADIUS=1.5),
             ),
+            NUSC=dict(
+                LOSS=dict(WEIGHT_ATTR=0.2, WEIGHT_SPEED=0.2),
+                INFERENCE=dict(NUM_IMAGES_PER_SAMPLE=6, MAX_NUM_DETS_PER_SAMPLE=500),
+            ),
         ),
+        DATALOADER=dict(TEST=dict(NUM_IMAGES_PER_GROUP=6)),
     )
     return _to_node(cfg)

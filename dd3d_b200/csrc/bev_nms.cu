@@ -141,6 +141,273 @@ __device__ void quat_to_mat3(const float* q, float* R) {  // pytorch3d quaternio
     R[6] = two_s * (i * k - j * r); R[7] = two_s * (j * k + i * r); R[8] = 1.f - two_s * (i * i + j * j);
 }
 
+// pytorch3d matrix_to_quaternion (rotation_conversions.py): best-conditioned of the four candidates, real part first,
+// no sign standardisation -- the quaternion the reference stores in pred_boxes3d_global (postprocessing.py:43-46).
+__device__ void mat3_to_quat(const float* m, float* q) {
+    const float arg[4] = {1.f + m[0] + m[4] + m[8], 1.f + m[0] - m[4] - m[8], 1.f - m[0] + m[4] - m[8],
+                          1.f - m[0] - m[4] + m[8]};
+    float qa[4];
+    int best = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        qa[i] = arg[i] > 0.f ? sqrtf(arg[i]) : 0.f;
+        if (qa[i] > qa[best]) best = i;
+    }
+    const float c[4][4] = {{qa[0] * qa[0], m[7] - m[5], m[2] - m[6], m[3] - m[1]},
+                           {m[7] - m[5], qa[1] * qa[1], m[3] + m[1], m[2] + m[6]},
+                           {m[2] - m[6], m[3] + m[1], qa[2] * qa[2], m[5] + m[7]},
+                           {m[3] - m[1], m[6] + m[2], m[7] + m[5], qa[3] * qa[3]}};
+    const float den = 2.0f * fmaxf(qa[best], 0.1f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = c[best][i] / den;
+}
+
+__device__ void invert_K(const float* K, float* iK) {  // adjugate in double, like decode.cu
+    const double a = K[0], bb = K[1], c = K[2], d = K[3], e = K[4], f = K[5], g = K[6], h = K[7], i9 = K[8];
+    const double A = e * i9 - f * h, Bc = -(d * i9 - f * g), Cc = d * h - e * g;
+    const double rdet = 1.0 / (a * A + bb * Bc + c * Cc);
+    iK[0] = static_cast<float>(A * rdet);
+    iK[1] = static_cast<float>(-(bb * i9 - c * h) * rdet);
+    iK[2] = static_cast<float>((bb * f - c * e) * rdet);
+    iK[3] = static_cast<float>(Bc * rdet);
+    iK[4] = static_cast<float>((a * i9 - c * g) * rdet);
+    iK[5] = static_cast<float>(-(a * f - c * d) * rdet);
+    iK[6] = static_cast<float>(Cc * rdet);
+    iK[7] = static_cast<float>(-(a * h - bb * g) * rdet);
+    iK[8] = static_cast<float>((a * e - bb * d) * rdet);
+}
+
+// One decoded box -> global rotation / translation (postprocessing.py:25-46) and its BEV top-surface rectangle
+// (boxes3d.py:47-64, bev_nms.py:71-96).
+__device__ void box_to_global(const Det& D, const float* iK, const float* Rw, const float* pose_t, float* R, float* t,
+                              float* rect) {
+    const float u = D.proj_ctr[0], v = D.proj_ctr[1];
+    const float tv[3] = {(iK[0] * u + iK[1] * v + iK[2]) * D.depth, (iK[3] * u + iK[4] * v + iK[5]) * D.depth,
+                         (iK[6] * u + iK[7] * v + iK[8]) * D.depth};
+    float Rs[9];
+    quat_to_mat3(D.quat, Rs);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) R[r * 3 + cc] = Rw[r * 3] * Rs[cc] + Rw[r * 3 + 1] * Rs[3 + cc] + Rw[r * 3 + 2] * Rs[6 + cc];
+        t[r] = Rw[r * 3] * tv[0] + Rw[r * 3 + 1] * tv[1] + Rw[r * 3 + 2] * tv[2] + pose_t[r];
+    }
+    const float hl = 0.5f * D.size[1], hw = 0.5f * D.size[0], hh = 0.5f * D.size[2];  // (l, w, h) = size[1, 0, 2]
+    // corners 0, 1, 5, 4 of the template: (+l,+w,+h), (+l,-w,+h), (-l,-w,+h), (-l,+w,+h)
+    const float sx[4] = {hl, hl, -hl, -hl}, sy[4] = {hw, -hw, -hw, hw};
+    float bx[4], by[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float X = R[0] * sx[k] + R[1] * sy[k] + R[2] * hh + t[0];
+        const float Y = R[3] * sx[k] + R[4] * sy[k] + R[5] * hh + t[1];
+        bx[k] = -Y;  // VEHICLE_TO_BEV_ROTATION: (x, y)_bev = (-Y, -X)
+        by[k] = -X;
+    }
+    const float fx = bx[0] - bx[3], fy = by[0] - by[3];
+    rect[0] = 0.5f * (bx[0] + bx[2]);
+    rect[1] = 0.5f * (by[0] + by[2]);
+    rect[2] = sqrtf((bx[0] - bx[1]) * (bx[0] - bx[1]) + (by[0] - by[1]) * (by[0] - by[1]));  // width
+    rect[3] = sqrtf(fx * fx + fy * fy);                                                        // length
+    rect[4] = atan2f(fx, fy) * 57.29577951308232f;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// NuscenesDD3D sample aggregation (nuscenes_dd3d.py:449-463 -> postprocessing.py:58-108): rotated NMS jointly over the
+// cameras of one sample.  Kernel 1: one CTA per sample group (sort by scores_3d, pairwise IoU bit matrix, greedy scan);
+// kernel 2: one CTA per image (cap on the survivors of the whole call, order-preserving compaction).
+constexpr int kGrpMax = 768;      // boxes per sample group (6 cameras x out_cap 128)
+constexpr int kGrpSort = 1024;
+constexpr int kGrpThreads = 256;
+constexpr int kGrpImages = 16;    // cameras per sample the kernel can hold
+constexpr int kGrpWords = kGrpMax / 64;
+
+struct AggParams {
+    Det* dets;             // [B][cap]
+    int32_t* counts;       // [B]
+    const float* K;        // [B][9]
+    const float* poses;    // [B][7]
+    const int32_t* group;  // [B] sample group of each image
+    float* global;         // [B][cap][10] : global quat (w,x,y,z), global tvec, size (pred_boxes3d_global)
+    float* keep_score;     // [B][cap] scratch: scores_3d of the NMS survivors, -1 elsewhere
+    int32_t* flags;        // bit 3: a group had more than kGrpMax boxes / kGrpImages images
+    int B, cap, max_dets;
+    float thr;
+};
+
+struct GrpSmem {
+    unsigned long long mask[kGrpMax][kGrpWords];
+    unsigned long long key[kGrpSort];
+    float rect[kGrpMax][5];
+    int cls[kGrpMax];
+    uint32_t src[kGrpMax];  // image << 16 | slot
+    int imgs[kGrpImages];
+    int offs[kGrpImages + 1];
+    int nimg;
+};
+
+__global__ void __launch_bounds__(kGrpThreads) sample_nms_kernel(const AggParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GrpSmem& S = *reinterpret_cast<GrpSmem*>(smem_raw);
+    const int g = blockIdx.x;
+    if (threadIdx.x == 0) {
+        int m = 0, total = 0;
+        S.offs[0] = 0;
+        for (int b = 0; b < p.B; ++b) {
+            if (p.group[b] != g) continue;
+            if (m == kGrpImages) {
+                atomicOr(p.flags, 8);
+                break;
+            }
+            int c = min(p.counts[b], p.cap);
+            if (total + c > kGrpMax) {
+                atomicOr(p.flags, 8);
+                c = kGrpMax - total;
+            }
+            S.imgs[m] = b;
+            total += c;
+            S.offs[++m] = total;
+        }
+        S.nimg = m;
+    }
+    __syncthreads();
+    const int nimg = S.nimg, n = S.offs[nimg];
+    // ---- 1. boxes to the global frame, BEV rectangles, sort keys; keep_score = -1 on every slot of the group's images
+    for (int m = 0; m < nimg; ++m)
+        for (int s = threadIdx.x; s < p.cap; s += blockDim.x) p.keep_score[static_cast<size_t>(S.imgs[m]) * p.cap + s] = -1.0f;
+    for (int i = threadIdx.x; i < kGrpSort; i += blockDim.x) S.key[i] = ~0ull;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int m = 0;
+        while (i >= S.offs[m + 1]) ++m;
+        const int b = S.imgs[m], slot = i - S.offs[m];
+        const Det& D = p.dets[static_cast<size_t>(b) * p.cap + slot];
+        float iK[9], Rw[9], R[9], t[3], q[4];
+        invert_K(p.K + b * 9, iK);
+        quat_to_mat3(p.poses + b * 7, Rw);
+        box_to_global(D, iK, Rw, p.poses + b * 7 + 4, R, t, S.rect[i]);
+        mat3_to_quat(R, q);
+        float* go = p.global + (static_cast<size_t>(b) * p.cap + slot) * 10;
+        go[0] = q[0]; go[1] = q[1]; go[2] = q[2]; go[3] = q[3];
+        go[4] = t[0]; go[5] = t[1]; go[6] = t[2];
+        go[7] = D.size[0]; go[8] = D.size[1]; go[9] = D.size[2];
+        S.cls[i] = D.cls;
+        S.src[i] = (static_cast<uint32_t>(b) << 16) | static_cast<uint32_t>(slot);
+        // descending scores_3d (non-negative floats order like their bit patterns), ties by concatenation index
+        S.key[i] = (static_cast<unsigned long long>(~__float_as_uint(D.score3d)) << 32) | static_cast<unsigned>(i);
+    }
+    for (int i = threadIdx.x; i < kGrpMax * kGrpWords; i += blockDim.x) (&S.mask[0][0])[i] = 0ull;
+    __syncthreads();
+    // ---- 2. bitonic sort of the keys
+    for (int k = 2; k <= kGrpSort; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < kGrpSort; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = S.key[i], b2 = S.key[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b2) == up) {
+                        S.key[i] = b2;
+                        S.key[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    // ---- 3. pairwise rotated IoU in sorted order (same class; same sample by construction)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int ri = warp; ri < n; ri += kGrpThreads / 32) {
+        const int i = static_cast<int>(S.key[ri] & 0xffffffffull);
+        for (int rj = ri + 1 + lane; rj < n; rj += 32) {
+            const int j = static_cast<int>(S.key[rj] & 0xffffffffull);
+            if (S.cls[i] == S.cls[j] && rotated_iou(S.rect[i], S.rect[j]) > p.thr)
+                atomicOr(&S.mask[ri][rj >> 6], 1ull << (rj & 63));
+        }
+    }
+    __syncthreads();
+    // ---- 4. greedy scan; survivors publish their score
+    if (threadIdx.x == 0) {
+        unsigned long long removed[kGrpWords];
+#pragma unroll
+        for (int w = 0; w < kGrpWords; ++w) removed[w] = 0ull;
+        for (int r = 0; r < n; ++r) {
+            if ((removed[r >> 6] >> (r & 63)) & 1ull) continue;
+#pragma unroll
+            for (int w = 0; w < kGrpWords; ++w) removed[w] |= S.mask[r][w];
+            const int i = static_cast<int>(S.key[r] & 0xffffffffull);
+            const uint32_t src = S.src[i];
+            const size_t at = static_cast<size_t>(src >> 16) * p.cap + (src & 0xffffu);
+            p.keep_score[at] = p.dets[at].score3d;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBevThreads) sample_compact_kernel(const AggParams p) {
+    __shared__ unsigned char keep[kBevMax];
+    __shared__ int new_pos[kBevMax];
+    __shared__ int s_total;
+    const int b = blockIdx.x;
+    const int n = min(min(p.counts[b], p.cap), kBevMax);
+    const size_t all = static_cast<size_t>(p.B) * p.cap;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    // survivors of the whole call (keep = keep[:max_dets] is applied to the concatenation of ALL images of the call,
+    // postprocessing.py:87-93)
+    int part = 0;
+    for (size_t i = threadIdx.x; i < all; i += blockDim.x) part += p.keep_score[i] >= 0.f;
+    atomicAdd(&s_total, part);
+    __syncthreads();
+    const bool capped = p.max_dets > 0 && s_total > p.max_dets;
+    __syncthreads();
+    for (int s = threadIdx.x; s < kBevMax; s += blockDim.x) {
+        bool k = false;
+        if (s < n) {
+            const size_t me = static_cast<size_t>(b) * p.cap + s;
+            const float sc = p.keep_score[me];
+            k = sc >= 0.f;
+            if (k && capped) {  // rank among the survivors in the NMS output order: score desc, concatenation index asc
+                int rank = 0;
+                for (size_t i = 0; i < all; ++i) {
+                    const float o = p.keep_score[i];
+                    rank += (o > sc) || (o == sc && i < me);
+                }
+                k = rank < p.max_dets;
+            }
+        }
+        keep[s] = k ? 1 : 0;
+    }
+    __syncthreads();
+    Det mine[kBevMax / kBevThreads];
+    float gl[kBevMax / kBevThreads][10];
+    for (int s = 0; s < kBevMax / kBevThreads; ++s) {
+        const int i = threadIdx.x + s * kBevThreads;
+        if (i < n && keep[i]) {
+            mine[s] = p.dets[static_cast<size_t>(b) * p.cap + i];
+            const float* go = p.global + (static_cast<size_t>(b) * p.cap + i) * 10;
+#pragma unroll
+            for (int t = 0; t < 10; ++t) gl[s][t] = go[t];
+        }
+    }
+    if (threadIdx.x == 0) {
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            new_pos[i] = m;
+            m += keep[i];
+        }
+        s_total = m;
+    }
+    __syncthreads();
+    for (int s = 0; s < kBevMax / kBevThreads; ++s) {
+        const int i = threadIdx.x + s * kBevThreads;
+        if (i < n && keep[i]) {
+            p.dets[static_cast<size_t>(b) * p.cap + new_pos[i]] = mine[s];
+            float* go = p.global + (static_cast<size_t>(b) * p.cap + new_pos[i]) * 10;
+#pragma unroll
+            for (int t = 0; t < 10; ++t) go[t] = gl[s][t];
+        }
+    }
+    if (threadIdx.x == 0) p.counts[b] = s_total;
+}
+
 struct BevParams {
     Det* dets;             // [B][cap], compacted in place
     int32_t* counts;       // [B]
@@ -171,46 +438,12 @@ __global__ void __launch_bounds__(kBevThreads) bev_nms_kernel(const BevParams p)
     const float* pose = p.poses + b * 7;
     float Rw[9];
     quat_to_mat3(pose, Rw);
-    // inverse intrinsics (adjugate in double, like decode.cu)
-    const double a = K[0], bb = K[1], c = K[2], d = K[3], e = K[4], f = K[5], g = K[6], h = K[7], i9 = K[8];
-    const double A = e * i9 - f * h, Bc = -(d * i9 - f * g), Cc = d * h - e * g;
-    const double rdet = 1.0 / (a * A + bb * Bc + c * Cc);
-    const float iK[9] = {static_cast<float>(A * rdet), static_cast<float>(-(bb * i9 - c * h) * rdet),
-                         static_cast<float>((bb * f - c * e) * rdet), static_cast<float>(Bc * rdet),
-                         static_cast<float>((a * i9 - c * g) * rdet), static_cast<float>(-(a * f - c * d) * rdet),
-                         static_cast<float>(Cc * rdet), static_cast<float>(-(a * h - bb * g) * rdet),
-                         static_cast<float>((a * e - bb * d) * rdet)};
+    float iK[9];
+    invert_K(K, iK);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const Det& D = dets[i];
-        const float u = D.proj_ctr[0], v = D.proj_ctr[1];
-        const float tv[3] = {(iK[0] * u + iK[1] * v + iK[2]) * D.depth, (iK[3] * u + iK[4] * v + iK[5]) * D.depth,
-                             (iK[6] * u + iK[7] * v + iK[8]) * D.depth};
-        float Rs[9], R[9], t[3];
-        quat_to_mat3(D.quat, Rs);
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) R[r * 3 + cc] = Rw[r * 3] * Rs[cc] + Rw[r * 3 + 1] * Rs[3 + cc] + Rw[r * 3 + 2] * Rs[6 + cc];
-            t[r] = Rw[r * 3] * tv[0] + Rw[r * 3 + 1] * tv[1] + Rw[r * 3 + 2] * tv[2] + pose[4 + r];
-        }
-        const float hl = 0.5f * D.size[1], hw = 0.5f * D.size[0], hh = 0.5f * D.size[2];  // (l, w, h) = size[1, 0, 2]
-        // corners 0, 1, 5, 4 of the template: (+l,+w,+h), (+l,-w,+h), (-l,-w,+h), (-l,+w,+h)
-        const float sx[4] = {hl, hl, -hl, -hl}, sy[4] = {hw, -hw, -hw, hw};
-        float bx[4], by[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float X = R[0] * sx[k] + R[1] * sy[k] + R[2] * hh + t[0];
-            const float Y = R[3] * sx[k] + R[4] * sy[k] + R[5] * hh + t[1];
-            bx[k] = -Y;  // VEHICLE_TO_BEV_ROTATION: (x, y)_bev = (-Y, -X)
-            by[k] = -X;
-        }
-        const float fx = bx[0] - bx[3], fy = by[0] - by[3];
-        rect[i][0] = 0.5f * (bx[0] + bx[2]);
-        rect[i][1] = 0.5f * (by[0] + by[2]);
-        rect[i][2] = sqrtf((bx[0] - bx[1]) * (bx[0] - bx[1]) + (by[0] - by[1]) * (by[0] - by[1]));  // width
-        rect[i][3] = sqrtf(fx * fx + fy * fy);                                                        // length
-        rect[i][4] = atan2f(fx, fy) * 57.29577951308232f;
-        cls[i] = D.cls;
+        float R[9], t[3];
+        box_to_global(dets[i], iK, Rw, pose + 4, R, t, rect[i]);
+        cls[i] = dets[i].cls;
     }
     for (int i = threadIdx.x; i < kBevMax * (kBevMax / 64); i += blockDim.x) (&mask[0][0])[i] = 0ull;
     __syncthreads();
@@ -282,6 +515,37 @@ cudaError_t launch_bev_nms(Det* dets, int32_t* counts, const float* K, const flo
     p.do_postprocess = do_postprocess;
     p.thr = thr;
     bev_nms_kernel<<<B, kBevThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+size_t sample_aggregate_scratch_bytes(int B, int cap) { return static_cast<size_t>(B) * cap * sizeof(float); }
+
+cudaError_t launch_sample_aggregate(Det* dets, int32_t* counts, const float* K, const float* poses, const int32_t* group,
+                                    int num_groups, float* global, void* scratch, int32_t* flags, int B, int cap,
+                                    float thr, int max_dets, cudaStream_t stream) {
+    if (cap > kBevMax || B >= 65536) return cudaErrorInvalidValue;
+    AggParams p;
+    p.dets = dets;
+    p.counts = counts;
+    p.K = K;
+    p.poses = poses;
+    p.group = group;
+    p.global = global;
+    p.keep_score = static_cast<float*>(scratch);
+    p.flags = flags;
+    p.B = B;
+    p.cap = cap;
+    p.max_dets = max_dets;
+    p.thr = thr;
+    static bool configured = false;
+    if (!configured) {
+        const cudaError_t e = cudaFuncSetAttribute(sample_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(sizeof(GrpSmem)));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    sample_nms_kernel<<<num_groups, kGrpThreads, sizeof(GrpSmem), stream>>>(p);
+    sample_compact_kernel<<<B, kBevThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

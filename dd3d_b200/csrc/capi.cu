@@ -312,6 +312,22 @@ int dd3d_op_bev_nms(dd3d_det* d_dets, int32_t* d_counts, const float* d_intrinsi
                        nullptr);
 }
 
+int64_t dd3d_op_sample_aggregate_scratch_bytes(int B, int cap) {
+    return static_cast<int64_t>(sample_aggregate_scratch_bytes(B, cap));
+}
+
+int dd3d_op_sample_aggregate(dd3d_det* d_dets, int32_t* d_counts, const float* d_intrinsics, const float* d_poses,
+                             const int32_t* d_group, int num_groups, float* d_global, void* d_scratch, int32_t* d_flags,
+                             int B, int cap, float iou_thresh, int max_dets, dd3d_stream stream) {
+    if (!d_dets || !d_counts || !d_intrinsics || !d_poses || !d_group || !d_global || !d_scratch || !d_flags || B < 1 ||
+        cap < 1 || cap > 256 || num_groups < 1 || num_groups > B)
+        return DD3D_ERR_INVALID;
+    return cuda_status(launch_sample_aggregate(reinterpret_cast<Det*>(d_dets), d_counts, d_intrinsics, d_poses, d_group,
+                                               num_groups, d_global, d_scratch, d_flags, B, cap, iou_thresh, max_dets,
+                                               static_cast<cudaStream_t>(stream)),
+                       nullptr);
+}
+
 int64_t dd3d_op_detect_scratch_bytes(int B, int pre_nms_topk) {
     return static_cast<int64_t>(decode_scratch_bytes(B, pre_nms_topk)) + DD3D_MAX_CLASSES * 3 * 4 + 256;
 }

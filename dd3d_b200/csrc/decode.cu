@@ -229,7 +229,21 @@ __device__ void decode_one(const DecodeParams& p, const DecodeLevel& L, int b, i
     d.loc[0] = lx;
     d.loc[1] = ly;
     d.index = index;
-    d.pad[0] = d.pad[1] = d.pad[2] = 0;
+    d.attr = 0;
+    d.speed = 0.f;
+    d.pad = 0;
+    if (p.attr_off >= 0) {  // NuscenesInference (nuscenes_dd3d.py:268-298): first maximum like torch.argmax
+        const float* a = L.cls + gp * p.cls_pitch + p.attr_off;
+        float best = __ldg(a);
+        for (int t = 1; t < p.num_attr; ++t) {
+            const float v = __ldg(a + t);
+            if (v > best) {
+                best = v;
+                d.attr = t;
+            }
+        }
+        d.speed = __ldg(a + p.num_attr);
+    }
 
     const float* g = L.b3d + gp * p.b3d_pitch + c;
     const int C = p.C;

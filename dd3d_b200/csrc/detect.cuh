@@ -7,6 +7,7 @@
 namespace dd3d {
 
 constexpr int kLevels = 5;
+constexpr int kNumAttributes = 3;  // MAX_NUM_ATTRIBUTES, tridet/data/datasets/nuscenes/build.py:77
 constexpr int kHistBins = 2048;
 constexpr int kBoundaryCap = 4096;  // candidates sharing the histogram bin of the k-th score (per image x level)
 
@@ -23,7 +24,9 @@ struct Det {
     float size[3];     // (W, L, H)
     float loc[2];      // feature location (x, y)
     int32_t index;     // pixel * num_classes + class at its level (deterministic tie-break key)
-    int32_t pad[3];
+    int32_t attr;      // NuscenesDD3D: argmax of the attribute logits at the pixel (nuscenes_dd3d.py:296), else 0
+    float speed;       // NuscenesDD3D: relu(speed conv) at the pixel (nuscenes_dd3d.py:297), else 0
+    int32_t pad;
 };
 static_assert(sizeof(Det) == 96, "Det must be 24 words");
 
@@ -38,6 +41,8 @@ struct DecodeLevel {
 struct DecodeParams {
     DecodeLevel lvl[kLevels];
     int B, C, cls_pitch, b3d_pitch;
+    int attr_off;       // NuscenesDD3D: channel of the first attribute logit in the cls map (speed follows), else -1
+    int num_attr;
     int topk;           // PRE_NMS_TOPK
     float thresh;       // PRE_NMS_THRESH
     int loc_offset_half;  // FEATURE_LOCATIONS_OFFSET == "half"
@@ -80,5 +85,12 @@ cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream);
 // BEV rotated NMS on the (already 2-D-NMSed, score-sorted) detections, in place; poses: [B][7] (w,x,y,z, tx,ty,tz).
 cudaError_t launch_bev_nms(Det* dets, int32_t* counts, const float* K, const float* poses, const int32_t* sizes,
                            int32_t* flags, int B, int cap, float thr, int do_postprocess, cudaStream_t stream);
+
+// NuscenesDD3D sample aggregation: BEV rotated NMS jointly over the images of each sample group, then the cap on the
+// survivors of the call; in place; global: [B][cap][10] pred_boxes3d_global rows; cap <= 256.
+size_t sample_aggregate_scratch_bytes(int B, int cap);
+cudaError_t launch_sample_aggregate(Det* dets, int32_t* counts, const float* K, const float* poses, const int32_t* group,
+                                    int num_groups, float* global, void* scratch, int32_t* flags, int B, int cap,
+                                    float thr, int max_dets, cudaStream_t stream);
 
 }  // namespace dd3d

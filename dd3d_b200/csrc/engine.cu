@@ -577,7 +577,8 @@ struct Builder {
     void build_heads(const std::vector<View>& feats) {
         const int C = E->desc.num_classes;
         const int L = static_cast<int>(feats.size());
-        const int cls_pitch = round_up(C, 16), b3d_pitch = round_up(11 * C, 16);
+        const bool nusc = E->desc.nuscenes_heads != 0;
+        const int cls_pitch = round_up(C + (nusc ? kNumAttributes + 1 : 0), 16), b3d_pitch = round_up(11 * C, 16);
         P->cls_pitch = cls_pitch;
         P->b3d_pitch = b3d_pitch;
         std::vector<View> cls_t, box_t, b3d_t;
@@ -592,10 +593,32 @@ struct Builder {
             P->lvl_h[l] = feats[l].H;
             P->lvl_w[l] = feats[l].W;
         }
-        // cls_logits (fcos2d.py:96,142): bias only, shared across levels
+        // cls_logits (fcos2d.py:96,142): bias only, shared across levels.  NuscenesDD3D adds attr_logits (3) and
+        // relu(speed) (1) on the same tower output (nuscenes_dd3d.py:311-312,380-383): fused as extra GEMM columns
+        // [cls C | attr 3 | speed 1] of the one predictor conv (still N = 16 for the 10 nuScenes classes).
         {
-            const ConvLayer& Lc = E->conv_layer("fcos2d_head.cls_logits", {"fcos2d_head.cls_logits"}, 256, 3);
-            const Epilogue& e = E->bn_epilogue("fcos2d_head.cls_logits|", "", "fcos2d_head.cls_logits.bias", C);
+            std::vector<std::string> names = {"fcos2d_head.cls_logits"};
+            if (nusc) {
+                names.push_back("attr_logits");
+                names.push_back("speed");
+            }
+            const ConvLayer& Lc = E->conv_layer(nusc ? "fcos2d_head.cls_logits+attr+speed" : "fcos2d_head.cls_logits",
+                                                names, 256, 3);
+            const std::string ekey = "fcos2d_head.cls_logits|";
+            if (E->epis.find(ekey) == E->epis.end()) {
+                std::vector<float> sc, bi, lo;
+                for (auto& n : names) {
+                    const HostTensor& b = E->weight(n + ".bias");
+                    for (float v : b.data) {
+                        sc.push_back(1.0f);
+                        bi.push_back(v);
+                        lo.push_back(n == "speed" ? 0.0f : -INFINITY);
+                    }
+                }
+                if (static_cast<int>(sc.size()) != Lc.cout) fail(DD3D_ERR_INVALID, "bad cls predictor bias shapes");
+                E->epilogue(ekey, sc, bi, nusc ? &lo : nullptr);
+            }
+            const Epilogue& e = E->epis.at(ekey);
             std::vector<SegSpec> segs(L);
             for (int l = 0; l < L; ++l) {
                 segs[l].in = cls_t[l];
@@ -823,6 +846,8 @@ void fill_decode_params(DecodeParams* dp, const dd3d_model_desc& desc, int B, in
     dp->C = desc.num_classes;
     dp->cls_pitch = cls_pitch;
     dp->b3d_pitch = b3d_pitch;
+    dp->attr_off = desc.nuscenes_heads ? desc.num_classes : -1;
+    dp->num_attr = kNumAttributes;
     dp->topk = desc.pre_nms_topk;
     dp->thresh = desc.pre_nms_thresh;
     dp->loc_offset_half = desc.feature_locations_offset_half;

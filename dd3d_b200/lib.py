@@ -36,6 +36,7 @@ class ModelDesc(C.Structure):
         ("predict_distance", C.c_int32),
         ("canonical_box3d_sizes", C.c_float * (MAX_CLASSES * 3)),
         ("out_cap", C.c_int32),
+        ("nuscenes_heads", C.c_int32),
     ]
 
 
@@ -66,6 +67,8 @@ SIGNATURES = {
     "dd3d_op_ese": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P]),
     "dd3d_op_ese_scratch_bytes": (_I64, [_I, _I, _I]),
     "dd3d_op_bev_nms": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, C.c_float, _I, _P]),
+    "dd3d_op_sample_aggregate_scratch_bytes": (_I64, [_I, _I]),
+    "dd3d_op_sample_aggregate": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, C.c_float, _I, _P]),
     "dd3d_op_detect_scratch_bytes": (_I64, [_I, _I]),
     "dd3d_op_detect": (_I, [C.POINTER(ModelDesc), _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(_P),
                             C.POINTER(_P), C.POINTER(_P), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -125,6 +128,8 @@ def desc_from_cfg(cfg, out_cap=None):
     if out_cap is None:
         out_cap = ((inf.POST_NMS_TOPK + 28 + 31) // 32 * 32) if cfg.DD3D.INFERENCE.DO_NMS else 5 * inf.PRE_NMS_TOPK
     d.out_cap = out_cap
+    from .arch import is_nuscenes_arch
+    d.nuscenes_heads = int(is_nuscenes_arch(cfg))
     return d
 
 

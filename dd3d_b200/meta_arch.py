@@ -14,8 +14,8 @@ import torch
 from torch import nn
 
 from . import lib as _lib
-from .arch import arch_of, param_specs, size_divisibility
-from .structures import Boxes, Boxes3D, Instances
+from .arch import arch_of, is_nuscenes_arch, param_specs, size_divisibility
+from .structures import Boxes, Boxes3D, GenericBoxes3D, Instances
 
 try:  # register next to the reference's DD3D when detectron2 is present (scripts/train.py:48 build_model)
     from detectron2.modeling.meta_arch.build import META_ARCH_REGISTRY  # type: ignore
@@ -27,6 +27,8 @@ class DD3DB200(nn.Module):
     def __init__(self, cfg):
         super().__init__()
         self.cfg = cfg
+        if is_nuscenes_arch(cfg) != isinstance(self, NuscenesDD3DB200):
+            raise ValueError(f"MODEL.META_ARCHITECTURE = {cfg.MODEL.META_ARCHITECTURE} does not match {type(self).__name__}")
         self.arch = arch_of(cfg)  # raises KeyError for an unknown FE.BUILDER like the reference registry
         if not cfg.MODEL.BOX3D_ON:
             raise NotImplementedError("DD3DB200 implements the BOX3D_ON configuration")
@@ -182,8 +184,10 @@ class DD3DB200(nn.Module):
             rows.append(q + t)
         return torch.tensor(rows, dtype=torch.float32)
 
-    def _wrap(self, out, counts, K, sizes, device):
-        """[B][cap][24] fp32 words + counts -> list[{"instances": Instances}] (fields: fcos2d.py:331-335, fcos3d.py:398)."""
+    def _wrap(self, out, counts, K, sizes, device, global_boxes=None):
+        """[B][cap][24] fp32 words + counts -> list[{"instances": Instances}] (fields: fcos2d.py:331-335, fcos3d.py:398;
+        NuscenesDD3D adds pred_attributes / pred_speeds, nuscenes_dd3d.py:296-297, and pred_boxes3d_global,
+        postprocessing.py:96-97)."""
         inv_K = torch.linalg.inv(K.reshape(-1, 3, 3).to(torch.float64)).to(torch.float32).to(device)
         results = []
         ints = out.view(torch.int32)
@@ -199,12 +203,22 @@ class DD3DB200(nn.Module):
             inst.pred_boxes3d = Boxes3D(d[:, 8:12].clone(), d[:, 12:14].clone(), d[:, 14:15].clone(),
                                         d[:, 15:18].clone(), inv_K[b][None].expand(n, 3, 3))
             inst.scores_3d = d[:, 5].clone()
+            if self._desc.nuscenes_heads:
+                inst.pred_attributes = di[:, 21].to(torch.int64)
+                inst.pred_speeds = d[:, 22].clone()
+            if global_boxes is not None:
+                gb = global_boxes[b, :n]
+                inst.pred_boxes3d_global = GenericBoxes3D(gb[:, 0:4].clone(), gb[:, 4:7].clone(), gb[:, 7:10].clone())
             results.append({"instances": inst})
         return results
 
     @torch.no_grad()
     def forward(self, batched_inputs):
         """Device path: inputs are moved to the GPU with torch, one small D2H (per-image counts) at the end."""
+        r = self._forward_device(batched_inputs)
+        return self._wrap(r["out"], r["counts"].cpu(), r["K"], r["sizes"], self._device)  # .cpu(): the only sync
+
+    def _forward_device(self, batched_inputs):
         device = self._device
         batch, K, sizes, shape, is_u8 = self._gather_inputs(batched_inputs, device)
         self._plan(*shape)
@@ -234,10 +248,10 @@ class DD3DB200(nn.Module):
                                       C.c_void_p(d_poses.data_ptr()), C.c_void_p(d_sizes.data_ptr()),
                                       C.c_void_p(self._bev_flags.data_ptr()), B, cap, float(self.bev_nms_iou_thresh),
                                       int(self.postprocess_in_inference), C.c_void_p(stream)), self._handle)
-            counts_h = counts.cpu()  # the only synchronisation
-        return self._wrap(out, counts_h, K, sizes, device)
+        return dict(out=out, counts=counts, K=K, sizes=sizes, d_K=d_K, B=B, cap=cap, stream=stream)
 
-    __call__ = forward
+    def __call__(self, batched_inputs):
+        return self.forward(batched_inputs)
 
     @torch.no_grad()
     def forward_host(self, batched_inputs):
@@ -312,6 +326,73 @@ class DD3DB200(nn.Module):
         return flags.value
 
 
+def group_indices(sample_tokens, num_images_per_sample):
+    """get_group_idxs (postprocessing.py:111-123): group index of every image, groups numbered in order of first
+    appearance; every sample must have exactly `num_images_per_sample` images in the call."""
+    order = {}
+    for t in sample_tokens:
+        order.setdefault(t, len(order))
+    sizes = {t: 0 for t in order}
+    for t in sample_tokens:
+        sizes[t] += 1
+    if not all(s == num_images_per_sample for s in sizes.values()):
+        raise ValueError(f"Group sizes does not match with 'num_images_per_sample'. {sizes}")
+    return [order[t] for t in sample_tokens]
+
+
+class NuscenesDD3DB200(DD3DB200):
+    """Mirror of ``tridet.modeling.dd3d.nuscenes_dd3d.NuscenesDD3D`` (nuscenes_dd3d.py:300-469) for inference: DD3D plus
+    the attribute / speed predictors on the cls tower (fused into the cls predictor GEMM), ``pred_attributes`` /
+    ``pred_speeds`` on every detection, and -- when ``postprocess_in_inference`` -- the cross-camera BEV NMS over the 6
+    images of each nuScenes sample with at most MAX_NUM_DETS_PER_SAMPLE survivors (``pred_boxes3d_global`` added).
+    Inputs additionally carry "sample_token" and the global camera "pose"."""
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.num_images_per_sample = cfg.DD3D.NUSC.INFERENCE.NUM_IMAGES_PER_SAMPLE
+        assert self.num_images_per_sample == 6  # nuscenes_dd3d.py:330
+        assert cfg.DATALOADER.TEST.NUM_IMAGES_PER_GROUP == 6
+        self.max_num_dets_per_sample = cfg.DD3D.NUSC.INFERENCE.MAX_NUM_DETS_PER_SAMPLE
+        self.sample_aggregate_in_inference = True  # test hook: False returns the per-image detections before the aggregation
+
+    @torch.no_grad()
+    def forward(self, batched_inputs):
+        r = self._forward_device(batched_inputs)
+        glob = None
+        if self.postprocess_in_inference and self.sample_aggregate_in_inference:
+            L = _lib.load()
+            device, B, cap = self._device, r["B"], r["cap"]
+            groups = group_indices([x["sample_token"] for x in batched_inputs], self.num_images_per_sample)
+            # nuscenes_sample_aggregate concatenates the Instances of the call (postprocessing.py:95); detectron2's
+            # Instances.cat asserts one common (output) image size
+            assert len({tuple(s[2:].tolist()) for s in r["sizes"]}) == 1, "images of one call must share the output size"
+            with torch.cuda.device(device):
+                d_poses = self._gather_poses([{"pose": x["pose"]} for x in batched_inputs]).to(device, non_blocking=True)
+                d_group = torch.tensor(groups, dtype=torch.int32).to(device, non_blocking=True)
+                glob = torch.zeros((B, cap, 10), dtype=torch.float32, device=device)
+                scratch = torch.empty(int(L.dd3d_op_sample_aggregate_scratch_bytes(B, cap)), dtype=torch.uint8, device=device)
+                self._agg_flags = torch.zeros(1, dtype=torch.int32, device=device)
+                _lib.check(
+                    L.dd3d_op_sample_aggregate(C.c_void_p(r["out"].data_ptr()), C.c_void_p(r["counts"].data_ptr()),
+                                               C.c_void_p(r["d_K"].data_ptr()), C.c_void_p(d_poses.data_ptr()),
+                                               C.c_void_p(d_group.data_ptr()), max(groups) + 1,
+                                               C.c_void_p(glob.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                               C.c_void_p(self._agg_flags.data_ptr()), B, cap,
+                                               float(self.bev_nms_iou_thresh), int(self.max_num_dets_per_sample or 0),
+                                               C.c_void_p(r["stream"])), self._handle)
+        return self._wrap(r["out"], r["counts"].cpu(), r["K"], r["sizes"], self._device, glob)
+
+    def forward_host(self, batched_inputs):
+        """Host-buffer path: the sample aggregation needs the detections of all cameras on the device, so this is the
+        device forward followed by the device->host copy of the results."""
+        return [{"instances": o["instances"].to("cpu")} for o in self.forward(batched_inputs)]
+
+    def overflow_flags(self):
+        f = super().overflow_flags()
+        if getattr(self, "_agg_flags", None) is not None:
+            f |= int(self._agg_flags.item())
+        return f
+
+
 class _DevArray:
     """Minimal __cuda_array_interface__ carrier so torch can alias engine-owned device memory."""
     def __init__(self, ptr, shape, typestr):
@@ -320,3 +401,4 @@ class _DevArray:
 
 if META_ARCH_REGISTRY is not None:  # pragma: no cover
     META_ARCH_REGISTRY.register(DD3DB200)
+    META_ARCH_REGISTRY.register(NuscenesDD3DB200)

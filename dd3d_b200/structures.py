@@ -193,6 +193,44 @@ except Exception:  # noqa: BLE001
                          for f in ("quat", "proj_ctr", "depth", "size", "inv_intrinsics")])
 
 
+try:  # pragma: no cover
+    from tridet.structures.boxes3d import GenericBoxes3D  # type: ignore
+except Exception:  # noqa: BLE001
+
+    class GenericBoxes3D:
+        """tridet.structures.boxes3d.GenericBoxes3D subset (boxes3d.py:19-144): (quat wxyz, tvec, size WLH) rows; the
+        type of ``pred_boxes3d_global`` (postprocessing.py:50-51)."""
+        def __init__(self, quat, tvec, size):
+            self.quat, self._tvec, self.size = quat, tvec, size
+
+        @property
+        def tvec(self):
+            return self._tvec
+
+        def vectorize(self):
+            return torch.cat([self.quat, self.tvec, self.size], dim=1)
+
+        @property
+        def device(self):
+            return self.quat.device
+
+        def to(self, *args, **kwargs):
+            return GenericBoxes3D(self.quat.to(*args, **kwargs), self.tvec.to(*args, **kwargs),
+                                  self.size.to(*args, **kwargs))
+
+        def __getitem__(self, item):
+            if isinstance(item, int):
+                return GenericBoxes3D(self.quat[item].view(1, -1), self.tvec[item].view(1, -1), self.size[item].view(1, -1))
+            return GenericBoxes3D(self.quat[item], self.tvec[item], self.size[item])
+
+        def __len__(self):
+            return self.quat.shape[0]
+
+        @classmethod
+        def cat(cls, boxes_list, dim=0):
+            return cls(*[torch.cat([getattr(b, f) for b in boxes_list], dim=dim) for f in ("quat", "tvec", "size")])
+
+
 def matrix_to_quaternion_wxyz(R):
     """3x3 rotation (tensor) -> [w, x, y, z] (host-side helper for 4x4 pose inputs)."""
     m = torch.as_tensor(R, dtype=torch.float64)

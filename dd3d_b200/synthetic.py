@@ -27,6 +27,8 @@ _PRED = {
     "depth": (1.0, None),
     "size": (0.5, 0.0),
     "conf": (1.0, 0.0),
+    "attr": (1.0, 0.0),
+    "speed": (1.0, 0.5),
 }
 
 
@@ -134,4 +136,34 @@ def make_inputs(batch, height, width, focal, seed_base=1, with_size=False, dtype
         if with_size:
             d["height"], d["width"] = height, width
         inputs.append(d)
+    return inputs
+
+
+# camera yaw (degrees, about the ego z axis) of the 6 synthetic cameras of a sample: two triplets of nearly parallel
+# cameras so that the cross-camera BEV NMS of NuscenesDD3D has overlapping boxes to suppress, plus one isolated view
+NUSC_CAMERA_YAWS = (0.0, 4.0, -4.0, 180.0, 176.0, -70.0)
+
+
+def make_nusc_inputs(num_samples, height, width, focal, seed_base=1, with_size=False):
+    """NuscenesDD3D batches (nuscenes_dd3d.py:337-469): 6 images per sample, each with "sample_token" and a global
+    camera "pose" given as a (quaternion wxyz, translation) pair (camera frame: x right, y down, z forward)."""
+    from .structures import matrix_to_quaternion_wxyz
+    inputs = make_inputs(6 * num_samples, height, width, focal, seed_base=seed_base, with_size=with_size)
+    cam_to_ego = torch.tensor([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]], dtype=torch.float64)
+
+    def rot_z(deg):
+        a = math.radians(deg)
+        return torch.tensor([[math.cos(a), -math.sin(a), 0.0], [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]],
+                            dtype=torch.float64)
+
+    for s in range(num_samples):
+        ego_R = rot_z(30.0 + 17.0 * s)
+        ego_t = torch.tensor([100.0 + 35.0 * s, 50.0 - 20.0 * s, 0.0], dtype=torch.float64)
+        for c, yaw in enumerate(NUSC_CAMERA_YAWS):
+            R = ego_R @ rot_z(yaw) @ cam_to_ego
+            t = ego_t + ego_R @ torch.tensor([0.5 * math.cos(math.radians(yaw)), 0.5 * math.sin(math.radians(yaw)), 1.5],
+                                             dtype=torch.float64)
+            x = inputs[6 * s + c]
+            x["sample_token"] = f"sample{s:04d}"
+            x["pose"] = (matrix_to_quaternion_wxyz(R), [float(v) for v in t])
     return inputs

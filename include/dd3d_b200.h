@@ -61,6 +61,8 @@ typedef struct dd3d_model_desc {
     int32_t predict_distance;               /* FCOS3D.PREDICT_DISTANCE */
     float canonical_box3d_sizes[DD3D_MAX_CLASSES * 3]; /* FCOS3D.CANONICAL_BOX3D_SIZES rows 0..num_classes-1 (W,L,H) */
     int32_t out_cap;        /* detection slots per image in the output buffer (>= post_nms_topk; ties may exceed it) */
+    int32_t nuscenes_heads; /* MODEL.META_ARCHITECTURE == NuscenesDD3D: attr_logits (3) + speed (1, relu) predictor convs
+                             * on the cls tower (nuscenes_dd3d.py:311-312,380-383) */
 } dd3d_model_desc;
 
 /* One detection = the fields the reference returns in Instances (fcos2d.py:331-335,263; fcos3d.py:398-399). */
@@ -76,7 +78,9 @@ typedef struct dd3d_det {
     float size[3];     /* pred_boxes3d.size (W, L, H) */
     float loc[2];      /* locations */
     int32_t index;     /* pixel * num_classes + class at its level */
-    int32_t pad[3];
+    int32_t attr;      /* pred_attributes (NuscenesDD3D, nuscenes_dd3d.py:296); 0 otherwise */
+    float speed;       /* pred_speeds (NuscenesDD3D, nuscenes_dd3d.py:297); 0 otherwise */
+    int32_t pad;
 } dd3d_det;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
@@ -162,6 +166,18 @@ int64_t dd3d_op_ese_scratch_bytes(int B, int HW, int C);
 int dd3d_op_bev_nms(dd3d_det* d_dets, int32_t* d_counts, const float* d_intrinsics, const float* d_poses,
                     const int32_t* d_sizes, int32_t* d_flags, int B, int cap, float iou_thresh, int do_postprocess,
                     dd3d_stream stream);
+/* NuscenesDD3D sample aggregation (nuscenes_dd3d.py:449-463 -> postprocessing.py:58-108 nuscenes_sample_aggregate with
+ * get_group_idxs groups, :111-129): BEV rotated NMS (scores_3d order, class aware) jointly over the images that share a
+ * sample group, then -- like the reference's keep[:max_num_dets_per_sample] on the concatenation of the whole call -- only
+ * the max_dets best survivors of the call stay (max_dets <= 0: no cap).  In place on d_dets [B][cap] / d_counts [B]
+ * (cap <= 256), survivors keep their order.  d_group: [B] group index (0..num_groups-1) of each image; d_poses: [B][7]
+ * global camera poses (input["pose"]); d_global: [B][cap][10] receives pred_boxes3d_global (quat wxyz, tvec, size) of the
+ * survivors, compacted like d_dets; d_scratch: dd3d_op_sample_aggregate_scratch_bytes(B, cap) bytes.  d_flags: bit 3 set
+ * if a group exceeded 768 boxes or 16 images. */
+int64_t dd3d_op_sample_aggregate_scratch_bytes(int B, int cap);
+int dd3d_op_sample_aggregate(dd3d_det* d_dets, int32_t* d_counts, const float* d_intrinsics, const float* d_poses,
+                             const int32_t* d_group, int num_groups, float* d_global, void* d_scratch, int32_t* d_flags,
+                             int B, int cap, float iou_thresh, int max_dets, dd3d_stream stream);
 /* decode + NMS on caller-provided head maps (layout documented in csrc/detect.cuh). */
 int64_t dd3d_op_detect_scratch_bytes(int B, int pre_nms_topk);
 int dd3d_op_detect(const dd3d_model_desc* h_desc, int B, const int32_t* h_level_hw /*[5][2]*/,

@@ -190,3 +190,45 @@ def bev_nms_image(det, pose_quat, pose_tvec, thr):
     rb = boxes3d_to_rotated_boxes(q, t, det["size"])
     keep = nms_rotated(rb, det["score3d"], det["cls"], thr)
     return torch.sort(keep).values
+
+
+def sample_aggregate(dets, group_ids, poses, thr, max_dets=None):
+    """NuscenesDD3D sample aggregation (nuscenes_dd3d.py:449-463 -> postprocessing.py:58-108): the detections of all
+    images of the call are concatenated in list order, classes are offset per sample group so that only boxes of the
+    same sample AND class compete (postprocessing.py:80-84), ONE rotated NMS in descending scores_3d order runs over the
+    lot (:87-89), the first `max_dets` survivors OF THE WHOLE CALL are kept (:92-93 -- the reference truncates across
+    all groups of the call, not per group; restated as is) and the survivors are split back per image in their original
+    order (:99-107).
+
+    dets: per-image dicts (quat, tvec, size, score3d, cls, ...); group_ids: per-image group index (images of one sample
+    share it); poses: per-image (quat wxyz, tvec) global camera pose.  Returns the filtered per-image dicts with
+    `quat_global` / `tvec_global` (pred_boxes3d_global, include_boxes3d_global=True) added."""
+    num_classes_off = 1 + max([int(d["cls"].max()) for d in dets if d["cls"].numel()] + [0])
+    qs, ts, rbs, cat_ids, scores, img_ids = [], [], [], [], [], []
+    for i, (d, (pq, pt)) in enumerate(zip(dets, poses)):
+        n = d["quat"].shape[0]
+        if n:
+            q, t = to_global(d["quat"], d["tvec"], pq, pt)
+        else:
+            q, t = torch.zeros(0, 4), torch.zeros(0, 3)
+        qs.append(q)
+        ts.append(t)
+        rbs.append(boxes3d_to_rotated_boxes(q, t, d["size"]) if n else torch.zeros(0, 5))
+        cat_ids.append(d["cls"].to(torch.long) + group_ids[i] * num_classes_off)
+        scores.append(d["score3d"])
+        img_ids.append(torch.full((n, ), i, dtype=torch.long))
+    rb, cid, sc, img = torch.cat(rbs), torch.cat(cat_ids), torch.cat(scores), torch.cat(img_ids)
+    keep = nms_rotated(rb, sc, cid, thr)
+    if max_dets:
+        keep = keep[:max_dets]
+    mask = torch.zeros(rb.shape[0], dtype=torch.bool)
+    mask[keep] = True
+    out, off = [], 0
+    for i, d in enumerate(dets):
+        n = d["quat"].shape[0]
+        m = mask[off:off + n]
+        o = {k: v[m] for k, v in d.items()}
+        o["quat_global"], o["tvec_global"] = qs[i][m], ts[i][m]
+        out.append(o)
+        off += n
+    return out

@@ -49,6 +49,7 @@ class DD3DOracle:
             self.strides = [4, 8, 16, 32, 64]  # p2..p6 (vovnet.py:428-454)
             self.size_divisibility = 64  # FPN 32 * 2 (vovnet.py:452)
         self.num_levels = 5
+        self.nuscenes = cfg.MODEL.META_ARCHITECTURE == "NuscenesDD3D"  # nuscenes_dd3d.py:300-335
 
     # ------------------------------------------------------------------------------------------
     # primitives
@@ -232,6 +233,9 @@ class DD3DOracle:
             cls_t = self._tower(f, "fcos2d_head.cls_tower", l)
             box_t = self._tower(f, "fcos2d_head.box2d_tower", l)
             out["logits"].append(self.conv(cls_t, "fcos2d_head.cls_logits", quant_out=False))
+            if self.nuscenes:  # nuscenes_dd3d.py:311-312,380-383: attribute logits / relu(speed) from the cls tower
+                out.setdefault("attr", []).append(self.conv(cls_t, "attr_logits", quant_out=False))
+                out.setdefault("speed", []).append(self.conv(cls_t, "speed", relu=True, quant_out=False))
             out["centerness"].append(self.conv(box_t, "fcos2d_head.centerness", quant_out=False))
             reg = self.conv(box_t, "fcos2d_head.box2d_reg", quant_out=False)
             reg = reg * sd[f"fcos2d_head.scales_box2d_reg.{l}.scale"]
@@ -296,9 +300,14 @@ class DD3DOracle:
         conf = gather("conf", 1)[:, 0].sigmoid()
         canon = torch.tensor(self.cfg.DD3D.FCOS3D.CANONICAL_BOX3D_SIZES, dtype=torch.float32)[cls]
         box3d = predictions_to_boxes3d(quat, ctr, depth, size, loc, inv_K, canon, self.cfg.DD3D.FCOS3D)
+        extra = {}
+        if self.nuscenes:  # NuscenesInference, nuscenes_dd3d.py:268-298: argmax attribute, speed at the candidate pixel
+            a = maps["attr"][lvl][b].permute(1, 2, 0).reshape(h * w, -1)[pix]
+            extra["attr"] = a.argmax(dim=1) if a.shape[0] else torch.zeros(0, dtype=torch.long)
+            extra["speed"] = maps["speed"][lvl][b].permute(1, 2, 0).reshape(-1)[pix]
         return dict(
             pixel=pix, cls=cls, level=torch.full_like(pix, lvl), box2d=boxes, score=score2d, score3d=score2d * conf,
-            loc=loc, **box3d)
+            loc=loc, **box3d, **extra)
 
     # ------------------------------------------------------------------------------------------
     # NMS + top-k + postprocess: fcos2d.py:346-367, detectron2 batched_nms / detector_postprocess
@@ -365,6 +374,18 @@ class DD3DOracle:
                 results.append(self.postprocess(d, sizes[b], out_size) if do_postprocess else d)
             else:
                 results.append(self.nms_topk_postprocess(dict(det), sizes[b], out_size, do_postprocess))
+        if self.nuscenes and do_postprocess:
+            # nuscenes_dd3d.py:449-463: BEV NMS jointly over the cameras of each sample, <= MAX_NUM_DETS survivors
+            from oracle.bev_nms_oracle import sample_aggregate
+            tokens = [x["sample_token"] for x in batched_inputs]
+            order = {t: i for i, t in enumerate(dict.fromkeys(tokens))}  # get_group_idxs, postprocessing.py:111-123
+            nper = self.cfg.DD3D.NUSC.INFERENCE.NUM_IMAGES_PER_SAMPLE
+            if any(tokens.count(t) != nper for t in order):
+                raise ValueError("Group sizes does not match with 'num_images_per_sample'.")
+            poses = [pose_of({"pose": x["pose"]}) for x in batched_inputs]
+            results = sample_aggregate(results, [order[t] for t in tokens], poses,
+                                       self.cfg.DD3D.INFERENCE.BEV_NMS_IOU_THRESH,
+                                       self.cfg.DD3D.NUSC.INFERENCE.MAX_NUM_DETS_PER_SAMPLE)
         if return_intermediates:
             return results, dict(batch=batch, features=feats, maps=maps, pre_nms=pre_nms, inv_K=inv_K, sizes=sizes)
         return results

@@ -27,6 +27,60 @@ CASES = {
     "dla34": ("kitti_3d", 2, 192, 320, 721.5, (21, 34), 2.0),
     "v2_99": ("nuscenes", 2, 128, 192, 1266.4, (0, 0), 1.0),
 }
+NUSC_CASE = ("v2_99", 1, 128, 192, 1266.4)  # NuscenesDD3D: backbone, samples (x 6 cameras), H, W, focal
+
+
+def nusc_case_inputs():
+    from dd3d_b200.synthetic import make_nusc_inputs
+    _, ns, H, W, focal = NUSC_CASE
+    inputs = make_nusc_inputs(ns, H, W, focal)
+    for x in inputs:  # the sample aggregation runs AFTER the rescale; detectron2's Instances.cat inside it requires
+        x["height"], x["width"] = 2 * H, 2 * W  # one common output size per call (all nuScenes images are 900x1600)
+    return inputs
+
+
+def with_reference_poses(inputs):
+    """(quat, tvec) pairs -> the reference's own Pose objects (tridet/structures/pose.py)."""
+    ref_standin.install()
+    from tridet.structures.pose import Pose
+    return [dict(x, pose=Pose(wxyz=np.float32(x["pose"][0]), tvec=np.float32(x["pose"][1]))) for x in inputs]
+
+
+def reference_sample_aggregate(dets, group_ids, poses, thr, max_dets):
+    """Runs the reference's nuscenes_sample_aggregate (postprocessing.py:58-108) on per-image detection dicts;
+    returns per image (kept original indices, global quat, global tvec)."""
+    ref_standin.install()
+    from tridet.modeling.dd3d.postprocessing import nuscenes_sample_aggregate
+    from tridet.structures.boxes3d import GenericBoxes3D
+    from tridet.structures.pose import Pose
+    from collections import OrderedDict
+
+    class _B3(GenericBoxes3D):
+        def __getitem__(self, i):
+            return _B3(self.quat[i], self.tvec[i], self.size[i])
+
+        def __len__(self):
+            return self.quat.shape[0]
+
+        @classmethod
+        def cat(cls, l):
+            return _B3(torch.cat([b.quat for b in l]), torch.cat([b.tvec for b in l]), torch.cat([b.size for b in l]))
+
+    insts = []
+    for d in dets:
+        inst = ref_standin.Instances((100, 100))
+        inst.pred_boxes3d = _B3(d["quat"], d["tvec"], d["size"])
+        inst.pred_classes = d["cls"]
+        inst.scores_3d = d["score3d"]
+        inst.orig_index = torch.arange(d["quat"].shape[0])
+        insts.append(inst)
+    groups = OrderedDict()
+    for i, g in enumerate(group_ids):
+        groups.setdefault(g, []).append(i)
+    rposes = [Pose(wxyz=np.float32(q), tvec=np.float32(t)) for q, t in poses]
+    num_classes = 1 + max(int(d["cls"].max()) for d in dets if d["cls"].numel())
+    out = nuscenes_sample_aggregate(insts, groups, num_classes, rposes, thr, max_num_dets_per_sample=max_dets)
+    return [(o.orig_index, o.pred_boxes3d_global.quat, o.pred_boxes3d_global.tvec) for o in out]
 
 
 def case_inputs(arch):
@@ -96,6 +150,43 @@ def main():
             })
             print(arch, "image", b, "detections", len(inst))
         np.savez_compressed(os.path.join(out_dir, f"golden_{arch}.npz"), **blob)
+
+    # NuscenesDD3D: the reference's own meta-arch on one 6-camera sample
+    arch = NUSC_CASE[0]
+    cfg = get_cfg(arch, "nuscenes", meta_arch="NuscenesDD3D")
+    model = ref_standin.build_reference_model(cfg).eval()
+    model.load_state_dict(make_state_dict(cfg))
+    with torch.no_grad():
+        outs = model(with_reference_poses(nusc_case_inputs()))
+    blob = {}
+    for b, o in enumerate(outs):
+        inst = o["instances"]
+        b3, g3 = inst.pred_boxes3d, inst.pred_boxes3d_global
+        blob.update({
+            f"boxes{b}": inst.pred_boxes.tensor.numpy(), f"scores{b}": inst.scores.numpy(),
+            f"scores_3d{b}": inst.scores_3d.numpy(), f"classes{b}": inst.pred_classes.numpy(),
+            f"levels{b}": inst.fpn_levels.numpy(), f"locations{b}": inst.locations.numpy(),
+            f"quat{b}": b3.quat.numpy(), f"proj_ctr{b}": b3.proj_ctr.numpy(), f"depth{b}": b3.depth.numpy(),
+            f"size{b}": b3.size.numpy(), f"tvec{b}": b3.tvec.numpy(), f"attr{b}": inst.pred_attributes.numpy(),
+            f"speed{b}": inst.pred_speeds.numpy(), f"quat_global{b}": g3.quat.numpy(),
+            f"tvec_global{b}": g3.tvec.numpy(), f"image_size{b}": np.array(inst.image_size),
+        })
+        print("nusc", arch, "image", b, "detections", len(inst))
+    np.savez_compressed(os.path.join(out_dir, f"golden_nusc_{arch}.npz"), **blob)
+
+    # sample aggregation on seeded random detections: 2 samples x 6 cameras, with and without the 500-cap biting
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_nuscenes import aggregate_case
+    blob = {}
+    for c, max_dets in enumerate((1000, 150)):
+        dets, gids, poses = aggregate_case(7 + c)
+        res = reference_sample_aggregate(dets, gids, poses, 0.3, max_dets)
+        for i, (keep, q, t) in enumerate(res):
+            blob[f"keep{c}_{i}"] = keep.numpy()
+            blob[f"quat{c}_{i}"] = q.numpy()
+            blob[f"tvec{c}_{i}"] = t.numpy()
+        print("aggregate case", c, "kept", sum(len(r[0]) for r in res), "of", sum(d["quat"].shape[0] for d in dets))
+    np.savez_compressed(os.path.join(out_dir, "sample_aggregate.npz"), **blob)
 
     # BEV rotated NMS: reference nuscenes_sample_aggregate on seeded random boxes / poses
     sys.path.insert(0, os.path.join(ROOT, "tests"))

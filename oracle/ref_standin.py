@@ -275,6 +275,8 @@ class Instances:
         if len(instance_lists) == 1:
             return instance_lists[0]
         image_size = instance_lists[0].image_size
+        for i in instance_lists[1:]:  # detectron2 asserts a common image size
+            assert i.image_size == image_size
         ret = Instances(image_size)
         for k in instance_lists[0]._fields.keys():
             values = [i.get(k) for i in instance_lists]
@@ -676,7 +678,8 @@ def install(reference_root=REFERENCE_ROOT):
 
     wi = _mod("fvcore.nn.weight_init", c2_msra_fill=_c2_msra_fill, c2_xavier_fill=_c2_xavier_fill)
     _mod("fvcore")
-    _mod("fvcore.nn", sigmoid_focal_loss=_noop, smooth_l1_loss=_noop, weight_init=wi)
+    sl1 = _mod("fvcore.nn.smooth_l1_loss", smooth_l1_loss=_noop)
+    _mod("fvcore.nn", sigmoid_focal_loss=_noop, smooth_l1_loss=sl1, weight_init=wi)
 
     rc = _mod("pytorch3d.transforms.rotation_conversions", quaternion_to_matrix=quaternion_to_matrix,
               matrix_to_quaternion=matrix_to_quaternion)
@@ -707,6 +710,10 @@ def install(reference_root=REFERENCE_ROOT):
     from tridet.layers.bev_nms import bev_nms  # noqa: E402  (the reference's own BEV NMS, rotated IoU from the stand-in)
     sys.modules["tridet.layers"].bev_nms = bev_nms
     _mod("tridet.utils.comm", reduce_sum=lambda x: x, get_world_size=lambda: 1)
+    # NuscenesDD3D (nuscenes_dd3d.py:13) only needs the constant from the devkit-dependent dataset builder
+    for pkg in ("tridet.data", "tridet.data.datasets", "tridet.data.datasets.nuscenes"):
+        _mod(pkg)
+    _mod("tridet.data.datasets.nuscenes.build", MAX_NUM_ATTRIBUTES=3)  # tridet/data/datasets/nuscenes/build.py:77
 
 
 def _c2_msra_fill(module):
@@ -724,5 +731,8 @@ def _c2_xavier_fill(module):
 def build_reference_model(cfg):
     """Instantiate the reference's own DD3D (tridet/modeling/dd3d/core.py:19) under the stand-in."""
     install()
+    if cfg.MODEL.META_ARCHITECTURE == "NuscenesDD3D":  # tridet/modeling/dd3d/nuscenes_dd3d.py:301
+        from tridet.modeling.dd3d.nuscenes_dd3d import NuscenesDD3D
+        return NuscenesDD3D(cfg)
     from tridet.modeling.dd3d.core import DD3D
     return DD3D(cfg)

@@ -189,7 +189,7 @@ def test_cabi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name)
     import ctypes
-    assert ctypes.sizeof(lib.ModelDesc) == 4 * (2 + 3 + 3 + 1 + 1 + 3 + 1 + 2 + 1 + 1 + 1 + 1 + 48 + 1)
+    assert ctypes.sizeof(lib.ModelDesc) == 4 * (2 + 3 + 3 + 1 + 1 + 3 + 1 + 2 + 1 + 1 + 1 + 1 + 48 + 1 + 1)
 
 
 def test_cabi_fails_loudly_without_gpu():
