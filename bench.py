@@ -31,6 +31,9 @@ WORKLOADS = {
     # name: (arch, dataset, per-GPU batch, H, W, focal, conv GFLOP / image from BASELINE.md)
     "v2_99": ("v2_99", "nuscenes", 32, 900, 1600, 1266.4, 3066.0),
     "dla34": ("dla34", "kitti_3d", 8, 384, 1280, 721.5, 220.8),
+    # NuscenesDD3D (configs/experiments/dd3d_nusc_v99.yaml): 5 samples x 6 cameras per GPU, attr/speed heads and the
+    # cross-camera sample aggregation inside the step
+    "nusc_v2_99": ("v2_99", "nuscenes", 30, 900, 1600, 1266.4, 3066.0),
 }
 
 
@@ -132,13 +135,13 @@ def cpu_oracle_rate(workload, images, warm=1, threads=None):
     from oracle.dd3d_oracle import DD3DOracle
     arch, ds, _, H, W, focal, _ = WORKLOADS[workload]
     torch.set_num_threads(threads or pick_threads())
-    cfg = get_cfg(arch, ds)
+    cfg = get_cfg(arch, ds, meta_arch="NuscenesDD3D" if workload.startswith("nusc") else "DD3D")
     orc = DD3DOracle(cfg, make_state_dict(cfg))
     times = []
     for i in range(warm + images):
         inp = make_inputs(1, H, W, focal, seed_base=1 + i)
         t0 = time.perf_counter()
-        orc.forward(inp)
+        orc.forward(inp, do_postprocess=not workload.startswith("nusc"))  # single images: no sample to aggregate
         dt = time.perf_counter() - t0
         if i >= warm:
             times.append(dt)
@@ -184,22 +187,27 @@ def main():
     from dd3d_b200 import lib
     from dd3d_b200.config import get_cfg
     from dd3d_b200.gather import all_gather_detections
-    from dd3d_b200.meta_arch import DD3DB200
-    from dd3d_b200.synthetic import make_inputs, make_state_dict
+    from dd3d_b200.meta_arch import DD3DB200, NuscenesDD3DB200, group_indices
+    from dd3d_b200.synthetic import make_inputs, make_nusc_inputs, make_state_dict
 
     arch, ds, B, H, W, focal, gflop_img = WORKLOADS[args.workload]
+    nusc = args.workload.startswith("nusc")
     if args.batch:
         B = args.batch
+    assert not nusc or B % 6 == 0, "NuscenesDD3D batches are whole 6-camera samples"
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = get_cfg(arch, ds)
-    model = DD3DB200(cfg).to(dev)
+    cfg = get_cfg(arch, ds, meta_arch="NuscenesDD3D" if nusc else "DD3D")
+    model = (NuscenesDD3DB200 if nusc else DD3DB200)(cfg).to(dev)
     model.load_state_dict(make_state_dict(cfg))
-    inputs = make_inputs(B, H, W, focal, seed_base=1 + rank * B)
+    if nusc:
+        inputs = make_nusc_inputs(B // 6, H, W, focal, seed_base=1 + rank * B)
+    else:
+        inputs = make_inputs(B, H, W, focal, seed_base=1 + rank * B)
     batch, K, sizes, shape, is_u8 = model._gather_inputs(inputs, dev)
     model._plan(*shape)
     L, handle = lib.load(), model._handle
@@ -215,14 +223,41 @@ def main():
     stream = torch.cuda.current_stream(dev)
     sp = C.c_void_p(stream.cuda_stream)
 
+    if nusc:  # sample aggregation operands (nuscenes_dd3d.py:449-463)
+        groups = group_indices([x["sample_token"] for x in inputs], 6)
+        d_poses = model._gather_poses(inputs).to(dev)
+        d_group = torch.tensor(groups, dtype=torch.int32, device=dev)
+        d_glob = torch.zeros((B, cap, 10), dtype=torch.float32, device=dev)
+        h_glob = torch.zeros((B, cap, 10), dtype=torch.float32).pin_memory()
+        d_scr = torch.empty(int(L.dd3d_op_sample_aggregate_scratch_bytes(B, cap)), dtype=torch.uint8, device=dev)
+        d_flags = torch.zeros(1, dtype=torch.int32, device=dev)
+
     def step_device():
         lib.check(L.dd3d_forward(handle, C.c_void_p(d_batch.data_ptr()), dtype_code, C.c_void_p(d_K.data_ptr()),
                                  C.c_void_p(d_sizes.data_ptr()), C.c_void_p(d_out.data_ptr()),
                                  C.c_void_p(d_cnt.data_ptr()), sp), handle)
+        if nusc:
+            lib.check(L.dd3d_op_sample_aggregate(
+                C.c_void_p(d_out.data_ptr()), C.c_void_p(d_cnt.data_ptr()), C.c_void_p(d_K.data_ptr()),
+                C.c_void_p(d_poses.data_ptr()), C.c_void_p(d_group.data_ptr()), max(groups) + 1,
+                C.c_void_p(d_glob.data_ptr()), C.c_void_p(d_scr.data_ptr()), C.c_void_p(d_flags.data_ptr()), B, cap,
+                float(model.bev_nms_iou_thresh), int(model.max_num_dets_per_sample), sp), handle)
         if world > 1:
             all_gather_detections(d_out, d_cnt)
 
+    def step_host_nusc():  # the aggregation needs all cameras on the device: explicit H2D / D2H around the device step
+        d_batch.copy_(h_batch, non_blocking=True)
+        d_K.copy_(h_K, non_blocking=True)
+        d_sizes.copy_(h_sizes, non_blocking=True)
+        step_device()
+        h_out.copy_(d_out, non_blocking=True)
+        h_cnt.copy_(d_cnt, non_blocking=True)
+        h_glob.copy_(d_glob, non_blocking=True)
+        stream.synchronize()
+
     def step_host():
+        if nusc:
+            return step_host_nusc()
         lib.check(L.dd3d_forward_host(handle, C.c_void_p(h_batch.data_ptr()), dtype_code, C.c_void_p(h_K.data_ptr()),
                                       C.c_void_p(h_sizes.data_ptr()), C.c_void_p(h_out.data_ptr()),
                                       C.c_void_p(h_cnt.data_ptr()), sp), handle)
@@ -256,6 +291,7 @@ def main():
     ms_dev, clocks = timed(step_device, ClockSampler(local_rank))
     ms_host, _ = timed(step_host)
     assert model.overflow_flags() == 0, "detection buffers overflowed"
+    assert not nusc or int(d_flags.item()) == 0, "sample aggregation overflowed"
     n_det = int(h_cnt.sum())
 
     # live per-kernel timing (CUDA events on the launch stream around every op of the step)
@@ -291,7 +327,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
-            "workload": f"{arch} DD3D bf16, batch {B} per GPU, {H}x{W} (padded to /{model.backbone.size_divisibility})",
+            "workload": f"{arch} {'NuscenesDD3D' if nusc else 'DD3D'} bf16, batch {B} per GPU, {H}x{W} "
+                        f"(padded to /{model.backbone.size_divisibility})",
             "global_batch": world * B, "parallelism": f"dp{world}",
             "l2": "inputs (%.0f MB uint8) and activations (GBs) exceed the 126 MB L2; no explicit flush" %
                   (batch.numel() / 1e6),
@@ -301,8 +338,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_host / args.steps,
                 "h2d_bytes_per_step": int(h_batch.numel() * h_batch.element_size() + h_K.numel() * 4 + h_sizes.numel() * 4),
-                "d2h_bytes_per_step": int(h_out.numel() * 4 + h_cnt.numel() * 4)},
-        "gpu_launches": model.launches_per_forward() * args.steps,
+                "d2h_bytes_per_step": int(h_out.numel() * 4 + h_cnt.numel() * 4 + (h_glob.numel() * 4 if nusc else 0))},
+        "gpu_launches": (model.launches_per_forward() + (2 if nusc else 0)) * args.steps,
         "roofline": {
             "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, %d launches/step)" % conv["launches"],
             "bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",

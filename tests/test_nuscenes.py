@@ -245,7 +245,9 @@ def test_nuscenes_forward_vs_emulating_oracle_and_golden():
             assert rel_err(gd["box2d"][ia], e["box2d"][ib], floor=32.0) < 5e-3
             assert rel_err(gd["speed"][ia], e["speed"][ib], floor=1.0) < 2e-2
             assert (gd["attr"][ia] == e["attr"][ib]).float().mean().item() > 0.95
-            assert rel_err(gd["tvec_global"][ia], e["tvec_global"][ib], floor=1.0) < 2e-2
+            # global positions: error relative to the camera-frame range (global coordinates carry the ego offset)
+            err = (gd["tvec_global"][ia] - e["tvec_global"][ib]).norm(dim=1) / e["tvec"][ib].norm(dim=1).clamp(min=1.0)
+            assert err.max().item() < 2e-2
     assert matched >= 0.9 * total
     # (3) fp32 reference golden, loose (bf16 storage)
     g = np.load(os.path.join(GOLDEN_DIR, f"golden_nusc_{arch}.npz"))
