@@ -92,7 +92,9 @@ def get_cfg(backbone="dla34", dataset="kitti_3d", nms_thresh=0.75, meta_arch="DD
                      NORM="FrozenBN", FUSE_TYPE="sum")
     fe["OUT_FEATURES"] = None
     cfg = dict(
-        INPUT=dict(FORMAT="BGR"),
+        # test-time resize: configs/experiments/dd3d_kitti_{dla34,v99}.yaml:34, dd3d_nusc_{dla34,v99}.yaml:43-44
+        INPUT=dict(FORMAT="BGR", AUG_ENABLED=True,
+                   RESIZE=dict(MIN_SIZE_TEST=384 if dataset == "kitti_3d" else 896, MAX_SIZE_TEST=100000)),
         MODEL=dict(
             DEVICE="cuda",
             META_ARCHITECTURE=meta_arch,

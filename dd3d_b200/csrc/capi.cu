@@ -113,6 +113,25 @@ int dd3d_forward_host(dd3d_handle h, const void* h_images, int img_dtype, const 
     });
 }
 
+int dd3d_resize_shape(int h, int w, int min_size, int max_size, int32_t* new_h, int32_t* new_w) {
+    if (h < 1 || w < 1 || !new_h || !new_w) return DD3D_ERR_INVALID;
+    int nh, nw;
+    resize_shortest_edge_shape(h, w, min_size, max_size, &nh, &nw);
+    *new_h = nh;
+    *new_w = nw;
+    return DD3D_OK;
+}
+
+int dd3d_forward_raw(dd3d_handle h, const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes,
+                     const float* h_intrinsics, int min_size, int max_size, dd3d_det* d_out, int32_t* d_counts,
+                     float* h_intrinsics_out, int32_t* h_new_sizes, dd3d_stream stream) {
+    if (!d_raw || !h_raw_sizes || !h_intrinsics || !d_out || !d_counts || raw_h < 1 || raw_w < 1) return DD3D_ERR_INVALID;
+    return guarded(h, [&](Engine& e) {
+        e.forward_raw(d_raw, raw_h, raw_w, h_raw_sizes, h_intrinsics, min_size, max_size, reinterpret_cast<Det*>(d_out),
+                      d_counts, h_intrinsics_out, h_new_sizes, static_cast<cudaStream_t>(stream));
+    });
+}
+
 int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags) {
     return guarded(h, [&](Engine& e) {
         if (!e.plan.valid) throw EngineError(DD3D_ERR_STATE, "no plan");
@@ -309,6 +328,16 @@ int dd3d_op_bev_nms(dd3d_det* d_dets, int32_t* d_counts, const float* d_intrinsi
         return DD3D_ERR_INVALID;
     return cuda_status(launch_bev_nms(reinterpret_cast<Det*>(d_dets), d_counts, d_intrinsics, d_poses, d_sizes, d_flags, B,
                                       cap, iou_thresh, do_postprocess, static_cast<cudaStream_t>(stream)),
+                       nullptr);
+}
+
+int dd3d_op_resize_preprocess(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes,
+                              const int32_t* h_new_sizes, void* d_out4, int B, int Hp, int Wp, const float* h_mean,
+                              const float* h_std, dd3d_stream stream) {
+    if (!d_raw || !h_raw_sizes || !h_new_sizes || !d_out4 || !h_mean || !h_std || B < 1) return DD3D_ERR_INVALID;
+    static ResizeTables tables;  // operator-level entry point: one table cache per process (tests; not thread safe)
+    return cuda_status(tables.launch(d_raw, raw_h, raw_w, h_raw_sizes, h_new_sizes, static_cast<__nv_bfloat16*>(d_out4), B,
+                                     Hp, Wp, h_mean, h_std, static_cast<cudaStream_t>(stream)),
                        nullptr);
 }
 

@@ -880,10 +880,47 @@ int Engine::launches_per_forward() const {
     return n;
 }
 
+void Engine::forward_raw(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes, const float* h_K,
+                         int min_size, int max_size, Det* d_out, int32_t* d_counts, float* h_K_out, int32_t* h_new_sizes,
+                         cudaStream_t stream) {
+    if (!plan.valid) fail(DD3D_ERR_STATE, "forward before plan");
+    const Plan& P = plan;
+    std::vector<int32_t> new_sizes(2 * P.B), sizes(4 * P.B);
+    std::vector<float> K(9 * P.B);
+    for (int b = 0; b < P.B; ++b) {
+        const int h0 = h_raw_sizes[2 * b], w0 = h_raw_sizes[2 * b + 1];
+        int nh, nw;
+        resize_shortest_edge_shape(h0, w0, min_size, max_size, &nh, &nw);
+        if (nh > P.Hs || nw > P.Ws)
+            fail(DD3D_ERR_INVALID, "resized image " + std::to_string(nh) + "x" + std::to_string(nw) + " exceeds the plan");
+        new_sizes[2 * b] = nh;
+        new_sizes[2 * b + 1] = nw;
+        // detections are mapped back to the ORIGINAL resolution: dataset dicts carry the file's height / width
+        // (core.py:154-157 input_per_image.get("height"))
+        sizes[4 * b] = nh; sizes[4 * b + 1] = nw; sizes[4 * b + 2] = h0; sizes[4 * b + 3] = w0;
+        // apply_imresize_intrinsics (resize_transform.py:13-21): float32 rows scaled by float32(new / old)
+        const float fx = static_cast<float>(static_cast<double>(nw) / w0), fy = static_cast<float>(static_cast<double>(nh) / h0);
+        for (int c = 0; c < 3; ++c) {
+            K[9 * b + c] = h_K[9 * b + c] * fx;
+            K[9 * b + 3 + c] = h_K[9 * b + 3 + c] * fy;
+            K[9 * b + 6 + c] = h_K[9 * b + 6 + c] * 1.0f;
+        }
+    }
+    if (h_K_out) memcpy(h_K_out, K.data(), K.size() * 4);
+    if (h_new_sizes) memcpy(h_new_sizes, new_sizes.data(), new_sizes.size() * 4);
+    cuda_check(cudaMemcpyAsync(P.d_K, K.data(), K.size() * 4, cudaMemcpyHostToDevice, stream), "H2D K");
+    cuda_check(cudaMemcpyAsync(P.d_sizes, sizes.data(), sizes.size() * 4, cudaMemcpyHostToDevice, stream), "H2D sizes");
+    raw_pending = true;
+    raw_args = {d_raw, raw_h, raw_w, h_raw_sizes, new_sizes.data()};
+    forward(nullptr, DD3D_IMG_U8, P.d_K, P.d_sizes, d_out, d_counts, stream);
+}
+
 void Engine::forward(const void* d_images, int img_dtype, const float* d_K, const int32_t* d_sizes, Det* d_out,
                      int32_t* d_counts, cudaStream_t stream) {
     if (!plan.valid) fail(DD3D_ERR_STATE, "forward before plan");
     const Plan& P = plan;
+    const bool raw = raw_pending;
+    raw_pending = false;
     size_t ev_i = 0;
     auto mark = [&](int cat) {  // opt_profile: CUDA events on the launch stream around every op
         if (!opt_profile) return;
@@ -898,9 +935,16 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
     };
     mark(-1);
     // sizes (h, w, out_h, out_w) -> the (h, w) pairs the preprocess kernel reads are its first two columns
-    cuda_check(launch_preprocess(d_images, img_dtype == DD3D_IMG_U8, d_sizes, 4, P.input.ptr, P.B, P.Hs, P.Ws, P.Hp, P.Wp,
-                                 desc.pixel_mean, desc.pixel_std, stream),
-               "preprocess");
+    if (raw) {
+        cuda_check(resize_tables.launch(raw_args.d_raw, raw_args.raw_h, raw_args.raw_w, raw_args.h_raw_sizes,
+                                        raw_args.h_new_sizes, P.input.ptr, P.B, P.Hp, P.Wp, desc.pixel_mean, desc.pixel_std,
+                                        stream),
+                   "resize + preprocess");
+    } else {
+        cuda_check(launch_preprocess(d_images, img_dtype == DD3D_IMG_U8, d_sizes, 4, P.input.ptr, P.B, P.Hs, P.Ws, P.Hp,
+                                     P.Wp, desc.pixel_mean, desc.pixel_std, stream),
+                   "preprocess");
+    }
     mark(0);
     for (const Op& op : P.ops) {
         switch (op.type) {

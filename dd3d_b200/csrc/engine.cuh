@@ -9,6 +9,7 @@
 #include "../../include/dd3d_b200.h"
 #include "conv_igemm.cuh"
 #include "detect.cuh"
+#include "resize.cuh"
 #include "small_kernels.cuh"
 
 namespace dd3d {
@@ -106,6 +107,10 @@ class Engine {
                  int32_t* d_counts, cudaStream_t stream);
     void forward_host(const void* h_images, int img_dtype, const float* h_K, const int32_t* h_sizes, Det* h_out,
                       int32_t* h_counts, cudaStream_t stream);
+    // raw dataset images: ResizeShortestEdge + intrinsics rescale (dataset_mapper.py:100-153) fused with the preprocess
+    void forward_raw(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes, const float* h_K,
+                     int min_size, int max_size, Det* d_out, int32_t* d_counts, float* h_K_out, int32_t* h_new_sizes,
+                     cudaStream_t stream);
     int launches_per_forward() const;
     // categories: 0 preprocess, 1 stem, 2 conv (tcgen05), 3 pool, 4 eSE, 5 relu, 6 decode, 7 nms
     void get_profile(double* ms, double* flops, double* bytes, int32_t* launches);
@@ -141,6 +146,14 @@ class Engine {
     std::vector<void*> device_allocs;
     float* d_canon = nullptr;
     Plan plan;
+    ResizeTables resize_tables;
+    struct RawArgs {
+        const uint8_t* d_raw;
+        int raw_h, raw_w;
+        const int32_t* h_raw_sizes;
+        const int32_t* h_new_sizes;
+    } raw_args{};
+    bool raw_pending = false;  // set by forward_raw for the forward() call it makes
 
    private:
     void* dev_alloc(size_t bytes);

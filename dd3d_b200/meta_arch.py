@@ -215,8 +215,66 @@ class DD3DB200(nn.Module):
     @torch.no_grad()
     def forward(self, batched_inputs):
         """Device path: inputs are moved to the GPU with torch, one small D2H (per-image counts) at the end."""
-        r = self._forward_device(batched_inputs)
+        return self._finish(self._forward_device(batched_inputs), batched_inputs)
+
+    @torch.no_grad()
+    def forward_raw(self, raw_inputs):
+        """GPU input pipeline: takes what the dataset holds -- {"image_hwc": (H, W, 3) uint8 BGR
+        array as cv2 reads it, "intrinsics": 3x3 of the original image, ...} -- and does the test-time work of
+        DefaultDatasetMapper (dataset_mapper.py:100-153: ResizeShortestEdge to INPUT.RESIZE.MIN_SIZE_TEST with PIL-exact
+        bilinear resampling, intrinsics rescale) on the device, fused with the model's normalisation.  Same outputs as
+        ``forward([mapper(x) for x in raw_inputs])``; detections are mapped back to the original resolution."""
+        return self._finish(self._forward_device_raw(raw_inputs), raw_inputs)
+
+    def _finish(self, r, batched_inputs):
         return self._wrap(r["out"], r["counts"].cpu(), r["K"], r["sizes"], self._device)  # .cpu(): the only sync
+
+    def _forward_device_raw(self, raw_inputs):
+        device = self._device
+        if self.do_bev_nms:
+            raise NotImplementedError("forward_raw with DO_BEV_NMS: run the mapper-style forward()")
+        L = _lib.load()
+        imgs = [torch.as_tensor(x["image_hwc"]) for x in raw_inputs]
+        if not all(im.dtype == torch.uint8 and im.dim() == 3 and im.shape[2] == 3 for im in imgs):
+            raise ValueError("forward_raw expects uint8 (H, W, 3) images")
+        B = len(imgs)
+        raw_h, raw_w = max(im.shape[0] for im in imgs), max(im.shape[1] for im in imgs)
+        rs = self.cfg.INPUT.RESIZE
+        min_size, max_size = (int(rs.MIN_SIZE_TEST), int(rs.MAX_SIZE_TEST)) if self.cfg.INPUT.AUG_ENABLED else (0, 0)
+        raw_sizes = torch.tensor([[im.shape[0], im.shape[1]] for im in imgs], dtype=torch.int32)
+        new_sizes = torch.zeros((B, 2), dtype=torch.int32)
+        nh, nw = C.c_int32(), C.c_int32()
+        for b in range(B):
+            _lib.check(L.dd3d_resize_shape(int(raw_sizes[b, 0]), int(raw_sizes[b, 1]), min_size, max_size, C.byref(nh),
+                                           C.byref(nw)))
+            new_sizes[b, 0], new_sizes[b, 1] = nh.value, nw.value
+        if all(tuple(im.shape) == (raw_h, raw_w, 3) for im in imgs):
+            raw = torch.stack(imgs, 0)
+        else:
+            raw = torch.zeros((B, raw_h, raw_w, 3), dtype=torch.uint8)
+            for b, im in enumerate(imgs):
+                raw[b, :im.shape[0], :im.shape[1]] = im
+        K0 = torch.stack([torch.as_tensor(x["intrinsics"], dtype=torch.float32) for x in raw_inputs], 0).reshape(B, 9).contiguous()
+        if torch.allclose(K0[0].reshape(3, 3), torch.eye(3)):  # image_list.py:57-62
+            raise ValueError("Intrinsics is Identity.")
+        self._plan(B, int(new_sizes[:, 0].max()), int(new_sizes[:, 1].max()))
+        cap = self._desc.out_cap
+        K = torch.empty((B, 9), dtype=torch.float32)
+        with torch.cuda.device(device):
+            d_raw = raw.to(device, non_blocking=True)
+            out = torch.empty((B, cap, _lib.DET_WORDS), dtype=torch.float32, device=device)
+            counts = torch.empty((B, ), dtype=torch.int32, device=device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(L.dd3d_set_option(self._handle, b"do_postprocess", int(self.postprocess_in_inference)), self._handle)
+            _lib.check(L.dd3d_set_option(self._handle, b"do_nms", int(self.do_nms)), self._handle)
+            _lib.check(
+                L.dd3d_forward_raw(self._handle, C.c_void_p(d_raw.data_ptr()), raw_h, raw_w, C.c_void_p(raw_sizes.data_ptr()),
+                                   C.c_void_p(K0.data_ptr()), min_size, max_size, C.c_void_p(out.data_ptr()),
+                                   C.c_void_p(counts.data_ptr()), C.c_void_p(K.data_ptr()), None, C.c_void_p(stream)),
+                self._handle)
+            d_K = K.to(device, non_blocking=True)
+        sizes = torch.cat([new_sizes, raw_sizes if self.postprocess_in_inference else new_sizes], 1)
+        return dict(out=out, counts=counts, K=K, sizes=sizes, d_K=d_K, B=B, cap=cap, stream=stream)
 
     def _forward_device(self, batched_inputs):
         device = self._device
@@ -354,9 +412,7 @@ class NuscenesDD3DB200(DD3DB200):
         self.max_num_dets_per_sample = cfg.DD3D.NUSC.INFERENCE.MAX_NUM_DETS_PER_SAMPLE
         self.sample_aggregate_in_inference = True  # test hook: False returns the per-image detections before the aggregation
 
-    @torch.no_grad()
-    def forward(self, batched_inputs):
-        r = self._forward_device(batched_inputs)
+    def _finish(self, r, batched_inputs):
         glob = None
         if self.postprocess_in_inference and self.sample_aggregate_in_inference:
             L = _lib.load()

@@ -134,6 +134,22 @@ int dd3d_get_profile(dd3d_handle h, double* h_ms, double* h_flops, double* h_byt
  * category and algorithmic FLOPs.  Returns the number of entries written (<= max_ops). */
 int dd3d_get_op_times(dd3d_handle h, float* h_ms, int32_t* h_cats, double* h_flops, int max_ops);
 
+/* ---- GPU input pipeline ------------------------------------------------------------------
+ * Replaces the per-image CPU work of DefaultDatasetMapper.__call__ at test time
+ * (tridet/data/dataset_mappers/dataset_mapper.py:100-153 with augmentations = [ResizeShortestEdge],
+ * tridet/data/augmentations/build.py:35-44): detectron2 ResizeShortestEdge.get_transform (output shape),
+ * ResizeTransform.apply_image = PIL.Image.resize(BILINEAR) (bit-exact restatement of Pillow's 8-bit ImagingResample),
+ * apply_imresize_intrinsics (tridet/data/augmentations/resize_transform.py:13-21), and the model's own preprocess. */
+int dd3d_resize_shape(int h, int w, int min_size, int max_size, int32_t* new_h, int32_t* new_w);
+/* d_raw: [B][raw_h][raw_w][3] uint8, cv2 layout (HWC, BGR); image b occupies the top-left h_raw_sizes[b] = (h, w) of its
+ * slot.  h_intrinsics: [B][9] of the ORIGINAL images.  min_size / max_size: INPUT.RESIZE.MIN_SIZE_TEST / MAX_SIZE_TEST
+ * (min_size 0: no resize).  The plan must cover the resized sizes (dd3d_resize_shape).  Detections are mapped back to
+ * the original resolution when option do_postprocess is on (dataset dicts carry the file's height / width).
+ * h_intrinsics_out [B][9] / h_new_sizes [B][2] (optional) receive the rescaled intrinsics and the resized (h, w). */
+int dd3d_forward_raw(dd3d_handle h, const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes,
+                     const float* h_intrinsics, int min_size, int max_size, dd3d_det* d_out, int32_t* d_counts,
+                     float* h_intrinsics_out, int32_t* h_new_sizes, dd3d_stream stream);
+
 /* ---- introspection for stage-level parity tests ---------------------------------------------------------- */
 /* name: "p0".."p4" (FPN outputs, bf16 NHWC), "cls0".."cls4", "box0".."box4", "b3d0".."b3d4" (fp32 NHWC head maps),
  * "input" (bf16 [B][Hp][Wp][4]).  Returns the device pointer and fills dims = {B, H, W, C, pitch, elem_bytes}. */
@@ -166,6 +182,10 @@ int64_t dd3d_op_ese_scratch_bytes(int B, int HW, int C);
 int dd3d_op_bev_nms(dd3d_det* d_dets, int32_t* d_counts, const float* d_intrinsics, const float* d_poses,
                     const int32_t* d_sizes, int32_t* d_flags, int B, int cap, float iou_thresh, int do_postprocess,
                     dd3d_stream stream);
+/* resize + normalise + pad + NHWC4 bf16 of raw HWC uint8 images (the first kernel of dd3d_forward_raw). */
+int dd3d_op_resize_preprocess(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes,
+                              const int32_t* h_new_sizes, void* d_out4, int B, int Hp, int Wp, const float* h_mean,
+                              const float* h_std, dd3d_stream stream);
 /* NuscenesDD3D sample aggregation (nuscenes_dd3d.py:449-463 -> postprocessing.py:58-108 nuscenes_sample_aggregate with
  * get_group_idxs groups, :111-129): BEV rotated NMS (scores_3d order, class aware) jointly over the images that share a
  * sample group, then -- like the reference's keep[:max_num_dets_per_sample] on the concatenation of the whole call -- only

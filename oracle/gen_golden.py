@@ -188,6 +188,18 @@ def main():
         print("aggregate case", c, "kept", sum(len(r[0]) for r in res), "of", sum(d["quat"].shape[0] for d in dets))
     np.savez_compressed(os.path.join(out_dir, "sample_aggregate.npz"), **blob)
 
+    # input pipeline: real Pillow resize + the reference's own intrinsics rescale
+    from PIL import Image
+    from test_input_pipeline import RESIZE_CASES, raw_image
+    from tridet.data.augmentations.resize_transform import ResizeTransform
+    blob = {}
+    for c, ((h, w), (nh, nw)) in enumerate(RESIZE_CASES):
+        blob[f"img{c}"] = np.asarray(Image.fromarray(raw_image(c, h, w)).resize((nw, nh), Image.BILINEAR))
+        K = np.float32([[721.5377, 0, 609.5593], [0, 721.5377, 172.854], [0, 0, 1]])
+        blob[f"K{c}"] = ResizeTransform(h, w, nh, nw).apply_intrinsics(K)
+    np.savez_compressed(os.path.join(out_dir, "input_pipeline.npz"), **blob)
+    print("input pipeline cases", len(RESIZE_CASES))
+
     # BEV rotated NMS: reference nuscenes_sample_aggregate on seeded random boxes / poses
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from test_bev_nms import _random_case

@@ -711,8 +711,28 @@ def install(reference_root=REFERENCE_ROOT):
     sys.modules["tridet.layers"].bev_nms = bev_nms
     _mod("tridet.utils.comm", reduce_sum=lambda x: x, get_world_size=lambda: 1)
     # NuscenesDD3D (nuscenes_dd3d.py:13) only needs the constant from the devkit-dependent dataset builder
-    for pkg in ("tridet.data", "tridet.data.datasets", "tridet.data.datasets.nuscenes"):
-        _mod(pkg)
+    for pkg in ("tridet.data", "tridet.data.datasets", "tridet.data.datasets.nuscenes", "tridet.data.augmentations"):
+        m = types.ModuleType(pkg)
+        m.__path__ = [os.path.join(reference_root, *pkg.split("."))]
+        m.__spec__ = importlib.machinery.ModuleSpec(pkg, None, is_package=True)
+        sys.modules[pkg] = m
+
+    # detectron2.data.transforms pieces tridet/data/augmentations/resize_transform.py binds to (type registry only)
+    class _ResizeTransform:
+        _types = {}
+
+        def __init__(self, h, w, new_h, new_w, interp=None):
+            self.h, self.w, self.new_h, self.new_w = h, w, new_h, new_w
+
+        @classmethod
+        def register_type(cls, data_type, func):
+            cls._types[data_type] = func
+
+        def apply_intrinsics(self, intrinsics):
+            return self._types["intrinsics"](self, intrinsics)
+
+    _mod("detectron2.data")
+    _mod("detectron2.data.transforms", ResizeTransform=_ResizeTransform, ResizeShortestEdge=object)
     _mod("tridet.data.datasets.nuscenes.build", MAX_NUM_ATTRIBUTES=3)  # tridet/data/datasets/nuscenes/build.py:77
 
 
