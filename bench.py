@@ -174,6 +174,9 @@ def main():
     ap.add_argument("--workload", default="v2_99", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--cpu-images", type=int, default=2, help="images timed for cpu_baseline (0 disables)")
+    ap.add_argument("--input", default="mapped", choices=["mapped", "raw"],
+                    help="raw: steps start from raw HWC uint8 dataset images (dd3d_forward_raw: ResizeShortestEdge to "
+                         "INPUT.RESIZE.MIN_SIZE_TEST + intrinsics rescale on the GPU); not the BASELINE configuration")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -209,6 +212,17 @@ def main():
     else:
         inputs = make_inputs(B, H, W, focal, seed_base=1 + rank * B)
     batch, K, sizes, shape, is_u8 = model._gather_inputs(inputs, dev)
+    raw_mode = args.input == "raw"
+    assert not (raw_mode and nusc), "--input raw is wired for the DD3D workloads"
+    if raw_mode:  # the mapped tensors stand in for the files: HWC raw images at the dataset resolution
+        min_size, max_size = int(cfg.INPUT.RESIZE.MIN_SIZE_TEST), int(cfg.INPUT.RESIZE.MAX_SIZE_TEST)
+        nh, nw = C.c_int32(), C.c_int32()
+        lib.check(lib.load().dd3d_resize_shape(H, W, min_size, max_size, C.byref(nh), C.byref(nw)))
+        shape = (B, nh.value, nw.value)
+        h_raw = batch.permute(0, 2, 3, 1).contiguous().pin_memory()
+        d_raw = h_raw.to(dev)
+        raw_sizes = torch.tensor([[H, W]] * B, dtype=torch.int32)
+        h_K_scaled = torch.empty((B, 9), dtype=torch.float32)
     model._plan(*shape)
     L, handle = lib.load(), model._handle
     cap = model._desc.out_cap
@@ -232,7 +246,17 @@ def main():
         d_scr = torch.empty(int(L.dd3d_op_sample_aggregate_scratch_bytes(B, cap)), dtype=torch.uint8, device=dev)
         d_flags = torch.zeros(1, dtype=torch.int32, device=dev)
 
+    def forward_raw_call():
+        lib.check(L.dd3d_forward_raw(handle, C.c_void_p(d_raw.data_ptr()), H, W, C.c_void_p(raw_sizes.data_ptr()),
+                                     C.c_void_p(h_K.data_ptr()), min_size, max_size, C.c_void_p(d_out.data_ptr()),
+                                     C.c_void_p(d_cnt.data_ptr()), C.c_void_p(h_K_scaled.data_ptr()), None, sp), handle)
+
     def step_device():
+        if raw_mode:
+            forward_raw_call()
+            if world > 1:
+                all_gather_detections(d_out, d_cnt)
+            return
         lib.check(L.dd3d_forward(handle, C.c_void_p(d_batch.data_ptr()), dtype_code, C.c_void_p(d_K.data_ptr()),
                                  C.c_void_p(d_sizes.data_ptr()), C.c_void_p(d_out.data_ptr()),
                                  C.c_void_p(d_cnt.data_ptr()), sp), handle)
@@ -255,9 +279,18 @@ def main():
         h_glob.copy_(d_glob, non_blocking=True)
         stream.synchronize()
 
+    def step_host_raw():  # raw dataset bytes in pinned host memory -> detections in host memory
+        d_raw.copy_(h_raw, non_blocking=True)
+        step_device()
+        h_out.copy_(d_out, non_blocking=True)
+        h_cnt.copy_(d_cnt, non_blocking=True)
+        stream.synchronize()
+
     def step_host():
         if nusc:
             return step_host_nusc()
+        if raw_mode:
+            return step_host_raw()
         lib.check(L.dd3d_forward_host(handle, C.c_void_p(h_batch.data_ptr()), dtype_code, C.c_void_p(h_K.data_ptr()),
                                       C.c_void_p(h_sizes.data_ptr()), C.c_void_p(h_out.data_ptr()),
                                       C.c_void_p(h_cnt.data_ptr()), sp), handle)
@@ -328,7 +361,8 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
             "workload": f"{arch} {'NuscenesDD3D' if nusc else 'DD3D'} bf16, batch {B} per GPU, {H}x{W} "
-                        f"(padded to /{model.backbone.size_divisibility})",
+                        f"(padded to /{model.backbone.size_divisibility})" +
+                        (f", raw HWC input resized on the GPU to {shape[1]}x{shape[2]}" if raw_mode else ""),
             "global_batch": world * B, "parallelism": f"dp{world}",
             "l2": "inputs (%.0f MB uint8) and activations (GBs) exceed the 126 MB L2; no explicit flush" %
                   (batch.numel() / 1e6),

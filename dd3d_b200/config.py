@@ -153,5 +153,10 @@ def get_cfg(backbone="dla34", dataset="kitti_3d", nms_thresh=0.75, meta_arch="DD
             ),
         ),
         DATALOADER=dict(TEST=dict(NUM_IMAGES_PER_GROUP=6)),
+        # test-time augmentation: configs/experiments/dd3d_kitti_{dla34,v99}.yaml:47-53, dd3d_nusc_v99.yaml:57-63
+        TEST=dict(IMS_PER_BATCH=80 if dataset == "kitti_3d" else 192,
+                  AUG=dict(ENABLED=True,
+                           MIN_SIZES=[320, 384, 448, 512, 576] if dataset == "kitti_3d" else [640, 768, 896, 1024, 1152],
+                           MAX_SIZE=100000, FLIP=True)),
     )
     return _to_node(cfg)

@@ -331,13 +331,43 @@ int dd3d_op_bev_nms(dd3d_det* d_dets, int32_t* d_counts, const float* d_intrinsi
                        nullptr);
 }
 
+static_assert(sizeof(dd3d_tta_view) == sizeof(TtaView), "dd3d_tta_view must mirror TtaView");
+
+int dd3d_op_tta_merged_cap(int num_views, int cap) { return tta_merged_cap(num_views, cap); }
+
+int64_t dd3d_op_tta_merge_scratch_bytes(int num_views, int cap) {
+    return static_cast<int64_t>(tta_scratch_bytes(num_views, cap));
+}
+
+int dd3d_op_tta_merge(const dd3d_det* d_dets, const int32_t* d_counts, const dd3d_tta_view* h_views, int num_views, int cap,
+                      float nms_thresh, int do_nms, void* d_scratch, dd3d_det* d_out, int32_t* d_out_count,
+                      int32_t* d_flags, dd3d_stream stream) {
+    if (!d_dets || !d_counts || !h_views || !d_scratch || !d_out || !d_out_count || !d_flags) return DD3D_ERR_INVALID;
+    return cuda_status(launch_tta_merge(reinterpret_cast<const Det*>(d_dets), d_counts,
+                                        reinterpret_cast<const TtaView*>(h_views), num_views, cap, nms_thresh, do_nms,
+                                        d_scratch, reinterpret_cast<Det*>(d_out), d_out_count, d_flags,
+                                        static_cast<cudaStream_t>(stream)),
+                       nullptr);
+}
+
+int dd3d_forward_resized(dd3d_handle h, const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes,
+                         const int32_t* h_new_sizes, const int32_t* h_flip, const float* h_intrinsics,
+                         const int32_t* h_sizes, dd3d_det* d_out, int32_t* d_counts, dd3d_stream stream) {
+    if (!d_raw || !h_raw_sizes || !h_new_sizes || !h_intrinsics || !h_sizes || !d_out || !d_counts) return DD3D_ERR_INVALID;
+    return guarded(h, [&](Engine& e) {
+        e.forward_resized(d_raw, raw_h, raw_w, h_raw_sizes, h_new_sizes, h_flip, h_intrinsics, h_sizes,
+                          reinterpret_cast<Det*>(d_out), d_counts, static_cast<cudaStream_t>(stream));
+    });
+}
+
 int dd3d_op_resize_preprocess(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes,
-                              const int32_t* h_new_sizes, void* d_out4, int B, int Hp, int Wp, const float* h_mean,
-                              const float* h_std, dd3d_stream stream) {
+                              const int32_t* h_new_sizes, const int32_t* h_flip, void* d_out4, int B, int Hp, int Wp,
+                              const float* h_mean, const float* h_std, dd3d_stream stream) {
     if (!d_raw || !h_raw_sizes || !h_new_sizes || !d_out4 || !h_mean || !h_std || B < 1) return DD3D_ERR_INVALID;
     static ResizeTables tables;  // operator-level entry point: one table cache per process (tests; not thread safe)
-    return cuda_status(tables.launch(d_raw, raw_h, raw_w, h_raw_sizes, h_new_sizes, static_cast<__nv_bfloat16*>(d_out4), B,
-                                     Hp, Wp, h_mean, h_std, static_cast<cudaStream_t>(stream)),
+    return cuda_status(tables.launch(d_raw, raw_h, raw_w, h_raw_sizes, h_new_sizes, h_flip,
+                                     static_cast<__nv_bfloat16*>(d_out4), B, Hp, Wp, h_mean, h_std,
+                                     static_cast<cudaStream_t>(stream)),
                        nullptr);
 }
 

@@ -86,6 +86,23 @@ cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream);
 cudaError_t launch_bev_nms(Det* dets, int32_t* counts, const float* K, const float* poses, const int32_t* sizes,
                            int32_t* flags, int B, int cap, float thr, int do_postprocess, cudaStream_t stream);
 
+// Test-time-augmentation merge (tta.cu): the views' detections back to the original image + one merged NMS.
+constexpr int kTtaMaxViews = 16;
+constexpr int kTtaMergedMax = 1024;  // merged detections the single NMS pass holds (10 views x POST_NMS_TOPK 100 fit)
+struct TtaView {       // one augmented view = ResizeShortestEdge scale (+ horizontal flip); mirrors dd3d_tta_view
+    int32_t flip;      // HFlipTransform applied after the resize
+    float view_w;      // width of the view (flip axis)
+    float inv_sx[2];   // fp32 x factors of the inverse resizes, applied in this order: view -> input, input -> original
+    float inv_sy[2];
+    float K_view[9];   // intrinsics the view was run with
+    float K_orig[9];   // inverse transforms applied to K_view = the original camera (re-projection of tvec)
+};
+int tta_merged_cap(int A, int cap);  // slots of the merged output buffer: min(A * cap, kTtaMergedMax)
+size_t tta_scratch_bytes(int A, int cap);
+cudaError_t launch_tta_merge(const Det* dets, const int32_t* counts, const TtaView* h_views, int A, int cap,
+                             float nms_thresh, int do_nms, void* scratch, Det* out, int32_t* out_count, int32_t* flags,
+                             cudaStream_t stream);
+
 // NuscenesDD3D sample aggregation: BEV rotated NMS jointly over the images of each sample group, then the cap on the
 // survivors of the call; in place; global: [B][cap][10] pred_boxes3d_global rows; cap <= 256.
 size_t sample_aggregate_scratch_bytes(int B, int cap);

@@ -58,6 +58,7 @@ Engine::Engine(const dd3d_model_desc& d) : desc(d) {
 
 Engine::~Engine() {
     release_plan();
+    for (auto& kv : plan_cache) cudaFree(kv.second.owned_workspace);
     for (void* p : device_allocs) cudaFree(p);
 }
 
@@ -809,10 +810,30 @@ void Engine::make_plan(int B, int Hs, int Ws, void* workspace, size_t bytes) {
     if (!finalized) fail(DD3D_ERR_STATE, "plan before finalize");
     if (B < 1 || Hs < 1 || Ws < 1) fail(DD3D_ERR_INVALID, "bad plan shape");
     cuda_check(cudaSetDevice(device), "cudaSetDevice");
+    if (workspace == nullptr && plan.valid && plan.owned_workspace && plan.B == B && plan.Hs == Hs && plan.Ws == Ws) return;
+    // park the active plan if it is engine-owned and small, else free it
+    if (plan.valid && plan.owned_workspace && plan.owned_bytes <= kPlanCacheBytes) {
+        if (plan_cache.size() >= kPlanCacheMax) {
+            cudaFree(plan_cache.begin()->second.owned_workspace);
+            plan_cache.erase(plan_cache.begin());
+        }
+        plan_cache[{plan.B, plan.Hs, plan.Ws}] = std::move(plan);
+        plan = Plan();
+    } else {
+        release_plan();
+    }
+    if (workspace == nullptr) {
+        auto it = plan_cache.find({B, Hs, Ws});
+        if (it != plan_cache.end()) {
+            plan = std::move(it->second);
+            plan_cache.erase(it);
+            return;
+        }
+    }
     const size_t need = workspace_bytes(B, Hs, Ws);
-    release_plan();
     if (workspace == nullptr) {
         cuda_check(cudaMalloc(&plan.owned_workspace, need), "cudaMalloc(workspace)");
+        plan.owned_bytes = need;
         workspace = plan.owned_workspace;
     } else if (bytes < need) {
         fail(DD3D_ERR_INVALID, "workspace too small: need " + std::to_string(need) + " bytes");
@@ -908,10 +929,22 @@ void Engine::forward_raw(const uint8_t* d_raw, int raw_h, int raw_w, const int32
     }
     if (h_K_out) memcpy(h_K_out, K.data(), K.size() * 4);
     if (h_new_sizes) memcpy(h_new_sizes, new_sizes.data(), new_sizes.size() * 4);
-    cuda_check(cudaMemcpyAsync(P.d_K, K.data(), K.size() * 4, cudaMemcpyHostToDevice, stream), "H2D K");
-    cuda_check(cudaMemcpyAsync(P.d_sizes, sizes.data(), sizes.size() * 4, cudaMemcpyHostToDevice, stream), "H2D sizes");
+    forward_resized(d_raw, raw_h, raw_w, h_raw_sizes, new_sizes.data(), nullptr, K.data(), sizes.data(), d_out, d_counts,
+                    stream);
+}
+
+void Engine::forward_resized(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes,
+                             const int32_t* h_new_sizes, const int32_t* h_flip, const float* h_K, const int32_t* h_sizes4,
+                             Det* d_out, int32_t* d_counts, cudaStream_t stream) {
+    if (!plan.valid) fail(DD3D_ERR_STATE, "forward before plan");
+    const Plan& P = plan;
+    for (int b = 0; b < P.B; ++b)
+        if (h_new_sizes[2 * b] > P.Hs || h_new_sizes[2 * b + 1] > P.Ws) fail(DD3D_ERR_INVALID, "resized image exceeds the plan");
+    cuda_check(cudaMemcpyAsync(P.d_K, h_K, static_cast<size_t>(P.B) * 36, cudaMemcpyHostToDevice, stream), "H2D K");
+    cuda_check(cudaMemcpyAsync(P.d_sizes, h_sizes4, static_cast<size_t>(P.B) * 16, cudaMemcpyHostToDevice, stream),
+               "H2D sizes");
     raw_pending = true;
-    raw_args = {d_raw, raw_h, raw_w, h_raw_sizes, new_sizes.data()};
+    raw_args = {d_raw, raw_h, raw_w, h_raw_sizes, h_new_sizes, h_flip};
     forward(nullptr, DD3D_IMG_U8, P.d_K, P.d_sizes, d_out, d_counts, stream);
 }
 
@@ -937,7 +970,7 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
     // sizes (h, w, out_h, out_w) -> the (h, w) pairs the preprocess kernel reads are its first two columns
     if (raw) {
         cuda_check(resize_tables.launch(raw_args.d_raw, raw_args.raw_h, raw_args.raw_w, raw_args.h_raw_sizes,
-                                        raw_args.h_new_sizes, P.input.ptr, P.B, P.Hp, P.Wp, desc.pixel_mean, desc.pixel_std,
+                                        raw_args.h_new_sizes, raw_args.h_flip, P.input.ptr, P.B, P.Hp, P.Wp, desc.pixel_mean, desc.pixel_std,
                                         stream),
                    "resize + preprocess");
     } else {

@@ -2,6 +2,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <array>
 #include <map>
 #include <string>
 #include <vector>
@@ -71,6 +72,7 @@ struct Plan {
     bool valid = false;
     int B = 0, Hs = 0, Ws = 0, Hp = 0, Wp = 0;
     void* owned_workspace = nullptr;
+    size_t owned_bytes = 0;
     View input;
     View fpn[kLevels];
     float* cls_map[kLevels] = {};
@@ -111,6 +113,11 @@ class Engine {
     void forward_raw(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes, const float* h_K,
                      int min_size, int max_size, Det* d_out, int32_t* d_counts, float* h_K_out, int32_t* h_new_sizes,
                      cudaStream_t stream);
+    // same with caller-chosen output shapes, optional horizontal flips, final intrinsics and (h, w, out_h, out_w) rows:
+    // the augmented views of test-time augmentation (test_time_augmentation.py:24-87)
+    void forward_resized(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes, const int32_t* h_new_sizes,
+                         const int32_t* h_flip, const float* h_K, const int32_t* h_sizes4, Det* d_out, int32_t* d_counts,
+                         cudaStream_t stream);
     int launches_per_forward() const;
     // categories: 0 preprocess, 1 stem, 2 conv (tcgen05), 3 pool, 4 eSE, 5 relu, 6 decode, 7 nms
     void get_profile(double* ms, double* flops, double* bytes, int32_t* launches);
@@ -146,12 +153,18 @@ class Engine {
     std::vector<void*> device_allocs;
     float* d_canon = nullptr;
     Plan plan;
+    // inactive engine-owned plans, keyed by (B, Hs, Ws): test-time augmentation cycles through one shape per scale
+    // (test_time_augmentation.py:57-64); only small plans are kept (kPlanCacheBytes each, kPlanCacheMax entries)
+    std::map<std::array<int, 3>, Plan> plan_cache;
+    static constexpr size_t kPlanCacheBytes = size_t(4) << 30;
+    static constexpr size_t kPlanCacheMax = 12;
     ResizeTables resize_tables;
     struct RawArgs {
         const uint8_t* d_raw;
         int raw_h, raw_w;
         const int32_t* h_raw_sizes;
         const int32_t* h_new_sizes;
+        const int32_t* h_flip;
     } raw_args{};
     bool raw_pending = false;  // set by forward_raw for the forward() call it makes
 

@@ -55,8 +55,9 @@ __global__ void __launch_bounds__(kResizeThreads) resize_preprocess_kernel(const
             const int rr = idx / kTileW, xx = idx - rr * kTileW;
             const int x = x0 + xx;
             if (x >= I.nw) continue;
-            const int xm = I.xmin[x];
-            const int32_t* k = I.kx + static_cast<size_t>(x) * I.ksx;
+            const int xs = I.flip ? I.nw - 1 - x : x;  // flipped output column x shows resized column nw-1-x
+            const int xm = I.xmin[xs];
+            const int32_t* k = I.kx + static_cast<size_t>(xs) * I.ksx;
             const uint8_t* row = src + static_cast<size_t>(r_lo + rr) * p.raw_w * 3;
             int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
             for (int t = 0; t < I.ksx; ++t) {
@@ -187,8 +188,8 @@ const ResizeTables::Axis* ResizeTables::axis(int in_size, int out_size, cudaErro
 }
 
 cudaError_t ResizeTables::launch(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes,
-                                 const int32_t* h_new_sizes, __nv_bfloat16* d_out4, int B, int Hp, int Wp,
-                                 const float mean[3], const float std[3], cudaStream_t stream) {
+                                 const int32_t* h_new_sizes, const int32_t* h_flip, __nv_bfloat16* d_out4, int B, int Hp,
+                                 int Wp, const float mean[3], const float std[3], cudaStream_t stream) {
     cudaError_t err = cudaSuccess;
     h_img.resize(B);
     int rows_cap = 1;
@@ -203,6 +204,7 @@ cudaError_t ResizeTables::launch(const uint8_t* d_raw, int raw_h, int raw_w, con
         I.h0 = h0; I.w0 = w0; I.nh = nh; I.nw = nw;
         I.kx = ax->d_k; I.xmin = ax->d_min; I.ksx = ax->ksize;
         I.ky = ay->d_k; I.ymin = ay->d_min; I.ksy = ay->ksize;
+        I.flip = h_flip ? (h_flip[b] != 0) : 0;
         for (int y0 = 0; y0 < nh; y0 += kTileH) {  // input rows one output tile needs
             const int y_last = (y0 + kTileH < nh ? y0 + kTileH : nh) - 1;
             int hi = ay->h_min[y_last] + ay->ksize;

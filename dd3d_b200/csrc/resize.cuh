@@ -21,6 +21,7 @@ struct ResizeImage {  // per-image kernel operands
     const int32_t* ky;    // [nh][ksy]
     const int32_t* ymin;  // [nh]
     int ksx, ksy;
+    int flip;  // horizontal flip AFTER the resize (HFlipTransform.apply_image = np.flip(axis=1)); test-time augmentation
 };
 
 // Coefficient tables per (input size, output size) axis pair, cached on the device; not thread safe (one per engine).
@@ -29,9 +30,10 @@ class ResizeTables {
     ~ResizeTables();
     // d_raw: [B][raw_h][raw_w][3] uint8 (image b occupies the top-left h0 x w0 of its slot); h_raw_sizes / h_new_sizes:
     // [B][2] (h, w) on the host; d_out4: [B][Hp][Wp][4] bf16 = ((resized - mean) / std, zero padded).
+    // h_flip: [B] flags or nullptr.
     cudaError_t launch(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes, const int32_t* h_new_sizes,
-                       __nv_bfloat16* d_out4, int B, int Hp, int Wp, const float mean[3], const float std[3],
-                       cudaStream_t stream);
+                       const int32_t* h_flip, __nv_bfloat16* d_out4, int B, int Hp, int Wp, const float mean[3],
+                       const float std[3], cudaStream_t stream);
 
   private:
     struct Axis {

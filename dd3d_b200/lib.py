@@ -40,6 +40,12 @@ class ModelDesc(C.Structure):
     ]
 
 
+class TtaView(C.Structure):
+    """dd3d_tta_view."""
+    _fields_ = [("flip", C.c_int32), ("view_w", C.c_float), ("inv_sx", C.c_float * 2), ("inv_sy", C.c_float * 2),
+                ("K_view", C.c_float * 9), ("K_orig", C.c_float * 9)]
+
+
 # name -> (restype, argtypes); every symbol include/dd3d_b200.h declares
 _P, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
 SIGNATURES = {
@@ -69,7 +75,11 @@ SIGNATURES = {
     "dd3d_op_bev_nms": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, C.c_float, _I, _P]),
     "dd3d_resize_shape": (_I, [_I, _I, _I, _I, _P, _P]),
     "dd3d_forward_raw": (_I, [_P, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
-    "dd3d_op_resize_preprocess": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "dd3d_forward_resized": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dd3d_op_tta_merged_cap": (_I, [_I, _I]),
+    "dd3d_op_tta_merge_scratch_bytes": (_I64, [_I, _I]),
+    "dd3d_op_tta_merge": (_I, [_P, _P, _P, _I, _I, C.c_float, _I, _P, _P, _P, _P, _P]),
+    "dd3d_op_resize_preprocess": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "dd3d_op_sample_aggregate_scratch_bytes": (_I64, [_I, _I]),
     "dd3d_op_sample_aggregate": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, C.c_float, _I, _P]),
     "dd3d_op_detect_scratch_bytes": (_I64, [_I, _I]),

@@ -83,6 +83,18 @@ typedef struct dd3d_det {
     int32_t pad;
 } dd3d_det;
 
+/* One augmented view of test-time augmentation: a ResizeShortestEdge scale optionally followed by a
+ * horizontal flip, described by what DD3DWithTTA needs to map its detections back (test_time_augmentation.py:190-239). */
+typedef struct dd3d_tta_view {
+    int32_t flip;       /* HFlipTransform after the resize */
+    float view_w;       /* width of the view (flip axis) */
+    float inv_sx[2];    /* fp32 x factors of the inverse ResizeTransforms, in application order: view -> model input,
+                         * model input -> original image (1 if the dataset mapper did not resize) */
+    float inv_sy[2];
+    float K_view[9];    /* intrinsics the view was run with (tfms.apply_intrinsics, :78-82) */
+    float K_orig[9];    /* inv_tfm.apply_intrinsics(K_view) (:214): the original camera, used by Boxes3D.from_vectors */
+} dd3d_tta_view;
+
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
 int dd3d_create(const dd3d_model_desc* h_desc, dd3d_handle* out);
 void dd3d_destroy(dd3d_handle h);
@@ -150,6 +162,13 @@ int dd3d_forward_raw(dd3d_handle h, const uint8_t* d_raw, int raw_h, int raw_w, 
                      const float* h_intrinsics, int min_size, int max_size, dd3d_det* d_out, int32_t* d_counts,
                      float* h_intrinsics_out, int32_t* h_new_sizes, dd3d_stream stream);
 
+/* Same kernels with caller-chosen shapes: h_new_sizes [B][2] resized (h, w), h_flip [B] (or NULL) horizontal flip after
+ * the resize, h_intrinsics [B][9] the intrinsics the views run with, h_sizes [B][4] (h, w, out_h, out_w) rows of
+ * dd3d_forward.  These are the augmented views of DatasetMapperTTA (test_time_augmentation.py:24-87). */
+int dd3d_forward_resized(dd3d_handle h, const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes,
+                         const int32_t* h_new_sizes, const int32_t* h_flip, const float* h_intrinsics,
+                         const int32_t* h_sizes, dd3d_det* d_out, int32_t* d_counts, dd3d_stream stream);
+
 /* ---- introspection for stage-level parity tests ---------------------------------------------------------- */
 /* name: "p0".."p4" (FPN outputs, bf16 NHWC), "cls0".."cls4", "box0".."box4", "b3d0".."b3d4" (fp32 NHWC head maps),
  * "input" (bf16 [B][Hp][Wp][4]).  Returns the device pointer and fills dims = {B, H, W, C, pitch, elem_bytes}. */
@@ -182,10 +201,22 @@ int64_t dd3d_op_ese_scratch_bytes(int B, int HW, int C);
 int dd3d_op_bev_nms(dd3d_det* d_dets, int32_t* d_counts, const float* d_intrinsics, const float* d_poses,
                     const int32_t* d_sizes, int32_t* d_flags, int B, int cap, float iou_thresh, int do_postprocess,
                     dd3d_stream stream);
-/* resize + normalise + pad + NHWC4 bf16 of raw HWC uint8 images (the first kernel of dd3d_forward_raw). */
+/* resize (+ optional horizontal flip, h_flip [B] or NULL) + normalise + pad + NHWC4 bf16 of raw HWC uint8 images (the
+ * first kernel of dd3d_forward_raw / dd3d_forward_resized). */
 int dd3d_op_resize_preprocess(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes,
-                              const int32_t* h_new_sizes, void* d_out4, int B, int Hp, int Wp, const float* h_mean,
-                              const float* h_std, dd3d_stream stream);
+                              const int32_t* h_new_sizes, const int32_t* h_flip, void* d_out4, int B, int Hp, int Wp,
+                              const float* h_mean, const float* h_std, dd3d_stream stream);
+/* Test-time-augmentation merge (DD3DWithTTA._get_augmented_instances + the merged NMS of _inference_one_image,
+ * tridet/modeling/dd3d/test_time_augmentation.py:160-171,190-239) for ONE image: d_dets [num_views][cap] / d_counts
+ * [num_views] are the views' detections (dd3d_forward* with do_postprocess = 0); 2-D boxes, 3-D boxes and the projected
+ * centres are mapped back to the original image, concatenated in view order and reduced by one class-aware NMS on
+ * scores_3d (do_nms = 0: no suppression).  d_out: dd3d_op_tta_merged_cap(num_views, cap) slots, always in descending
+ * scores_3d; field `level` = view index.  d_flags bit 4: more merged detections than slots. */
+int dd3d_op_tta_merged_cap(int num_views, int cap);
+int64_t dd3d_op_tta_merge_scratch_bytes(int num_views, int cap);
+int dd3d_op_tta_merge(const dd3d_det* d_dets, const int32_t* d_counts, const dd3d_tta_view* h_views, int num_views, int cap,
+                      float nms_thresh, int do_nms, void* d_scratch, dd3d_det* d_out, int32_t* d_out_count,
+                      int32_t* d_flags, dd3d_stream stream);
 /* NuscenesDD3D sample aggregation (nuscenes_dd3d.py:449-463 -> postprocessing.py:58-108 nuscenes_sample_aggregate with
  * get_group_idxs groups, :111-129): BEV rotated NMS (scores_3d order, class aware) jointly over the images that share a
  * sample group, then -- like the reference's keep[:max_num_dets_per_sample] on the concatenation of the whole call -- only

@@ -30,6 +30,24 @@ CASES = {
 NUSC_CASE = ("v2_99", 1, 128, 192, 1266.4)  # NuscenesDD3D: backbone, samples (x 6 cameras), H, W, focal
 
 
+TTA_CASE = dict(arch="dla34", dataset="kitti_3d", H=96, W=320, orig=(94, 313), focal=721.5, min_sizes=[64, 96, 128],
+                ims_per_batch=4, pre_nms_thresh=0.02)
+
+
+def tta_case():
+    """(cfg, mapped dataset dict) of the TTA fixture: the mapped image is a resized version of a 94x313 original, three
+    scales x flip = 6 views run in chunks of 4 (so one chunk mixes two scales and is zero padded)."""
+    c = TTA_CASE
+    cfg = get_cfg(c["arch"], c["dataset"])
+    cfg.DD3D.INFERENCE.DO_POSTPROCESS = False
+    cfg.DD3D.FCOS2D.INFERENCE.PRE_NMS_THRESH = c["pre_nms_thresh"]
+    cfg.TEST.AUG.MIN_SIZES = list(c["min_sizes"])
+    cfg.TEST.IMS_PER_BATCH = c["ims_per_batch"]
+    x = make_inputs(1, c["H"], c["W"], c["focal"])[0]
+    x["height"], x["width"] = c["orig"]
+    return cfg, x
+
+
 def nusc_case_inputs():
     from dd3d_b200.synthetic import make_nusc_inputs
     _, ns, H, W, focal = NUSC_CASE
@@ -187,6 +205,21 @@ def main():
             blob[f"tvec{c}_{i}"] = t.numpy()
         print("aggregate case", c, "kept", sum(len(r[0]) for r in res), "of", sum(d["quat"].shape[0] for d in dets))
     np.savez_compressed(os.path.join(out_dir, "sample_aggregate.npz"), **blob)
+
+    # test-time augmentation: the reference's own DD3DWithTTA around its own DD3D
+    from tridet.modeling.dd3d.test_time_augmentation import DD3DWithTTA
+    cfg, x = tta_case()
+    model = ref_standin.build_reference_model(cfg).eval()
+    model.load_state_dict(make_state_dict(cfg))
+    with torch.no_grad():
+        inst = DD3DWithTTA(cfg, model)([x])[0]["instances"]
+    b3 = inst.pred_boxes3d
+    np.savez_compressed(
+        os.path.join(out_dir, "tta_dla34.npz"), boxes=inst.pred_boxes.tensor.numpy(), scores=inst.scores.numpy(),
+        scores_3d=inst.scores_3d.numpy(), classes=inst.pred_classes.numpy(), quat=b3.quat.numpy(),
+        proj_ctr=b3.proj_ctr.numpy(), depth=b3.depth.numpy(), size=b3.size.numpy(), tvec=b3.tvec.numpy(),
+        inv_K=b3.inv_intrinsics.numpy(), image_size=np.array(inst.image_size))
+    print("tta merged detections", len(inst))
 
     # input pipeline: real Pillow resize + the reference's own intrinsics rescale
     from PIL import Image

@@ -648,6 +648,187 @@ def _mod(name, **attrs):
 _INSTALLED = False
 
 
+# ----------------------------------------------------------------------------------------------
+# fvcore.transforms.transform / detectron2.data.transforms (restated; un-vendored third-party code)
+# ----------------------------------------------------------------------------------------------
+class Transform:
+    """fvcore Transform: apply_box through the four corners, per-class registry of extra data types."""
+    def _set_attributes(self, params=None):
+        if params:
+            for k, v in params.items():
+                if k != "self" and not k.startswith("_"):
+                    setattr(self, k, v)
+
+    def apply_box(self, box):
+        import numpy as np
+        idxs = np.array([(0, 1), (2, 1), (0, 3), (2, 3)]).flatten()
+        coords = np.asarray(box).reshape(-1, 4)[:, idxs].reshape(-1, 2)
+        coords = self.apply_coords(coords).reshape((-1, 4, 2))
+        minxy = coords.min(axis=1)
+        maxxy = coords.max(axis=1)
+        return np.concatenate((minxy, maxxy), axis=1)
+
+    @classmethod
+    def register_type(cls, data_type, func):
+        def wrapper(transform, x):
+            return func(transform, x)
+        setattr(cls, "apply_" + data_type, wrapper)
+
+    def inverse(self):
+        raise NotImplementedError
+
+
+class NoOpTransform(Transform):
+    def apply_image(self, img):
+        return img
+
+    def apply_coords(self, coords):
+        return coords
+
+    def inverse(self):
+        return self
+
+    def __getattr__(self, name):
+        if name.startswith("apply_"):
+            return lambda x: x
+        raise AttributeError("NoOpTransform object has no attribute {}".format(name))
+
+
+class HFlipTransform(Transform):
+    def __init__(self, width):
+        self.width = width
+
+    def apply_image(self, img):
+        import numpy as np
+        return np.flip(img, axis=1) if img.ndim <= 3 else np.flip(img, axis=-2)
+
+    def apply_coords(self, coords):
+        coords[:, 0] = self.width - coords[:, 0]
+        return coords
+
+    def inverse(self):
+        return self
+
+
+class VFlipTransform(Transform):
+    def __init__(self, height):
+        self.height = height
+
+    def apply_image(self, img):
+        import numpy as np
+        return np.flip(img, axis=0)
+
+    def apply_coords(self, coords):
+        coords[:, 1] = self.height - coords[:, 1]
+        return coords
+
+    def inverse(self):
+        return self
+
+
+class TransformList(Transform):
+    def __init__(self, transforms):
+        flat = []
+        for t in transforms:
+            assert isinstance(t, Transform), t
+            flat.extend(t.transforms if isinstance(t, TransformList) else [t])
+        self.transforms = flat
+
+    def _apply(self, x, meth):
+        for t in self.transforms:
+            x = getattr(t, meth)(x)
+        return x
+
+    def __getattr__(self, name):
+        if name.startswith("apply_"):
+            return lambda x: self._apply(x, name)
+        raise AttributeError("TransformList object has no attribute {}".format(name))
+
+    def __add__(self, other):
+        others = other.transforms if isinstance(other, TransformList) else [other]
+        return TransformList(self.transforms + others)
+
+    def __radd__(self, other):
+        others = other.transforms if isinstance(other, TransformList) else [other]
+        return TransformList(others + self.transforms)
+
+    def __len__(self):
+        return len(self.transforms)
+
+    def inverse(self):
+        return TransformList([x.inverse() for x in self.transforms[::-1]])
+
+
+class ResizeTransform(Transform):
+    """detectron2 ResizeTransform: uint8 images through PIL (BILINEAR), coordinates scaled by new / old."""
+    def __init__(self, h, w, new_h, new_w, interp=None):
+        self.h, self.w, self.new_h, self.new_w, self.interp = h, w, new_h, new_w, interp
+
+    def apply_image(self, img, interp=None):
+        import numpy as np
+        from PIL import Image
+        assert img.shape[:2] == (self.h, self.w) and img.dtype == np.uint8
+        pil = Image.fromarray(img).resize((self.new_w, self.new_h), Image.BILINEAR)
+        return np.asarray(pil)
+
+    def apply_coords(self, coords):
+        coords[:, 0] = coords[:, 0] * (self.new_w * 1.0 / self.w)
+        coords[:, 1] = coords[:, 1] * (self.new_h * 1.0 / self.h)
+        return coords
+
+    def inverse(self):
+        return ResizeTransform(self.new_h, self.new_w, self.h, self.w, self.interp)
+
+
+class ResizeShortestEdge:
+    """detectron2 ResizeShortestEdge (sample_style "range" or "choice"; one size at test time)."""
+    def __init__(self, short_edge_length, max_size=sys.maxsize, sample_style="range", interp=None):
+        if isinstance(short_edge_length, int):
+            short_edge_length = (short_edge_length, short_edge_length)
+        self.short_edge_length, self.max_size, self.is_range = short_edge_length, max_size, sample_style == "range"
+
+    def get_transform(self, image):
+        import numpy as np
+        h, w = image.shape[:2]
+        if self.is_range:
+            size = np.random.randint(self.short_edge_length[0], self.short_edge_length[1] + 1)
+        else:
+            size = np.random.choice(self.short_edge_length)
+        if size == 0:
+            return NoOpTransform()
+        scale = size * 1.0 / min(h, w)
+        if h < w:
+            newh, neww = size, scale * w
+        else:
+            newh, neww = scale * h, size
+        if max(newh, neww) > self.max_size:
+            scale = self.max_size * 1.0 / max(newh, neww)
+            newh = newh * scale
+            neww = neww * scale
+        return ResizeTransform(h, w, int(newh + 0.5), int(neww + 0.5))
+
+
+class RandomFlip:
+    def __init__(self, prob=0.5, *, horizontal=True, vertical=False):
+        self.prob, self.horizontal = prob, horizontal
+
+    def get_transform(self, image):
+        import numpy as np
+        h, w = image.shape[:2]
+        if np.random.uniform() < self.prob:
+            return HFlipTransform(w) if self.horizontal else VFlipTransform(h)
+        return NoOpTransform()
+
+
+def apply_augmentations(augmentations, image):
+    tfms = []
+    for aug in augmentations:
+        t = aug.get_transform(image)
+        image = t.apply_image(image)
+        tfms.append(t)
+    return image, TransformList(tfms)
+
+
 def install(reference_root=REFERENCE_ROOT):
     """Put the stand-in modules and the reference's `tridet` package on the import path."""
     global _INSTALLED
@@ -717,22 +898,18 @@ def install(reference_root=REFERENCE_ROOT):
         m.__spec__ = importlib.machinery.ModuleSpec(pkg, None, is_package=True)
         sys.modules[pkg] = m
 
-    # detectron2.data.transforms pieces tridet/data/augmentations/resize_transform.py binds to (type registry only)
-    class _ResizeTransform:
-        _types = {}
-
-        def __init__(self, h, w, new_h, new_w, interp=None):
-            self.h, self.w, self.new_h, self.new_w = h, w, new_h, new_w
-
-        @classmethod
-        def register_type(cls, data_type, func):
-            cls._types[data_type] = func
-
-        def apply_intrinsics(self, intrinsics):
-            return self._types["intrinsics"](self, intrinsics)
-
+    # fvcore.transforms / detectron2.data.transforms: the transform machinery the dataset mapper and the TTA wrapper use
+    _mod("fvcore.transforms", NoOpTransform=NoOpTransform, HFlipTransform=HFlipTransform, VFlipTransform=VFlipTransform,
+         Transform=Transform, TransformList=TransformList)
+    _mod("fvcore.transforms.transform", NoOpTransform=NoOpTransform, HFlipTransform=HFlipTransform,
+         VFlipTransform=VFlipTransform, Transform=Transform, TransformList=TransformList)
     _mod("detectron2.data")
-    _mod("detectron2.data.transforms", ResizeTransform=_ResizeTransform, ResizeShortestEdge=object)
+    _mod("detectron2.data.detection_utils", read_image=_noop)
+    _mod("detectron2.data.transforms", ResizeTransform=ResizeTransform, ResizeShortestEdge=ResizeShortestEdge,
+         RandomFlip=RandomFlip, apply_augmentations=apply_augmentations)
+    # the reference's own registrations of intrinsics / box3d handlers on those classes
+    import tridet.data.augmentations.resize_transform  # noqa: F401,E402
+    import tridet.data.augmentations.flip_transform  # noqa: F401,E402
     _mod("tridet.data.datasets.nuscenes.build", MAX_NUM_ATTRIBUTES=3)  # tridet/data/datasets/nuscenes/build.py:77
 
 

@@ -90,10 +90,11 @@ def _expected_input(resized_list, Hp, Wp):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cases", [[0], [1, 2], [3, 4, 5], [6, 7], [0, 1, 2, 3, 4, 5, 6, 7]])
-def test_resize_preprocess_kernel_bit_exact(cases):
-    """dd3d_op_resize_preprocess == PIL-exact oracle resize followed by (x - mean) / std in fp32, rounded to bf16, zero
-    padded; ragged batches share one slot size."""
+@pytest.mark.parametrize("cases,flip", [([0], 0), ([1, 2], 0), ([3, 4, 5], 1), ([6, 7], 0), ([0, 1, 2, 3, 4, 5, 6, 7], 1)])
+def test_resize_preprocess_kernel_bit_exact(cases, flip):
+    """dd3d_op_resize_preprocess == PIL-exact oracle resize (then np.flip(axis=1) for the test-time-augmentation flip on
+    every other image) followed by (x - mean) / std in fp32, rounded to bf16, zero padded; ragged batches share one slot
+    size."""
     from dd3d_b200 import lib
     L = lib.load()
     raws = [raw_image(c, *RESIZE_CASES[c][0]) for c in cases]
@@ -110,12 +111,16 @@ def test_resize_preprocess_kernel_bit_exact(cases):
     d_raw = buf.cuda()
     d_out = torch.full((Bn, Hp, Wp, 4), 7.0, dtype=torch.bfloat16, device="cuda")
     mean, std = (C.c_float * 3)(*MEAN), (C.c_float * 3)(*STD)
+    flips = torch.tensor([(b % 2 == 0) and flip for b in range(Bn)], dtype=torch.int32)
     st = L.dd3d_op_resize_preprocess(C.c_void_p(d_raw.data_ptr()), raw_h, raw_w, C.c_void_p(raw_sizes.data_ptr()),
-                                     C.c_void_p(new_sizes.data_ptr()), C.c_void_p(d_out.data_ptr()), Bn, Hp, Wp, mean, std,
+                                     C.c_void_p(new_sizes.data_ptr()), C.c_void_p(flips.data_ptr()) if flip else None,
+                                     C.c_void_p(d_out.data_ptr()), Bn, Hp, Wp, mean, std,
                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert st == 0
     torch.cuda.synchronize()
-    exp = _expected_input([IO.pil_resize_bilinear(r, *n) for r, n in zip(raws, news)], Hp, Wp)
+    resized = [IO.pil_resize_bilinear(r, *n) for r, n in zip(raws, news)]
+    resized = [np.ascontiguousarray(np.flip(r, axis=1)) if f else r for r, f in zip(resized, flips.tolist())]
+    exp = _expected_input(resized, Hp, Wp)
     assert torch.equal(d_out.cpu().view(torch.int16), exp.view(torch.int16))
 
 
