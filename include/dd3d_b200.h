@@ -210,8 +210,8 @@ int dd3d_op_resize_preprocess(const uint8_t* d_raw, int raw_h, int raw_w, const 
  * tridet/modeling/dd3d/test_time_augmentation.py:160-171,190-239) for ONE image: d_dets [num_views][cap] / d_counts
  * [num_views] are the views' detections (dd3d_forward* with do_postprocess = 0); 2-D boxes, 3-D boxes and the projected
  * centres are mapped back to the original image, concatenated in view order and reduced by one class-aware NMS on
- * scores_3d (do_nms = 0: no suppression).  d_out: dd3d_op_tta_merged_cap(num_views, cap) slots, always in descending
- * scores_3d; field `level` = view index.  d_flags bit 4: more merged detections than slots. */
+ * scores_3d (do_nms = 0: the plain concatenation in view order).  d_out: dd3d_op_tta_merged_cap(num_views, cap) slots,
+ * descending scores_3d after the NMS; field `level` = view index.  d_flags bit 4: more merged detections than slots. */
 int dd3d_op_tta_merged_cap(int num_views, int cap);
 int64_t dd3d_op_tta_merge_scratch_bytes(int num_views, int cap);
 int dd3d_op_tta_merge(const dd3d_det* d_dets, const int32_t* d_counts, const dd3d_tta_view* h_views, int num_views, int cap,
