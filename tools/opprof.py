@@ -1,5 +1,6 @@
-"""Dev tool: per-op device times of one forward (python tools_opprof.py v2_99 32)."""
-import sys, torch
+"""Dev tool: per-op device times of one forward (python tools/opprof.py v2_99 32)."""
+import os, sys, torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from bench import WORKLOADS
 from dd3d_b200.config import get_cfg
 from dd3d_b200.meta_arch import DD3DB200
