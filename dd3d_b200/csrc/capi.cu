@@ -246,7 +246,8 @@ int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch,
     g.H = Ho;
     g.W = Wo;
     choose_tile(Ho, Wo, &g.th, &g.tw);
-    bool ok = make_weight_map(&p.w_map, d_w, taps * kchunks * kBlockK, cout_pad, block_n);
+    bool ok = true;
+    p.cta2 = conv_use_cta2();
     p.halo = conv_prefer_halo(taps, stride, block_n, 1, &Ho, &Wo) ? conv_halo_mode() : 0;
     if (p.halo) {
         g.th = kHaloTh;
@@ -276,6 +277,10 @@ int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch,
         g.res_W = res_up2 ? Wo / 2 : Wo;
     }
     conv_finalize_params(&p);
+    if (!make_weight_map(&p.w_map, d_w, taps * kchunks * kBlockK, cout_pad, p.cta2 ? block_n / 2 : block_n)) {
+        fprintf(stderr, "dd3d_op_conv2d: %s\n", conv_last_error());
+        return DD3D_ERR_CUDA;
+    }
     return cuda_status(launch_conv(p, device_sms(), static_cast<cudaStream_t>(stream)), nullptr);
 }
 

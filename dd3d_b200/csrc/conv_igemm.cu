@@ -54,12 +54,17 @@ constexpr int kBarBytes = 512;
 
 struct TileCoord {
     int seg, img, y0, x0, n_blk;
+    bool valid;  // false: the padding tile of an odd CTA pair (coordinates beyond the batch: loads zero-fill, stores skip)
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work) {
+// CTA pair (CTA2): work item = (pair of consecutive M-tiles, n-block); CTA `rank` of the pair owns tile 2 * pair + rank.
+template <bool CTA2>
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work, int rank) {
     TileCoord t;
     t.n_blk = work % p.n_blocks;
     int mt = work / p.n_blocks;
+    if (CTA2) mt = 2 * mt + rank;
+    t.valid = mt < p.total_tiles;
     int s = 0;
 #pragma unroll
     for (int i = 1; i < kMaxSeg; ++i) {
@@ -97,13 +102,22 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-template <bool HALO>
+template <bool HALO, bool CTA2>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // generic: num_stages x [A 16 KiB | B block_n*128].  halo: num_stages x [B block_n*128], then 3 x [A patch 23 KiB]
-    const int stage_bytes = (HALO ? 0 : kABytes) + p.block_n * 128;
+    // CTA pair: one tcgen05.mma.cta_group::2 (M = 256) covers the two CTAs' pixel tiles; each CTA stages its own A tile
+    // and HALF of the weight tile (b_rows rows), which halves the shared-memory traffic per MMA -- the limiter of the
+    // single-CTA kernel (operand reads + TMA writes exceed 128 B/clk for N <= 256).
+    const int rank = CTA2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+    const bool leader = rank == 0;
+    const int w_first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int w_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int w_total = CTA2 ? p.pair_work : p.total_work;
+    const int b_rows = CTA2 ? p.block_n / 2 : p.block_n;
+    const int stage_bytes = (HALO ? 0 : kABytes) + b_rows * 128;
     uint8_t* halo_a = smem + p.num_stages * stage_bytes;
     uint8_t* staging = halo_a + (HALO ? kHaloAStages * kHaloABytes : 0);
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
@@ -130,7 +144,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+            ptx::mbar_init(&tempty_bar[i], CTA2 ? 8 : 4);  // one arrival per epilogue warp (of both CTAs of a pair)
         }
         for (int i = 0; i < kHaloAStages; ++i) {
             ptx::mbar_init(&afull_bar[i], 1);
@@ -139,13 +153,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, p.tmem_cols);
-        ptx::tmem_relinquish();
+        if (CTA2) {
+            ptx::tmem_alloc2(tmem_slot, p.tmem_cols);
+            ptx::tmem_relinquish2();
+        } else {
+            ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (CTA2) ptx::cluster_sync();  // the peer's barriers and TMEM must exist before anything targets them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // the leader's barriers as seen from either CTA of the pair (shared::cluster addresses; 8 bytes per barrier)
+    const uint32_t full0 = CTA2 ? ptx::mapa(&full_bar[0], 0) : 0;
+    const uint32_t afull0 = CTA2 ? ptx::mapa(&afull_bar[0], 0) : 0;
+    const uint32_t tempty0 = CTA2 ? ptx::mapa(&tempty_bar[0], 0) : 0;
     // Programmatic dependent launch: everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the
     // tail of the previous kernel in the stream; from here on we touch its outputs, so wait for it, and let the next
     // kernel start its own prologue as our CTAs retire.
@@ -159,17 +183,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         // generic variant, weight (B) producer in the halo variant.  Whole warp runs the loop; one elected lane issues.
         int stage = 0;
         uint32_t phase = 0;
-        for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
-            const TileCoord t = decode_tile(p, work);
+        for (int work = w_first; work < w_total; work += w_step) {
+            const TileCoord t = decode_tile<CTA2>(p, work, rank);
             const ConvSeg& g = p.seg[t.seg];
             if (HALO) {
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     for (int tap = 0; tap < 9; ++tap) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                         if (elect_one()) {
-                            ptx::mbar_expect_tx(&full_bar[stage], p.block_n * 128);
-                            ptx::tma_load_2d(smem + stage * stage_bytes, &p.w_map, &full_bar[stage],
-                                             (tap * p.kchunks + kc) * kBlockK, t.n_blk * p.block_n);
+                            if (CTA2) {  // the leader arms the barrier for both halves of the weight tile
+                                if (leader) ptx::mbar_expect_tx(&full_bar[stage], p.block_n * 128);
+                                ptx::tma2_load_2d(smem + stage * stage_bytes, &p.w_map, full0 + stage * 8,
+                                                  (tap * p.kchunks + kc) * kBlockK, t.n_blk * p.block_n + rank * b_rows);
+                            } else {
+                                ptx::mbar_expect_tx(&full_bar[stage], p.block_n * 128);
+                                ptx::tma_load_2d(smem + stage * stage_bytes, &p.w_map, &full_bar[stage],
+                                                 (tap * p.kchunks + kc) * kBlockK, t.n_blk * p.block_n);
+                            }
                         }
                         __syncwarp();
                         if (++stage == p.num_stages) {
@@ -187,16 +217,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                     if (elect_one()) {
                         uint8_t* a_dst = smem + stage * stage_bytes;
-                        ptx::mbar_expect_tx(&full_bar[stage], kABytes);  // the weight tile is armed + issued by warp 6
-                        if (p.stride == 1) {
+                        // the weight tile is armed + issued by warp 6; in a CTA pair the leader arms for both CTAs
+                        if (!CTA2 || leader) ptx::mbar_expect_tx(&full_bar[stage], CTA2 ? 2 * kABytes : kABytes);
+                        // stride 2: input (2*oy + r - 1, 2*ox + s - 1) in the parity-split view [B][H/2][2][W/2][wp*C..]
+                        const int wp = (s == 1) ? 0 : 1;
+                        const int dw = (s == 0) ? -1 : 0;
+                        const int hp = (r == 1) ? 0 : 1;
+                        const int dh = (r == 0) ? -1 : 0;
+                        if (CTA2) {
+                            if (p.stride == 1) {
+                                ptx::tma2_load_4d(a_dst, &g.in_map[0], full0 + stage * 8, kc * kBlockK, t.x0 + s - 1,
+                                                  t.y0 + r - 1, t.img);
+                            } else {
+                                ptx::tma2_load_5d(a_dst, &g.in_map[wp], full0 + stage * 8, kc * kBlockK, t.x0 + dw, hp,
+                                                  t.y0 + dh, t.img);
+                            }
+                        } else if (p.stride == 1) {
                             ptx::tma_load_4d(a_dst, &g.in_map[0], &full_bar[stage], kc * kBlockK, t.x0 + s - 1,
                                              t.y0 + r - 1, t.img);
                         } else {
-                            // input (2*oy + r - 1, 2*ox + s - 1) in the parity-split view [B][H/2][2][W/2][wp*C..]
-                            const int wp = (s == 1) ? 0 : 1;
-                            const int dw = (s == 0) ? -1 : 0;
-                            const int hp = (r == 1) ? 0 : 1;
-                            const int dh = (r == 0) ? -1 : 0;
                             ptx::tma_load_5d(a_dst, &g.in_map[wp], &full_bar[stage], kc * kBlockK, t.x0 + dw, hp,
                                              t.y0 + dh, t.img);
                         }
@@ -215,14 +254,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t b_bytes = p.block_n * 128;
-            for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+            for (int work = w_first; work < w_total; work += w_step) {
                 const int n0 = (work % p.n_blocks) * p.block_n;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 7);
                     if (elect_one()) {
-                        ptx::mbar_expect_tx(&full_bar[stage], b_bytes);
-                        ptx::tma_load_2d(smem + stage * stage_bytes + kABytes, &p.w_map, &full_bar[stage], kb * kBlockK,
-                                         n0);
+                        if (CTA2) {
+                            if (leader) ptx::mbar_expect_tx(&full_bar[stage], b_bytes);  // both halves
+                            ptx::tma2_load_2d(smem + stage * stage_bytes + kABytes, &p.w_map, full0 + stage * 8,
+                                              kb * kBlockK, n0 + rank * b_rows);
+                        } else {
+                            ptx::mbar_expect_tx(&full_bar[stage], b_bytes);
+                            ptx::tma_load_2d(smem + stage * stage_bytes + kABytes, &p.w_map, &full_bar[stage],
+                                             kb * kBlockK, n0);
+                        }
                     }
                     __syncwarp();
                     if (++stage == p.num_stages) {
@@ -236,15 +281,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             // [18][10][64 ch] (180 rows of 128 B, 128B-swizzled, zero-filled outside the image) per 64-channel block
             int as = 0;
             uint32_t aphase = 0;
-            for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
-                const TileCoord t = decode_tile(p, work);
+            for (int work = w_first; work < w_total; work += w_step) {
+                const TileCoord t = decode_tile<CTA2>(p, work, rank);
                 const ConvSeg& g = p.seg[t.seg];
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(&aempty_bar[as], aphase ^ 1, 5);
                     if (elect_one()) {
-                        ptx::mbar_expect_tx(&afull_bar[as], kHaloPW * kHaloPH * 128);
-                        ptx::tma_load_4d(halo_a + as * kHaloABytes, &g.in_map[0], &afull_bar[as], kc * kBlockK,
-                                         t.x0 - 1, t.y0 - 1, t.img);
+                        if (CTA2) {
+                            if (leader) ptx::mbar_expect_tx(&afull_bar[as], 2 * kHaloPW * kHaloPH * 128);
+                            ptx::tma2_load_4d(halo_a + as * kHaloABytes, &g.in_map[0], afull0 + as * 8, kc * kBlockK,
+                                              t.x0 - 1, t.y0 - 1, t.img);
+                        } else {
+                            ptx::mbar_expect_tx(&afull_bar[as], kHaloPW * kHaloPH * 128);
+                            ptx::tma_load_4d(halo_a + as * kHaloABytes, &g.in_map[0], &afull_bar[as], kc * kBlockK,
+                                             t.x0 - 1, t.y0 - 1, t.img);
+                        }
                     }
                     __syncwarp();
                     if (++as == kHaloAStages) {
@@ -255,9 +306,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             }
         }
     } else if (warp == 1) {
+      if (!CTA2 || leader) {  // CTA pair: only the leader issues; its MMAs read both CTAs' smem and write both TMEMs
         // -------------------------------------------------------------------- warp 1: tcgen05.mma issuer
         // Descriptor high word is constant; the low word is (addr >> 4) | LBO, advanced by 2 (= 32 bytes) per K=16 step.
-        const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, p.block_n);
+        const uint32_t idesc = ptx::make_idesc_bf16(CTA2 ? 2 * kBlockM : kBlockM, p.block_n);
         constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);                   // SBO 1024, v1, SW128
         constexpr uint32_t kHaloDescHi = ((kHaloPW * 128u) >> 4) | (1u << 14) | (2u << 29);     // SBO = 10 pixels
         const uint32_t lo0 = (ptx::smem_u32(smem) >> 4) | (1u << 16);
@@ -269,7 +321,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         uint32_t acc_phase = 0;
         int as = 0;
         uint32_t aphase = 0;
-        for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+        for (int work = w_first; work < w_total; work += w_step) {
             ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * p.chains * p.block_n;  // chain c lives at + c * block_n
@@ -290,11 +342,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                                 if (k < ksteps) {  // channels beyond cin are zero padding: skip their K steps
                                     const uint64_t adesc = (static_cast<uint64_t>(kHaloDescHi) << 32) | (a_tap + 2 * k);
                                     const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
-                                    ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                                    if (CTA2) {
+                                        ptx::umma2_bf16(d_tmem, adesc, bdesc, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                                    } else {
+                                        ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                                    }
                                 }
                             }
-                            ptx::umma_commit(&empty_bar[stage]);
-                            if (tap == 8) ptx::umma_commit(&aempty_bar[as]);  // patch free once its 36 MMAs retire
+                            if (CTA2) {
+                                ptx::umma_commit2(&empty_bar[stage], 3);
+                                if (tap == 8) ptx::umma_commit2(&aempty_bar[as], 3);
+                            } else {
+                                ptx::umma_commit(&empty_bar[stage]);
+                                if (tap == 8) ptx::umma_commit(&aempty_bar[as]);  // patch free once its 36 MMAs retire
+                            }
                         }
                         __syncwarp();
                         if (++stage == p.num_stages) {
@@ -324,10 +385,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                                 const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
                                 const int j = kb * (kBlockK / 16) + k;  // MMA index within the tile
                                 const int chain = j & (p.chains - 1);   // optional split-K accumulator chains
-                                ptx::umma_bf16(d_tmem + chain * p.block_n, adesc, bdesc, idesc, j >= p.chains ? 1u : 0u);
+                                if (CTA2) {
+                                    ptx::umma2_bf16(d_tmem + chain * p.block_n, adesc, bdesc, idesc, j >= p.chains ? 1u : 0u);
+                                } else {
+                                    ptx::umma_bf16(d_tmem + chain * p.block_n, adesc, bdesc, idesc, j >= p.chains ? 1u : 0u);
+                                }
                             }
                         }
-                        ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                        // frees the smem slot (of both CTAs of a pair) once these MMAs retire
+                        if (CTA2) {
+                            ptx::umma_commit2(&empty_bar[stage], 3);
+                        } else {
+                            ptx::umma_commit(&empty_bar[stage]);
+                        }
                     }
                     __syncwarp();
                     if (++stage == p.num_stages) {
@@ -336,13 +406,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     }
                 }
             }
-            if (elect_one()) ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+            if (elect_one()) {  // accumulator complete -> epilogue (of both CTAs of a pair)
+                if (CTA2) {
+                    ptx::umma_commit2(&tfull_bar[acc], 3);
+                } else {
+                    ptx::umma_commit(&tfull_bar[acc]);
+                }
+            }
             __syncwarp();
             if (++acc == p.acc_stages) {
                 acc = 0;
                 acc_phase ^= 1;
             }
         }
+      }
     } else {
         // ---------------------------------------------------------------- epilogue (warps 2..5)
         const int q = warp & 3;  // TMEM lane quarter accessible to this warp
@@ -351,13 +428,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         int acc = 0;
         uint32_t acc_phase = 0;
         int sbuf = 0;
-        for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
-            const TileCoord t = decode_tile(p, work);
+        for (int work = w_first; work < w_total; work += w_step) {
+            const TileCoord t = decode_tile<CTA2>(p, work, rank);
             const ConvSeg& g = p.seg[t.seg];
             const int ly = row / g.tw;
             const int lx = row - ly * g.tw;
             const int oy = t.y0 + ly, ox = t.x0 + lx;
-            const bool in_img = (oy < g.H) && (ox < g.W);
+            const bool in_img = t.valid && (oy < g.H) && (ox < g.W);
             const int n_base = t.n_blk * p.block_n;
 
             const __nv_bfloat16* res_ptr = nullptr;
@@ -470,10 +547,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
                     ptx::named_bar_sync(1, 128);
                     if (store_leader) {
-                        ptx::tma_store_4d(&g.out_map, stag, n_base + c0, t.x0, t.y0, t.img);
+                        if (t.valid) ptx::tma_store_4d(&g.out_map, stag, n_base + c0, t.x0, t.y0, t.img);
                         ptx::tma_store_commit();
                     }
-                    if (g.pool_partial != nullptr) {
+                    if (g.pool_partial != nullptr && t.valid) {
                         // eSE global-average-pool, fused: per-tile channel sums of the bf16 tile just staged (exactly the
                         // values the reference pools, vovnet.py:181).  Thread e covers channels 8*(e&7).. of rows
                         // (e>>3) + 16*i; the 4 row-groups of a warp are shuffle-reduced; one fp32 partial per
@@ -517,7 +594,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (CTA2) {
+                    ptx::mbar_arrive_cluster(tempty0 + acc * 8);  // the leader's MMA warp waits for both CTAs' epilogues
+                } else {
+                    ptx::mbar_arrive(&tempty_bar[acc]);
+                }
+            }
             if (++acc == p.acc_stages) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -528,9 +611,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (CTA2) ptx::cluster_sync();  // neither CTA may retire while the other can still target its smem / TMEM / barriers
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+        if (CTA2) {
+            ptx::tmem_dealloc2(tmem_base, p.tmem_cols);
+        } else {
+            ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+        }
     }
 }
 
@@ -667,7 +755,20 @@ void conv_finalize_params(ConvParams* p) {
         tile += g.tiles_x * g.tiles_y * p->B;
     }
     p->total_work = tile * p->n_blocks;
-    const int stage_bytes = (p->halo ? 0 : kABytes) + p->block_n * 128;
+    p->total_tiles = tile;
+    // CTA pairs pay off where the weight tile is large (measured per layer, profiles/r01d_cta2_ab.md): N >= 160 and at
+    // least two waves of tiles; small-N layers (stem, OSA2) are issue/epilogue-bound and lose a few % to the pairing.
+    if (p->cta2 == 2) {  // auto
+        static int min_n = -1;
+        if (min_n < 0) {
+            const char* e = getenv("DD3D_CONV_CTA2_MINN");
+            min_n = e ? atoi(e) : 160;
+        }
+        p->cta2 = (p->block_n >= min_n && tile >= 4 * 74) ? 1 : 0;
+    }
+    if (p->cta2 && (tile < 2 || (p->block_n % 16) != 0)) p->cta2 = 0;
+    p->pair_work = ((tile + 1) / 2) * p->n_blocks;
+    const int stage_bytes = (p->halo ? 0 : kABytes) + (p->cta2 ? p->block_n / 2 : p->block_n) * 128;
     const int fixed = 2 * kStagingBytes + 1024 /*alignment slack*/ + kBarBytes +
                       (p->halo ? kHaloAStages * kHaloABytes : 0);
     int stages = (kSmemBudget - fixed) / stage_bytes;
@@ -697,39 +798,67 @@ void conv_finalize_params(ConvParams* p) {
     p->tmem_cols = cols;
 }
 
+int conv_use_cta2() {  // 0 never, 1 always (where legal), 2 auto (per-layer rule in conv_finalize_params)
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("DD3D_CONV_CTA2");
+        mode = e ? (!strcmp(e, "auto") ? 2 : (atoi(e) != 0)) : kConvCta2Default;
+    }
+    return mode;
+}
+
 cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
-    const int stage_bytes = (p.halo ? 0 : kABytes) + p.block_n * 128;
+    const int stage_bytes = (p.halo ? 0 : kABytes) + (p.cta2 ? p.block_n / 2 : p.block_n) * 128;
     const int smem_bytes = p.num_stages * stage_bytes + 2 * kStagingBytes + 1024 + kBarBytes +
                            (p.halo ? kHaloAStages * kHaloABytes : 0);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e =
-            cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kSmemBudget);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+            e = cudaFuncSetAttribute(conv_igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     if (p.total_work <= 0) return cudaSuccess;
-    const int grid = std::min(p.total_work, num_sms);
+    // CTA pairs: an even grid of 2-CTA clusters (one pair per TPC), each pair loops over pair-work items
+    const int grid = p.cta2 ? 2 * std::min(p.pair_work, num_sms / 2) : std::min(p.total_work, num_sms);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kConvThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
     static int use_pdl = -1;
     if (use_pdl < 0) {
         const char* e = getenv("DD3D_NO_PDL");
         use_pdl = (e && atoi(e)) ? 0 : 1;
     }
+    if (use_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (p.cta2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = use_pdl ? 1 : 0;
-    return p.halo ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, p)
-                  : cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, p);
+    cfg.numAttrs = na;
+    if (p.cta2)
+        return p.halo ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, p)
+                      : cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, true>, p);
+    return p.halo ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, p)
+                  : cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, false>, p);
 }
 
 }  // namespace dd3d

@@ -55,7 +55,12 @@ struct ConvParams {
     int cin;          // real input channels (the zero-padded K steps of the last 64-channel block are skipped)
     int last_ksteps;  // K=16 steps of the last channel block: ceil((cin - 64*(kchunks-1)) / 16)
     int halo;  // 1: 3x3 stride-1 halo-reuse variant (tile 16x8, A patch loaded once per 64-channel block)
+    int cta2;         // 1: CTA-pair variant (cluster of 2, tcgen05.mma.cta_group::2, M = 256); w_map box = block_n / 2 rows
+    int total_tiles;  // sum of M-tiles over the segments
+    int pair_work;    // ceil(total_tiles / 2) * n_blocks
 };
+static_assert(sizeof(ConvParams) <= 4096, "kernel parameter space");
+constexpr int kConvCta2Default = 2;  // auto; DD3D_CONV_CTA2=0|1|auto overrides
 
 // Host helpers (conv_igemm.cu)
 const char* conv_last_error();
@@ -63,6 +68,9 @@ bool make_act_map(CUtensorMap* map, const void* base, int B, int H, int W, int C
 bool make_act_map_s2(CUtensorMap* map, const void* base, int wp, int B, int H, int W, int C, int pitch, int th,
                      int tw);
 bool make_weight_map(CUtensorMap* map, const void* base, int ktot, int cout_pad, int block_n);
+// CTA-pair policy for ConvParams::cta2 before conv_finalize_params: 0 never, 1 always, 2 auto (finalize decides; the
+// w_map box must then be block_n / 2 rows iff the finalized cta2 is 1)
+int conv_use_cta2();
 void choose_tile(int H, int W, int* th, int* tw);
 int conv_tiles_per_image(int H, int W);  // M-tiles per image of the generic tiling
 // Halo variant (3x3, stride 1): non-swizzled [8-channel group][18x10 pixels][8 ch] patch loads.

@@ -138,6 +138,7 @@ const ConvLayer& Engine::conv_layer(const std::string& key, const std::vector<st
     L.d_w = static_cast<__nv_bfloat16*>(dev_alloc(packed.size() * 2));
     cuda_check(cudaMemcpy(L.d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice), "upload conv weights");
     if (!make_weight_map(&L.w_map, L.d_w, L.ktot, L.cout_pad, L.block_n)) fail(DD3D_ERR_CUDA, conv_last_error());
+    if (!make_weight_map(&L.w_map_half, L.d_w, L.ktot, L.cout_pad, L.block_n / 2)) fail(DD3D_ERR_CUDA, conv_last_error());
     return convs.emplace(key, L).first->second;
 }
 
@@ -247,7 +248,7 @@ struct Builder {
         op.type = Op::CONV;
         ConvParams& p = op.conv;
         memset(&p, 0, sizeof(p));
-        p.w_map = L.w_map;
+        p.cta2 = conv_use_cta2();  // policy; conv_finalize_params turns it into the per-layer decision
         p.nseg = static_cast<int>(segs.size());
         p.B = B;
         p.taps = L.taps;
@@ -312,6 +313,7 @@ struct Builder {
             }
         }
         conv_finalize_params(&p);
+        p.w_map = p.cta2 ? L.w_map_half : L.w_map;
         for (int s = 0; s < p.nseg; ++s)
             op.flops += 2.0 * B * p.seg[s].H * p.seg[s].W * static_cast<double>(L.cout) * L.cin * L.taps;
         P->ops.push_back(op);

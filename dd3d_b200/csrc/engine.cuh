@@ -36,6 +36,7 @@ struct ConvLayer {
     int cin, cout, ksize, taps, kchunks, ktot, cout_pad, block_n, n_blocks;
     __nv_bfloat16* d_w;
     CUtensorMap w_map;
+    CUtensorMap w_map_half;  // box of block_n / 2 rows: each CTA of a pair loads half of the weight tile
 };
 struct Epilogue {
     float* d_scale;

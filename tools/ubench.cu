@@ -12,8 +12,43 @@
 
 using namespace dd3d;
 
+__device__ __forceinline__ bool elect_one_() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// generic K-major smem descriptor: layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B, 0 = none (interleaved)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout) << 61;
+    return d;
+}
+
+// operand descriptor of K16 slice k (0..3) of a 64-channel k-block stored in layout `lay` at `base`:
+//   0: SW128  rows of 128 B, slice = +32 B inside the row, 8-row groups 1024 B apart
+//   1: SW32   four sub-tiles [rows][32 B] (rows*32 B each), 8-row groups 256 B apart
+//   2: SW64   two sub-tiles [rows][64 B], slice = +32 B inside the row, 8-row groups 512 B apart
+//   3: none   core matrices 8 rows x 16 B contiguous; K chunks `rows*16` B apart, 8-row groups 128 B apart
+__device__ __forceinline__ uint64_t slice_desc(uint32_t base, int k, int lay, int rows) {
+    switch (lay) {
+        case 1: return make_desc(base + k * rows * 32, 16, 256, 6);
+        case 2: return make_desc(base + (k >> 1) * rows * 64 + (k & 1) * 32, 16, 512, 4);
+        case 3: return make_desc(base + k * 2 * rows * 16, rows * 16, 128, 0);
+        default: return make_desc(base + k * 32, 16, 1024, 2);
+    }
+}
+
 __global__ void __launch_bounds__(128, 1)
-mma_kernel(int N, int chains, int cper, int iters, long long* cycles) {
+mma_kernel(int N, int chains, int cper, int iters, int lay_a, int lay_b, long long* cycles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
@@ -33,30 +68,28 @@ mma_kernel(int N, int chains, int cper, int iters, long long* cycles) {
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = slot;
-    if (threadIdx.x == 0) {
+    if (warp == 0) {  // whole-warp loop, elect.sync around the issue only (the conv kernel's issue pattern)
         const uint32_t idesc = ptx::make_idesc_bf16(128, N);
         const uint32_t a = ptx::smem_u32(smem), b = a + 16384;
+        uint64_t ad[4], bd[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ad[k] = slice_desc(a, k, lay_a, 128);
+            bd[k] = slice_desc(b, k, lay_b, N);
+        }
         uint32_t phase = 0;
         const long long t0 = clock64();
-        for (int i = 0; i < iters; ++i) {
-            const int k = i & 3;
-            ptx::umma_bf16(tmem + (i % chains) * N, ptx::make_sw128_desc(a + k * 32), ptx::make_sw128_desc(b + k * 32),
-                           idesc, i >= chains);
-            if ((i + 1) % cper == 0) {
+        for (int i = 0; i < iters; i += 4) {  // one "k-block": 4 MMAs + a commit, like the conv kernel
+            if (elect_one_()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ptx::umma_bf16(tmem, ad[k], bd[k], idesc, (i | k) != 0 ? 1u : 0u);
                 ptx::umma_commit(&bar);
-                if (cper >= 1024 || (i + 1) == iters) {  // only wait at the very end (or for huge groups)
-                    ptx::mbar_wait(&bar, phase, 1);
-                    phase ^= 1;
-                } else {
-                    // do not wait: the barrier just flips phases
-                    phase ^= 1;
-                }
             }
+            __syncwarp();
+            phase ^= 1;
         }
-        ptx::umma_commit(&bar);
-        // final drain: poll until the LAST commit's phase completes
-        ptx::mbar_wait(&bar, phase, 2);
-        cycles[blockIdx.x] = clock64() - t0;
+        ptx::mbar_wait(&bar, phase ^ 1, 2);
+        if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -133,24 +166,27 @@ int main() {
     cudaEventCreate(&e1);
     printf("# mode0: MMA M128xNxK16 from ONE thread per SM, 148 CTAs. ns per MMA (event time / iters)\n");
     const int iters = 20000;
-    for (int N : {16, 64, 128, 256}) {
-        for (int chains : {1, 2}) {
-            for (int cper : {4, 100000}) {
-                if (chains * N > 512) continue;
-                mma_kernel<<<148, 128, 50 * 1024>>>(N, chains, cper, iters, d_cycles);
+    const char* lname[4] = {"SW128", "SW32", "SW64", "NONE"};
+    for (int N : {16, 64, 128, 192, 256}) {
+        for (int lay_a : {0, 1, 2, 3}) {
+            for (int lay_b : {0, 1}) {
+                if (lay_b == 1 && lay_a != 1) continue;
+                const int chains = 1, cper = 4;
+                mma_kernel<<<148, 128, 50 * 1024>>>(N, chains, cper, iters, lay_a, lay_b, d_cycles);
                 cudaDeviceSynchronize();
                 cudaEventRecord(e0);
-                mma_kernel<<<148, 128, 50 * 1024>>>(N, chains, cper, iters, d_cycles);
+                mma_kernel<<<148, 128, 50 * 1024>>>(N, chains, cper, iters, lay_a, lay_b, d_cycles);
                 cudaEventRecord(e1);
                 cudaError_t err = cudaDeviceSynchronize();
                 float ms = 0;
                 cudaEventElapsedTime(&ms, e0, e1);
                 cudaMemcpy(h, d_cycles, sizeof(h), cudaMemcpyDeviceToHost);
-                printf("N=%3d chains=%d commit_every=%6d : %7.1f ns/MMA  %7.1f cycles/MMA (clock64)  %s\n", N, chains, cper,
+                printf("N=%3d A=%-5s B=%-5s : %7.1f ns/MMA  %7.1f cycles/MMA (clock64)  %s\n", N, lname[lay_a], lname[lay_b],
                        ms * 1e6 / iters, (double)h[0] / iters, cudaGetErrorString(err));
             }
         }
     }
+    if (getenv("UBENCH_MMA_ONLY")) return 0;
     // TMA
     const int rows_total = 1 << 20;  // 1M rows x 128 B = 128 MB (>= L2)
     void* d_mat;
