@@ -57,12 +57,26 @@ struct TileCoord {
     bool valid;  // false: the padding tile of an odd CTA pair (coordinates beyond the batch: loads zero-fill, stores skip)
 };
 
+// x / d for 0 <= x < 2^24 without the ~40-instruction integer division: fp32 reciprocal estimate, corrected by one.
+// (every warp decodes every tile; the divisions were 10 % of the epilogue warps' samples, profiles/r01d_cta2_ab.md)
+__device__ __forceinline__ int fast_div(int x, int d, float inv_d) {
+    int q = __float2int_rz(__int2float_rz(x) * inv_d);
+    const int r = x - q * d;
+    q += (r >= d) ? 1 : 0;
+    q -= (r < 0) ? 1 : 0;
+    return q;
+}
+
 // CTA pair (CTA2): work item = (pair of consecutive M-tiles, n-block); CTA `rank` of the pair owns tile 2 * pair + rank.
 template <bool CTA2>
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work, int rank) {
     TileCoord t;
-    t.n_blk = work % p.n_blocks;
-    int mt = work / p.n_blocks;
+    int mt = work;
+    t.n_blk = 0;
+    if (p.n_blocks > 1) {
+        mt = fast_div(work, p.n_blocks, p.inv_n_blocks);
+        t.n_blk = work - mt * p.n_blocks;
+    }
     if (CTA2) mt = 2 * mt + rank;
     t.valid = mt < p.total_tiles;
     int s = 0;
@@ -74,9 +88,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work, 
     const ConvSeg& g = p.seg[s];
     int local = mt - g.tile_begin;
     int per_img = g.tiles_x * g.tiles_y;
-    t.img = local / per_img;
+    t.img = fast_div(local, per_img, g.inv_per_img);
     int r = local - t.img * per_img;
-    int ty = r / g.tiles_x;
+    int ty = fast_div(r, g.tiles_x, g.inv_tiles_x);
     int tx = r - ty * g.tiles_x;
     t.y0 = ty * g.th;
     t.x0 = tx * g.tw;
@@ -468,6 +482,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     } else {
                         ptx::tmem_ld16(t_addr + c0 + h, v);
                     }
+                    // fetch the BN affine of these columns while the TMEM load is in flight (both latencies used to be
+                    // paid back to back by the single epilogue warp of each scheduler: ncu, profiles/r01d_cta2_ab.md)
+                    const int n0 = n_base + c0 + h;  // absolute output channel of v[0]
+                    float4 sc[8], bi[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (4 * i < cols) {
+                            sc[i] = __ldg(reinterpret_cast<const float4*>(g.scale + n0 + 4 * i));
+                            bi[i] = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 4 * i));
+                        }
+                    }
                     ptx::tmem_ld_wait();
                     for (int ch = 1; ch < p.chains; ++ch) {  // add the other split-K chains (fp32)
                         uint32_t w[32];
@@ -481,17 +506,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         for (int i = 0; i < 32; ++i)
                             if (i < cols) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
                     }
-                    const int n0 = n_base + c0 + h;  // absolute output channel of v[0]
                     float y[32];
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         if (i < cols) {
-                            const float4 sc = __ldg(reinterpret_cast<const float4*>(g.scale + n0 + i));
-                            const float4 bi = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
-                            y[i + 0] = fmaf(__uint_as_float(v[i + 0]), sc.x, bi.x);
-                            y[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc.y, bi.y);
-                            y[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc.z, bi.z);
-                            y[i + 3] = fmaf(__uint_as_float(v[i + 3]), sc.w, bi.w);
+                            y[i + 0] = fmaf(__uint_as_float(v[i + 0]), sc[i >> 2].x, bi[i >> 2].x);
+                            y[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc[i >> 2].y, bi[i >> 2].y);
+                            y[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc[i >> 2].z, bi[i >> 2].z);
+                            y[i + 3] = fmaf(__uint_as_float(v[i + 3]), sc[i >> 2].w, bi[i >> 2].w);
                         }
                     }
                     if (res_ptr != nullptr) {
@@ -752,8 +774,11 @@ void conv_finalize_params(ConvParams* p) {
         g.tiles_x = (g.W + g.tw - 1) / g.tw;
         g.tiles_y = (g.H + g.th - 1) / g.th;
         g.tile_begin = tile;
+        g.inv_per_img = 1.0f / static_cast<float>(g.tiles_x * g.tiles_y);
+        g.inv_tiles_x = 1.0f / static_cast<float>(g.tiles_x);
         tile += g.tiles_x * g.tiles_y * p->B;
     }
+    p->inv_n_blocks = 1.0f / static_cast<float>(p->n_blocks);
     p->total_work = tile * p->n_blocks;
     p->total_tiles = tile;
     // CTA pairs pay off where the weight tile is large (measured per layer, profiles/r01d_cta2_ab.md): N >= 160 and at
@@ -825,6 +850,7 @@ cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
         attr_set = true;
     }
     if (p.total_work <= 0) return cudaSuccess;
+    if (p.total_work >= (1 << 24)) return cudaErrorInvalidValue;  // fast_div range of the tile decode
     // CTA pairs: an even grid of 2-CTA clusters (one pair per TPC), each pair loops over pair-work items
     const int grid = p.cta2 ? 2 * std::min(p.pair_work, num_sms / 2) : std::min(p.total_work, num_sms);
     cudaLaunchConfig_t cfg;

@@ -31,6 +31,7 @@ struct ConvSeg {
     int tiles_x, tiles_y;
     int tile_begin;   // index of this segment's first M-tile
     int tw_shift;     // log2(tw)
+    float inv_per_img, inv_tiles_x;  // reciprocals for the division-free tile decode (conv_finalize_params)
     float* pool_partial;  // optional [B][tiles_per_image][4][pool_pitch] per-tile channel sums (eSE avg-pool), or nullptr
     int pool_pitch;
 };
@@ -58,6 +59,7 @@ struct ConvParams {
     int cta2;         // 1: CTA-pair variant (cluster of 2, tcgen05.mma.cta_group::2, M = 256); w_map box = block_n / 2 rows
     int total_tiles;  // sum of M-tiles over the segments
     int pair_work;    // ceil(total_tiles / 2) * n_blocks
+    float inv_n_blocks;
 };
 static_assert(sizeof(ConvParams) <= 4096, "kernel parameter space");
 constexpr int kConvCta2Default = 2;  // auto; DD3D_CONV_CTA2=0|1|auto overrides
