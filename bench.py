@@ -299,6 +299,44 @@ def main():
             d_cnt.copy_(h_cnt, non_blocking=True)
             all_gather_detections(d_out, d_cnt)[1].cpu()
 
+    h_out2 = torch.zeros_like(h_out).pin_memory()
+    h_cnt2 = torch.zeros_like(h_cnt).pin_memory()
+
+    def submit(slot):
+        lib.check(L.dd3d_submit_host(handle, slot, C.c_void_p(h_batch.data_ptr()), dtype_code, C.c_void_p(h_K.data_ptr()),
+                                     C.c_void_p(h_sizes.data_ptr()), C.c_void_p((h_out2 if slot else h_out).data_ptr()),
+                                     C.c_void_p((h_cnt2 if slot else h_cnt).data_ptr()), sp), handle)
+
+    def run_host_pipelined(n):
+        """n end-to-end steps through dd3d_submit_host / dd3d_wait_host: every step copies its batch H2D and its
+        detections D2H; the H2D of step k+1 (copy stream) overlaps the kernels of step k."""
+        submit(0)
+        for k in range(n):
+            if k + 1 < n:
+                submit((k + 1) & 1)
+            lib.check(L.dd3d_wait_host(handle, k & 1), handle)
+            if world > 1:  # whole-batch eval: gather every rank's detections
+                d_out.copy_(h_out2 if k & 1 else h_out, non_blocking=True)
+                d_cnt.copy_(h_cnt2 if k & 1 else h_cnt, non_blocking=True)
+                all_gather_detections(d_out, d_cnt)[1].cpu()
+
+    def timed_pipelined():
+        run_host_pipelined(args.warmup)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_host_pipelined(args.steps)
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
     def timed(fn, sampler=None):
         for _ in range(args.warmup):
             fn()
@@ -323,6 +361,9 @@ def main():
 
     ms_dev, clocks = timed(step_device, ClockSampler(local_rank))
     ms_host, _ = timed(step_host)
+    ms_host_serial = ms_host
+    if not nusc and not raw_mode:  # double-buffered host path (H2D of the next step overlaps this step's kernels)
+        ms_host = min(ms_host, timed_pipelined())
     assert model.overflow_flags() == 0, "detection buffers overflowed"
     assert not nusc or int(d_flags.item()) == 0, "sample aggregation overflowed"
     n_det = int(h_cnt.sum())
@@ -371,6 +412,10 @@ def main():
         },
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_host / args.steps,
+                "path": "dd3d_submit_host / dd3d_wait_host (double-buffered: H2D of step k+1 overlaps the kernels of step "
+                        "k; every step still copies its inputs H2D and its detections D2H inside the timed region)"
+                        if ms_host < ms_host_serial else "dd3d_forward_host (serial H2D -> kernels -> D2H)",
+                "serial_ms_per_step": ms_host_serial / args.steps,
                 "h2d_bytes_per_step": int(h_batch.numel() * h_batch.element_size() + h_K.numel() * 4 + h_sizes.numel() * 4),
                 "d2h_bytes_per_step": int(h_out.numel() * 4 + h_cnt.numel() * 4 + (h_glob.numel() * 4 if nusc else 0))},
         "gpu_launches": (model.launches_per_forward() + (2 if nusc else 0)) * args.steps,

@@ -132,6 +132,19 @@ int dd3d_forward_raw(dd3d_handle h, const uint8_t* d_raw, int raw_h, int raw_w, 
     });
 }
 
+int dd3d_submit_host(dd3d_handle h, int slot, const void* h_images, int img_dtype, const float* h_intrinsics,
+                     const int32_t* h_sizes, dd3d_det* h_out, int32_t* h_counts, dd3d_stream stream) {
+    if (!h_images || !h_intrinsics || !h_sizes || !h_out || !h_counts) return DD3D_ERR_INVALID;
+    return guarded(h, [&](Engine& e) {
+        e.submit_host(slot, h_images, img_dtype, h_intrinsics, h_sizes, reinterpret_cast<Det*>(h_out), h_counts,
+                      static_cast<cudaStream_t>(stream));
+    });
+}
+
+int dd3d_wait_host(dd3d_handle h, int slot) {
+    return guarded(h, [&](Engine& e) { e.wait_host(slot); });
+}
+
 int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags) {
     return guarded(h, [&](Engine& e) {
         if (!e.plan.valid) throw EngineError(DD3D_ERR_STATE, "no plan");

@@ -58,7 +58,12 @@ Engine::Engine(const dd3d_model_desc& d) : desc(d) {
 
 Engine::~Engine() {
     release_plan();
-    for (auto& kv : plan_cache) cudaFree(kv.second.owned_workspace);
+    for (auto& kv : plan_cache) free_plan(&kv.second);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (h2d_done[i]) cudaEventDestroy(h2d_done[i]);
+        if (all_done[i]) cudaEventDestroy(all_done[i]);
+    }
     for (void* p : device_allocs) cudaFree(p);
 }
 
@@ -803,20 +808,24 @@ size_t Engine::workspace_bytes(int B, int Hs, int Ws) {
     return build(&tmp, B, Hs, Ws, nullptr, true);
 }
 
-void Engine::release_plan() {
-    if (plan.owned_workspace) cudaFree(plan.owned_workspace);
-    plan = Plan();
+void Engine::free_plan(Plan* P) {
+    if (P->owned_workspace) cudaFree(P->owned_workspace);
+    if (P->slot1) cudaFree(P->slot1);
+    *P = Plan();
 }
+
+void Engine::release_plan() { free_plan(&plan); }
 
 void Engine::make_plan(int B, int Hs, int Ws, void* workspace, size_t bytes) {
     if (!finalized) fail(DD3D_ERR_STATE, "plan before finalize");
     if (B < 1 || Hs < 1 || Ws < 1) fail(DD3D_ERR_INVALID, "bad plan shape");
+    if (slot_busy[0] || slot_busy[1]) fail(DD3D_ERR_STATE, "plan change with a pending dd3d_submit_host");
     cuda_check(cudaSetDevice(device), "cudaSetDevice");
     if (workspace == nullptr && plan.valid && plan.owned_workspace && plan.B == B && plan.Hs == Hs && plan.Ws == Ws) return;
     // park the active plan if it is engine-owned and small, else free it
     if (plan.valid && plan.owned_workspace && plan.owned_bytes <= kPlanCacheBytes) {
         if (plan_cache.size() >= kPlanCacheMax) {
-            cudaFree(plan_cache.begin()->second.owned_workspace);
+            free_plan(&plan_cache.begin()->second);
             plan_cache.erase(plan_cache.begin());
         }
         plan_cache[{plan.B, plan.Hs, plan.Ws}] = std::move(plan);
@@ -1104,6 +1113,61 @@ void Engine::forward_host(const void* h_images, int img_dtype, const float* h_K,
     cuda_check(cudaMemcpyAsync(h_counts, P.d_counts, static_cast<size_t>(P.B) * 4, cudaMemcpyDeviceToHost, stream),
                "D2H counts");
     cuda_check(cudaStreamSynchronize(stream), "sync");
+}
+
+// Double-buffered host path.  Slot s owns one set of device staging buffers; its inputs travel on a private copy stream,
+// so the H2D of the next batch overlaps the kernels of the current one (the copy engines and the SMs are independent),
+// while kernels and the (small) D2H stay ordered on the caller's stream.
+void Engine::submit_host(int slot, const void* h_images, int img_dtype, const float* h_K, const int32_t* h_sizes, Det* h_out,
+                         int32_t* h_counts, cudaStream_t stream) {
+    if (!plan.valid) fail(DD3D_ERR_STATE, "submit before plan");
+    if (slot < 0 || slot > 1) fail(DD3D_ERR_INVALID, "slot must be 0 or 1");
+    if (slot_busy[slot]) fail(DD3D_ERR_STATE, "slot resubmitted before dd3d_wait_host");
+    Plan& P = plan;
+    const size_t img_cap = static_cast<size_t>(P.B) * 3 * P.Hs * P.Ws * 4;
+    const size_t out_bytes = static_cast<size_t>(P.B) * desc.out_cap * sizeof(Det);
+    if (copy_stream == nullptr) {
+        cuda_check(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int i = 0; i < 2; ++i) {
+            cuda_check(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming), "cudaEventCreate");
+            cuda_check(cudaEventCreateWithFlags(&all_done[i], cudaEventDisableTiming), "cudaEventCreate");
+        }
+    }
+    if (slot == 1 && P.slot1 == nullptr) {
+        const size_t a = 1024;
+        auto up = [&](size_t n) { return (n + a - 1) / a * a; };
+        const size_t total = up(img_cap) + up(P.B * 36) + up(P.B * 16) + up(out_bytes) + up(P.B * 4);
+        cuda_check(cudaMalloc(&P.slot1, total), "cudaMalloc(slot 1 staging)");
+        uint8_t* q = static_cast<uint8_t*>(P.slot1);
+        P.s1_images = q; q += up(img_cap);
+        P.s1_K = reinterpret_cast<float*>(q); q += up(P.B * 36);
+        P.s1_sizes = reinterpret_cast<int32_t*>(q); q += up(P.B * 16);
+        P.s1_out = reinterpret_cast<Det*>(q); q += up(out_bytes);
+        P.s1_counts = reinterpret_cast<int32_t*>(q);
+    }
+    void* d_img = slot ? P.s1_images : P.d_images;
+    float* d_K = slot ? P.s1_K : P.d_K;
+    int32_t* d_sz = slot ? P.s1_sizes : P.d_sizes;
+    Det* d_out = slot ? P.s1_out : P.d_out;
+    int32_t* d_cnt = slot ? P.s1_counts : P.d_counts;
+    const size_t img_bytes = static_cast<size_t>(P.B) * 3 * P.Hs * P.Ws * (img_dtype == DD3D_IMG_U8 ? 1 : 4);
+    cuda_check(cudaMemcpyAsync(d_img, h_images, img_bytes, cudaMemcpyHostToDevice, copy_stream), "H2D images");
+    cuda_check(cudaMemcpyAsync(d_K, h_K, static_cast<size_t>(P.B) * 36, cudaMemcpyHostToDevice, copy_stream), "H2D K");
+    cuda_check(cudaMemcpyAsync(d_sz, h_sizes, static_cast<size_t>(P.B) * 16, cudaMemcpyHostToDevice, copy_stream), "H2D sizes");
+    cuda_check(cudaEventRecord(h2d_done[slot], copy_stream), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(stream, h2d_done[slot], 0), "cudaStreamWaitEvent");
+    forward(d_img, img_dtype, d_K, d_sz, d_out, d_cnt, stream);
+    cuda_check(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, stream), "D2H dets");
+    cuda_check(cudaMemcpyAsync(h_counts, d_cnt, static_cast<size_t>(P.B) * 4, cudaMemcpyDeviceToHost, stream), "D2H counts");
+    cuda_check(cudaEventRecord(all_done[slot], stream), "cudaEventRecord");
+    slot_busy[slot] = true;
+}
+
+void Engine::wait_host(int slot) {
+    if (slot < 0 || slot > 1) fail(DD3D_ERR_INVALID, "slot must be 0 or 1");
+    if (!slot_busy[slot]) fail(DD3D_ERR_STATE, "dd3d_wait_host without dd3d_submit_host");
+    cuda_check(cudaEventSynchronize(all_done[slot]), "cudaEventSynchronize");
+    slot_busy[slot] = false;
 }
 
 }  // namespace dd3d

@@ -74,6 +74,12 @@ struct Plan {
     int B = 0, Hs = 0, Ws = 0, Hp = 0, Wp = 0;
     void* owned_workspace = nullptr;
     size_t owned_bytes = 0;
+    void* slot1 = nullptr;  // second set of host-path staging buffers (dd3d_submit_host slot 1), allocated on first use
+    void* s1_images = nullptr;
+    float* s1_K = nullptr;
+    int32_t* s1_sizes = nullptr;
+    Det* s1_out = nullptr;
+    int32_t* s1_counts = nullptr;
     View input;
     View fpn[kLevels];
     float* cls_map[kLevels] = {};
@@ -110,6 +116,10 @@ class Engine {
                  int32_t* d_counts, cudaStream_t stream);
     void forward_host(const void* h_images, int img_dtype, const float* h_K, const int32_t* h_sizes, Det* h_out,
                       int32_t* h_counts, cudaStream_t stream);
+    // double-buffered host path: H2D of one slot on a private copy stream while the other slot computes
+    void submit_host(int slot, const void* h_images, int img_dtype, const float* h_K, const int32_t* h_sizes, Det* h_out,
+                     int32_t* h_counts, cudaStream_t stream);
+    void wait_host(int slot);
     // raw dataset images: ResizeShortestEdge + intrinsics rescale (dataset_mapper.py:100-153) fused with the preprocess
     void forward_raw(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes, const float* h_K,
                      int min_size, int max_size, Det* d_out, int32_t* d_counts, float* h_K_out, int32_t* h_new_sizes,
@@ -160,6 +170,9 @@ class Engine {
     static constexpr size_t kPlanCacheBytes = size_t(4) << 30;
     static constexpr size_t kPlanCacheMax = 12;
     ResizeTables resize_tables;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, all_done[2] = {nullptr, nullptr};
+    bool slot_busy[2] = {false, false};
     struct RawArgs {
         const uint8_t* d_raw;
         int raw_h, raw_w;
@@ -174,6 +187,7 @@ class Engine {
     float* upload_f32(const std::vector<float>& v);
     size_t build(Plan* P, int B, int Hs, int Ws, void* workspace, bool dry);
     void release_plan();
+    static void free_plan(Plan* P);
 };
 
 }  // namespace dd3d

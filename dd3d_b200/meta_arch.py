@@ -340,6 +340,44 @@ class DD3DB200(nn.Module):
                                     C.c_void_p(hb["counts"].data_ptr()), C.c_void_p(stream)), self._handle)
         return self._wrap(hb["out"], hb["counts"], K, sizes, torch.device("cpu"))
 
+    @torch.no_grad()
+    def submit_host(self, batched_inputs, slot=0):
+        """Double-buffered host path (dd3d_submit_host): enqueues H2D -> kernels -> D2H for `slot` (0 / 1) and returns;
+        ``wait_host(slot)`` returns the results.  Submitting the next batch to the other slot before waiting overlaps
+        its H2D with the current batch's kernels.  All batches of a pipeline must share one plan shape."""
+        batch, K, sizes, shape, is_u8 = self._gather_inputs(batched_inputs, self._device)
+        self._plan(*shape)
+        L = _lib.load()
+        B, cap = shape[0], self._desc.out_cap
+        if not hasattr(self, "_slots"):
+            self._slots = {}
+        hb = self._slots.get(slot)
+        if hb is None or hb["img"].shape != batch.shape or hb["img"].dtype != batch.dtype:
+            hb = dict(img=torch.empty_like(batch).pin_memory(), K=torch.empty_like(K).pin_memory(),
+                      sizes=torch.empty_like(sizes).pin_memory(),
+                      out=torch.empty((B, cap, _lib.DET_WORDS), dtype=torch.float32).pin_memory(),
+                      counts=torch.empty((B, ), dtype=torch.int32).pin_memory())
+            self._slots[slot] = hb
+        hb["img"].copy_(batch)
+        hb["K"].copy_(K)
+        hb["sizes"].copy_(sizes)
+        hb["ctx"] = (K, sizes)
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            _lib.check(L.dd3d_set_option(self._handle, b"do_postprocess", int(self.postprocess_in_inference)),
+                       self._handle)
+            _lib.check(
+                L.dd3d_submit_host(self._handle, int(slot), C.c_void_p(hb["img"].data_ptr()),
+                                   _lib.IMG_U8 if is_u8 else _lib.IMG_F32, C.c_void_p(hb["K"].data_ptr()),
+                                   C.c_void_p(hb["sizes"].data_ptr()), C.c_void_p(hb["out"].data_ptr()),
+                                   C.c_void_p(hb["counts"].data_ptr()), C.c_void_p(stream)), self._handle)
+
+    def wait_host(self, slot=0):
+        hb = self._slots[slot]
+        _lib.check(_lib.load().dd3d_wait_host(self._handle, int(slot)), self._handle)
+        K, sizes = hb["ctx"]
+        return self._wrap(hb["out"].clone(), hb["counts"].clone(), K, sizes, torch.device("cpu"))
+
     # ------------------------------------------------------------------ introspection (stage-level parity tests)
     def get_tensor(self, name):
         """Device tensor of an engine-internal map after a forward: 'p0'..'p4', 'cls0'.., 'box0'.., 'b3d0'.., 'input'."""

@@ -127,6 +127,14 @@ int dd3d_forward(dd3d_handle h, const void* d_images, int img_dtype, const float
  * then synchronises `stream`. */
 int dd3d_forward_host(dd3d_handle h, const void* h_images, int img_dtype, const float* h_intrinsics,
                       const int32_t* h_sizes, dd3d_det* h_out, int32_t* h_counts, dd3d_stream stream);
+/* Double-buffered host path for a serving / evaluation loop (the role of the reference dataloader's prefetch +
+ * x["image"].to(device), core.py:65): dd3d_submit_host enqueues H2D (on an engine-owned copy stream) -> kernels -> D2H (on
+ * `stream`) for slot 0 or 1 and returns at once; dd3d_wait_host blocks until that slot's detections are in h_out /
+ * h_counts.  Submitting batch i+1 to the other slot before waiting for batch i overlaps its H2D with batch i's kernels.
+ * Host buffers must be pinned and stay valid until the wait; a slot must be waited before it is submitted again. */
+int dd3d_submit_host(dd3d_handle h, int slot, const void* h_images, int img_dtype, const float* h_intrinsics,
+                     const int32_t* h_sizes, dd3d_det* h_out, int32_t* h_counts, dd3d_stream stream);
+int dd3d_wait_host(dd3d_handle h, int slot);
 /* bit 0: more candidates tied at the k-th pre-NMS score than the boundary buffer holds; bit 1: more than
  * out_cap detections survived.  Reads a device word (synchronises `stream`). */
 int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags);

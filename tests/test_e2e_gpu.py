@@ -165,3 +165,35 @@ def test_full_size_properties_v2_99():
         assert (q.norm(dim=1) - 1).abs().max() < 1e-3
         d = inst.pred_boxes3d.depth
         assert (d >= 0.1).all() and (d <= 80.0).all()
+
+
+@pytest.mark.gpu
+def test_submit_wait_host_matches_forward_host():
+    """Double-buffered host path: two different batches in flight on slots 0 / 1 give exactly the results of the serial
+    dd3d_forward_host calls (same kernels, same stream order)."""
+    from dd3d_b200.config import get_cfg
+    from dd3d_b200.meta_arch import DD3DB200
+    from dd3d_b200.synthetic import make_inputs, make_state_dict
+    cfg = get_cfg("dla34", "kitti_3d")
+    model = DD3DB200(cfg).to("cuda")
+    model.load_state_dict(make_state_dict(cfg))
+    batches = [make_inputs(2, 192, 320, 721.5, seed_base=1 + 7 * i) for i in range(3)]
+    ref = [model.forward_host(b) for b in batches]
+    got = []
+    model.submit_host(batches[0], 0)
+    for k in range(3):
+        if k + 1 < 3:
+            model.submit_host(batches[k + 1], (k + 1) & 1)
+        got.append(model.wait_host(k & 1))
+    with pytest.raises(RuntimeError):
+        model.wait_host(0)  # nothing pending on the slot
+    total = 0
+    for r, g in zip(ref, got):
+        for a, b in zip(r, g):
+            ia, ib = a["instances"], b["instances"]
+            assert len(ia) == len(ib)
+            total += len(ia)
+            assert torch.equal(ia.pred_boxes.tensor, ib.pred_boxes.tensor)
+            assert torch.equal(ia.scores_3d, ib.scores_3d)
+            assert torch.equal(ia.pred_boxes3d.vectorize(), ib.pred_boxes3d.vectorize())
+    assert total > 10
