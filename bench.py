@@ -202,6 +202,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = get_cfg(arch, ds, meta_arch="NuscenesDD3D" if nusc else "DD3D")
