@@ -113,6 +113,15 @@ int dd3d_forward_host(dd3d_handle h, const void* h_images, int img_dtype, const 
     });
 }
 
+int dd3d_set_conv_policy(const char* name, int value) {
+    if (!name) return DD3D_ERR_INVALID;
+    if (!strcmp(name, "cta2")) {
+        conv_set_cta2(value);
+        return DD3D_OK;
+    }
+    return DD3D_ERR_INVALID;
+}
+
 int dd3d_resize_shape(int h, int w, int min_size, int max_size, int32_t* new_h, int32_t* new_w) {
     if (h < 1 || w < 1 || !new_h || !new_w) return DD3D_ERR_INVALID;
     int nh, nw;

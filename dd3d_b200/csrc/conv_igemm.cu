@@ -823,14 +823,17 @@ void conv_finalize_params(ConvParams* p) {
     p->tmem_cols = cols;
 }
 
+static int g_cta2_mode = -1;
+
 int conv_use_cta2() {  // 0 never, 1 always (where legal), 2 auto (per-layer rule in conv_finalize_params)
-    static int mode = -1;
-    if (mode < 0) {
+    if (g_cta2_mode < 0) {
         const char* e = getenv("DD3D_CONV_CTA2");
-        mode = e ? (!strcmp(e, "auto") ? 2 : (atoi(e) != 0)) : kConvCta2Default;
+        g_cta2_mode = e ? (!strcmp(e, "auto") ? 2 : (atoi(e) != 0)) : kConvCta2Default;
     }
-    return mode;
+    return g_cta2_mode;
 }
+
+void conv_set_cta2(int mode) { g_cta2_mode = (mode >= 0 && mode <= 2) ? mode : -1; }
 
 cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
     const int stage_bytes = (p.halo ? 0 : kABytes) + (p.cta2 ? p.block_n / 2 : p.block_n) * 128;

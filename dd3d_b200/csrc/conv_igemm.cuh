@@ -73,6 +73,7 @@ bool make_weight_map(CUtensorMap* map, const void* base, int ktot, int cout_pad,
 // CTA-pair policy for ConvParams::cta2 before conv_finalize_params: 0 never, 1 always, 2 auto (finalize decides; the
 // w_map box must then be block_n / 2 rows iff the finalized cta2 is 1)
 int conv_use_cta2();
+void conv_set_cta2(int mode);  // process-wide override (plans built afterwards); -1: back to the environment / default
 void choose_tile(int H, int W, int* th, int* tw);
 int conv_tiles_per_image(int H, int W);  // M-tiles per image of the generic tiling
 // Halo variant (3x3, stride 1): non-swizzled [8-channel group][18x10 pixels][8 ch] patch loads.

@@ -59,6 +59,7 @@ SIGNATURES = {
     "dd3d_plan": (_I, [_P, _I, _I, _I, _P, _I64]),
     "dd3d_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
     "dd3d_forward_host": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
+    "dd3d_set_conv_policy": (_I, [C.c_char_p, _I]),
     "dd3d_submit_host": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P]),
     "dd3d_wait_host": (_I, [_P, _I]),
     "dd3d_overflow_flags": (_I, [_P, _P, C.POINTER(C.c_int32)]),

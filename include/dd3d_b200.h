@@ -142,6 +142,10 @@ int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags);
  * scripts/train.py:206-209, test_time_augmentation.py:107), "do_nms" (core.py:134), and "profile" (see
  * dd3d_get_profile). */
 int dd3d_set_option(dd3d_handle h, const char* name, int value);
+/* Process-wide kernel-selection policy for plans / operator calls made afterwards (tests, A/B measurements):
+ * "cta2" = 0 single-CTA conv kernel everywhere, 1 CTA pairs (tcgen05.mma.cta_group::2) wherever legal, 2 auto (default:
+ * pairs for block_n >= 160 and >= 296 tiles), -1 back to the DD3D_CONV_CTA2 environment setting. */
+int dd3d_set_conv_policy(const char* name, int value);
 /* Number of kernel launches one dd3d_forward enqueues (for the bench's gpu_launches claim). */
 int dd3d_launches_per_forward(dd3d_handle h);
 

@@ -313,3 +313,36 @@ def test_decode_and_nms_vs_oracle(arch, rate, seed):
             assert np.array_equal(gi[:, 20].numpy(), (ref["pixel"] * Cn + ref["cls"]).numpy())  # same order
             np.testing.assert_allclose(got[:, 0:4], ref["box2d"], rtol=1e-5, atol=1e-3)
             np.testing.assert_allclose(got[:, 5], ref["score3d"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,H,W,B,relu,res", CONV_CASES)
+def test_conv_cta_pair_bitwise_equals_single_cta(cin, cout, k, stride, H, W, B, relu, res):
+    """The CTA-pair kernel (tcgen05.mma.cta_group::2, M = 256, half weight tile per CTA) accumulates every output in the
+    same K order as the single-CTA kernel: outputs must be bit-identical, including odd tile counts (padding tile),
+    ragged maps, channel tails, stride 2 and residuals."""
+    from dd3d_b200 import lib
+    L = lib.load()
+    g = torch.Generator().manual_seed(cin * 131 + cout + k + H)
+    x = _rand_act(B, H, W, cin, seed=cin + H)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k)**0.5
+    scale = 0.5 + torch.rand(cout, generator=g)
+    bias = torch.randn(cout, generator=g) * 0.5
+    Ho, Wo = H // stride, W // stride
+    residual = None
+    if res == 1:
+        residual = _rand_act(B, Ho, Wo, cout, seed=5)
+    elif res == 2:
+        residual = _rand_act(B, Ho // 2, Wo // 2, cout, seed=6)
+    outs = []
+    try:
+        for mode in (0, 1):
+            assert L.dd3d_set_conv_policy(b"cta2", mode) == 0
+            outs.append(gpu_ops.conv2d(x, w, scale, bias, stride, relu, residual, res == 2))
+            if cout <= 112:  # fp32 predictor path as well
+                outs.append(gpu_ops.conv2d(x, w, scale, bias, stride, False, None, False, out_f32=True))
+    finally:
+        L.dd3d_set_conv_policy(b"cta2", -1)
+    n = len(outs) // 2
+    for a, b in zip(outs[:n], outs[n:]):
+        assert torch.equal(a.view(torch.int16) if a.dtype == torch.bfloat16 else a.view(torch.int32),
+                           b.view(torch.int16) if b.dtype == torch.bfloat16 else b.view(torch.int32))
