@@ -43,12 +43,10 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kStagingBytes = kBlockM * 128;    // one 64-channel bf16 output chunk
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
-// halo variant: per 64-channel block the A operand is ONE (16+2)x(8+2)-pixel patch stored as 8 planes
-// [8-channel group][180 pixels][8 ch = 16 B]; plane stride padded to a multiple of 128 B (TMA destination alignment)
+// halo variant: per 64-channel block the A operand is ONE (16+2)x(8+2)-pixel patch = 180 rows of 128 B (64 channels),
+// 128B-swizzled by TMA; the slot is rounded up to a multiple of 1024 B so every patch keeps the swizzle-atom alignment
 constexpr int kHaloPW = kHaloTw + 2, kHaloPH = kHaloTh + 2;
-constexpr int kHaloPlaneTx = kHaloPW * kHaloPH * 16;          // 2880 bytes delivered per TMA box
-constexpr int kHaloPlane = (kHaloPlaneTx + 127) / 128 * 128;  // 2944
-constexpr int kHaloABytes = 8 * kHaloPlane;                    // 23552 = 23 KiB (keeps 1024-byte alignment)
+constexpr int kHaloABytes = (kHaloPW * kHaloPH * 128 + 1023) / 1024 * 1024;  // 23552
 constexpr int kHaloAStages = 3;
 constexpr int kBarBytes = 512;
 
@@ -466,6 +464,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.chains * p.block_n;
 
+            // residual (BasicBlock identity / FPN top-down map): fetched ONE 32-column step ahead, so the L2 / DRAM latency
+            // of this thread's row is paid once per tile instead of once per step (the FPN laterals were bound by it)
+            uint4 rpre[4];
+            auto load_res = [&](int col) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    rpre[i] = (col + 8 * i < p.block_n) ? __ldg(reinterpret_cast<const uint4*>(res_ptr + col + 8 * i))
+                                                        : make_uint4(0u, 0u, 0u, 0u);
+                }
+            };
+            if (res_ptr != nullptr) load_res(0);
+
             for (int c0 = 0; c0 < p.block_n; c0 += 64) {
                 const int chunk_cols = min(64, p.block_n - c0);
                 uint8_t* stag = staging + sbuf * kStagingBytes;
@@ -520,8 +530,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) {
                             if (i < cols) {
-                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_ptr + c0 + h + i));
-                                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rpre[i >> 3]);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const float2 f = __bfloat1622float2(rb[j]);
@@ -530,6 +539,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                                 }
                             }
                         }
+                        if (c0 + h + 32 < p.block_n) load_res(c0 + h + 32);  // next step's columns, consumed next iteration
                     }
                     if (p.relu) {
 #pragma unroll

@@ -76,11 +76,11 @@ int conv_use_cta2();
 void conv_set_cta2(int mode);  // process-wide override (plans built afterwards); -1: back to the environment / default
 void choose_tile(int H, int W, int* th, int* tw);
 int conv_tiles_per_image(int H, int W);  // M-tiles per image of the generic tiling
-// Halo variant (3x3, stride 1): non-swizzled [8-channel group][18x10 pixels][8 ch] patch loads.
+// Halo variant (3x3, stride 1): one 128B-swizzled [18][10][64 ch] patch per 64-channel block serves all nine taps.
 constexpr int kHaloTh = 16, kHaloTw = 8;
 int conv_halo_mode();
 bool make_act_map_halo(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch);
-// Policy: use the halo variant when its fixed 16x8 tiling costs at most ~15 % more tiles than the best generic
+// Policy: use the halo variant when its fixed 16x8 tiling costs at most 10 % more tiles than the best generic
 // tiling over all segments (env DD3D_CONV_MODE=generic|halo overrides, for tests).
 bool conv_prefer_halo(int taps, int stride, int block_n, int nseg, const int* Hs, const int* Ws);
 // Fills num_stages / tmem_cols / total_work / tile bookkeeping from the already-set fields.

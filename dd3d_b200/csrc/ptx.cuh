@@ -212,30 +212,6 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
     return d;
 }
-// Same layout, but the 8-row groups are `sbo` bytes apart and the start address may sit at any 128-byte row of the
-// 1024-byte swizzle pattern; `base_offset` = (start >> 7) & 7 tells the hardware where in the pattern row 0 is.
-__device__ __forceinline__ uint64_t make_sw128_desc_ex(uint32_t smem_addr, uint32_t sbo, uint32_t base_offset) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-    d |= static_cast<uint64_t>(1) << 16;
-    d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(base_offset & 7) << 49;
-    d |= static_cast<uint64_t>(2) << 61;
-    return d;
-}
-// K-major, NON-swizzled ("interleaved") operand: core matrix = 8 rows x 16 B stored contiguously (rows 16 B apart);
-// `lbo` = byte distance between the two 16-byte K-chunks of one MMA (K=16 bf16), `sbo` = byte distance between
-// consecutive 8-row groups.  Only 16-byte alignment is required, so the start address can be shifted by whole
-// pixels -- this is what lets one halo patch serve all nine taps of a 3x3 conv.
-__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-    d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
-    d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
-    d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell); layout type 0 = SWIZZLE_NONE
-    return d;
-}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
 __host__ __device__ inline uint32_t make_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
