@@ -3,7 +3,7 @@
 The names/shapes follow what ``DD3D(cfg).state_dict()`` yields in the reference
 (tridet/modeling/dd3d/core.py:19-55; DLA-34 tridet/modeling/feature_extractor/dla.py:250-361; V2-99-eSE
 tridet/modeling/feature_extractor/vovnet.py:79-87,276-336; FPN + top blocks dla.py:537-561, vovnet.py:411-454;
-heads fcos2d.py:55-108, fcos3d.py:81-139).  tests/test_oracle_vs_reference.py checks this inventory against the
+heads fcos2d.py:55-108, fcos3d.py:81-139).  tests/test_cpu_oracle.py::test_inventory_and_oracle_vs_live_reference checks this inventory against the
 reference's own state_dict when /root/reference is present.
 """
 from collections import OrderedDict
