@@ -190,6 +190,22 @@ def test_cabi_library_exports_every_declared_symbol():
         assert hasattr(L, name)
     import ctypes
     assert ctypes.sizeof(lib.ModelDesc) == 4 * (2 + 3 + 3 + 1 + 1 + 3 + 1 + 2 + 1 + 1 + 1 + 1 + 48 + 1 + 1)
+    assert ctypes.sizeof(lib.TtaView) == 4 * (1 + 1 + 2 + 2 + 9 + 9)  # dd3d_tta_view
+    assert lib.DET_WORDS * 4 == 96  # dd3d_det
+
+
+def test_tile_decode_fast_division():
+    """conv_igemm.cu fast_div (fp32 reciprocal estimate + one correction) restated in numpy: exact for every tile index
+    the kernel can see (x < 2^24, launch_conv refuses more) and every divisor a plan can produce."""
+    import numpy as np
+    rs = np.random.RandomState(0)
+    for d in [1, 2, 3, 7, 50, 57, 200, 750, 2850, 11400, 19999] + [int(v) for v in rs.randint(1, 20000, size=40)]:
+        inv = np.float32(1.0) / np.float32(d)
+        x = np.concatenate([rs.randint(0, 1 << 24, size=50000), [0, d - 1, d, 2 * d - 1, (1 << 24) - 1]]).astype(np.int64)
+        q = np.trunc(x.astype(np.float32) * inv).astype(np.int64)
+        r = x - q * d
+        q = q + (r >= d) - (r < 0)
+        assert np.array_equal(q, x // d), d
 
 
 def test_cabi_fails_loudly_without_gpu():
