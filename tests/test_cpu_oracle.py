@@ -128,6 +128,49 @@ def test_inventory_and_oracle_vs_live_reference(arch, have_reference):
         assert (ref.pred_boxes3d.tvec - out["tvec"]).abs().max() < 1e-3
 
 
+FLAG_CASES = [
+    dict(FEATURE_LOCATIONS_OFFSET="half"),
+    dict(PREDICT_DISTANCE=True),
+    dict(PREDICT_ALLOCENTRIC_ROT=False),
+    dict(SCALE_DEPTH_BY_FOCAL_LENGTHS=False),
+    dict(FEATURE_LOCATIONS_OFFSET="half", PREDICT_DISTANCE=True, PREDICT_ALLOCENTRIC_ROT=False),
+]
+
+
+def apply_flags(cfg, flags):
+    for k, v in flags.items():
+        if k == "FEATURE_LOCATIONS_OFFSET":
+            cfg.DD3D.FEATURE_LOCATIONS_OFFSET = v
+        else:
+            cfg.DD3D.FCOS3D[k] = v
+    return cfg
+
+
+@pytest.mark.parametrize("flags", FLAG_CASES, ids=lambda f: "+".join(f))
+def test_oracle_decode_flags_vs_live_reference(flags, have_reference):
+    """The non-default decode switches the reference reads (core.py:38, fcos3d.py:36-47,306-312): feature-location offset
+    "half", PREDICT_DISTANCE, egocentric quaternions, no focal-length depth scaling -- oracle == the reference's forward."""
+    if not have_reference:
+        pytest.skip("/root/reference not present (GPU box)")
+    from oracle import ref_standin
+    cfg = apply_flags(get_cfg("dla34", "kitti_3d"), flags)
+    cfg.DD3D.FCOS2D.INFERENCE.PRE_NMS_THRESH = 0.03
+    model = ref_standin.build_reference_model(cfg).eval()
+    sd = make_state_dict(cfg)
+    model.load_state_dict(sd)
+    inputs = make_inputs(1, 128, 256, 721.5, seed_base=7)
+    with torch.no_grad():
+        ref = model(inputs)[0]["instances"]
+    out = DD3DOracle(cfg, sd).forward(inputs)[0]
+    assert len(ref) == out["box2d"].shape[0] > 5
+    assert (ref.pred_boxes.tensor - out["box2d"]).abs().max() < 1e-3
+    assert (ref.locations - out["loc"]).abs().max() == 0
+    assert (ref.scores_3d - out["score3d"]).abs().max() < 1e-5
+    assert quat_dist(ref.pred_boxes3d.quat, out["quat"]).max() < 1e-4
+    assert (ref.pred_boxes3d.depth.reshape(-1) - out["depth"]).abs().max() < 1e-3
+    assert (ref.pred_boxes3d.tvec - out["tvec"]).abs().max() < 1e-3
+
+
 # ------------------------------------------------------------------------------------------------ host logic / ABI
 def test_identity_intrinsics_raises():
     cfg = get_cfg("dla34", "kitti_3d")

@@ -246,8 +246,28 @@ def _oracle_maps(maps, Cn, level_hw, B):
 def test_decode_and_nms_vs_oracle(arch, rate, seed):
     """Random head maps; `rate` = logit bias: -0.5 floods the levels far beyond PRE_NMS_TOPK (exact top-k path),
     -9 yields no candidate at all (empty path)."""
+    _decode_case(arch, rate, seed, {})
+
+
+@pytest.mark.parametrize("flags", [
+    dict(FEATURE_LOCATIONS_OFFSET="half"), dict(PREDICT_DISTANCE=True), dict(PREDICT_ALLOCENTRIC_ROT=False),
+    dict(SCALE_DEPTH_BY_FOCAL_LENGTHS=False),
+    dict(FEATURE_LOCATIONS_OFFSET="half", PREDICT_DISTANCE=True, PREDICT_ALLOCENTRIC_ROT=False)], ids=lambda f: "+".join(f))
+def test_decode_flags_vs_oracle(flags):
+    """The decode switches of dd3d_model_desc (feature-location offset, PREDICT_DISTANCE, egocentric quaternions, no
+    focal-length depth scaling; fcos3d.py:36-47, core.py:38) against the oracle, which test_cpu_oracle pins against the
+    reference for the same switches."""
+    _decode_case("dla34", -2.0, 11, flags)
+
+
+def _decode_case(arch, rate, seed, flags):
     ds = "nuscenes" if arch == "v2_99" else "kitti_3d"
     cfg = get_cfg(arch, ds)
+    for k, v in flags.items():
+        if k == "FEATURE_LOCATIONS_OFFSET":
+            cfg.DD3D.FEATURE_LOCATIONS_OFFSET = v
+        else:
+            cfg.DD3D.FCOS3D[k] = v
     desc = lib.desc_from_cfg(cfg)
     Cn = cfg.DD3D.NUM_CLASSES
     B = 2
