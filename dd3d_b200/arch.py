@@ -144,7 +144,12 @@ MAX_NUM_ATTRIBUTES = 3  # tridet/data/datasets/nuscenes/build.py:77
 
 
 def is_nuscenes_arch(cfg):
-    return cfg.MODEL.META_ARCHITECTURE == "NuscenesDD3D"
+    """MODEL.META_ARCHITECTURE names the reference class ("DD3D" / "NuscenesDD3D", configs/meta_arch/dd3d.yaml:12,
+    configs/experiments/dd3d_nusc_*.yaml:9) or its registered B200 mirror ("DD3DB200" / "NuscenesDD3DB200")."""
+    name = cfg.MODEL.META_ARCHITECTURE
+    if name not in ("DD3D", "NuscenesDD3D", "DD3DB200", "NuscenesDD3DB200"):
+        raise KeyError("No object named '{}' found in 'META_ARCH' registry!".format(name))
+    return name.startswith("NuscenesDD3D")
 
 
 def arch_of(cfg):

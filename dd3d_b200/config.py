@@ -83,7 +83,7 @@ _FEATURE_EXTRACTORS = {
 }
 
 
-def get_cfg(backbone="dla34", dataset="kitti_3d", nms_thresh=0.75, meta_arch="DD3D"):
+def get_cfg(backbone="dla34", dataset="kitti_3d", nms_thresh=0.75, meta_arch="DD3D", act_dtype="bf16"):
     """backbone in {"dla34", "v2_99"}; dataset in {"kitti_3d", "nuscenes"} (head constants only); meta_arch in
     {"DD3D", "NuscenesDD3D"} (configs/experiments/dd3d_nusc_{dla34,v99}.yaml:9,30-36)."""
     ds = _DATASETS[dataset]
@@ -147,16 +147,18 @@ def get_cfg(backbone="dla34", dataset="kitti_3d", nms_thresh=0.75, meta_arch="DD
                           WEIGHT_BOX3D=2.0, WEIGHT_CONF3D=1.0),
                 PREPARE_TARGET=dict(CENTER_SAMPLE=True, POS_RADIUS=1.5),
             ),
-            NUSC=dict(
-                LOSS=dict(WEIGHT_ATTR=0.2, WEIGHT_SPEED=0.2),
-                INFERENCE=dict(NUM_IMAGES_PER_SAMPLE=6, MAX_NUM_DETS_PER_SAMPLE=500),
-            ),
         ),
-        DATALOADER=dict(TEST=dict(NUM_IMAGES_PER_GROUP=6)),
+        # engine-side switch (not a reference key): 16-bit storage type of activations / weights, "bf16" | "fp16"
+        B200=dict(ACT_DTYPE=act_dtype),
         # test-time augmentation: configs/experiments/dd3d_kitti_{dla34,v99}.yaml:47-53, dd3d_nusc_v99.yaml:57-63
-        TEST=dict(IMS_PER_BATCH=80 if dataset == "kitti_3d" else 192,
+        # IMS_PER_BATCH: dd3d_kitti_*.yaml 80, dd3d_nusc_dla34.yaml 96, dd3d_nusc_v99.yaml 192
+        TEST=dict(IMS_PER_BATCH=80 if dataset == "kitti_3d" else (96 if backbone == "dla34" else 192),
                   AUG=dict(ENABLED=True,
                            MIN_SIZES=[320, 384, 448, 512, 576] if dataset == "kitti_3d" else [640, 768, 896, 1024, 1152],
                            MAX_SIZE=100000, FLIP=True)),
     )
+    if meta_arch == "NuscenesDD3D":  # configs/experiments/dd3d_nusc_{dla34,v99}.yaml:30-36,69-71
+        cfg["DD3D"]["NUSC"] = dict(LOSS=dict(WEIGHT_ATTR=0.2, WEIGHT_SPEED=0.2),
+                                   INFERENCE=dict(NUM_IMAGES_PER_SAMPLE=6, MAX_NUM_DETS_PER_SAMPLE=500))
+        cfg["DATALOADER"] = dict(TEST=dict(NUM_IMAGES_PER_GROUP=6))
     return _to_node(cfg)

@@ -1,4 +1,5 @@
 // extern "C" boundary of libdd3d_b200.so (declared in include/dd3d_b200.h).  Plain pointers and sizes only.
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -15,6 +16,7 @@ struct dd3d_engine {
 namespace {
 
 thread_local std::string g_create_error;
+int g_op_fp16 = 0;  // element type of the operator-level entry points (dd3d_set_conv_policy("op_fp16", v))
 
 template <typename F>
 int guarded(dd3d_handle h, F&& f) {
@@ -119,6 +121,10 @@ int dd3d_set_conv_policy(const char* name, int value) {
         conv_set_cta2(value);
         return DD3D_OK;
     }
+    if (!strcmp(name, "op_fp16")) {
+        g_op_fp16 = value ? 1 : 0;
+        return DD3D_OK;
+    }
     return DD3D_ERR_INVALID;
 }
 
@@ -173,10 +179,21 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value) {
             e.desc.do_nms = value ? 1 : 0;
         } else if (n == "profile") {
             e.opt_profile = value ? 1 : 0;
+        } else if (n == "workspace_fill") {
+            e.opt_workspace_fill = (value >= 0 && value <= 255) ? value : -1;
         } else {
             throw EngineError(DD3D_ERR_INVALID, "unknown option: " + n);
         }
     });
+}
+
+int dd3d_num_ops(dd3d_handle h) {
+    int n = 0;
+    int st = guarded(h, [&](Engine& e) {
+        if (!e.plan.valid) throw EngineError(DD3D_ERR_STATE, "no plan");
+        n = static_cast<int>(e.plan.ops.size());
+    });
+    return st == DD3D_OK ? n : st;
 }
 
 int dd3d_launches_per_forward(dd3d_handle h) {
@@ -207,7 +224,17 @@ int dd3d_get_tensor(dd3d_handle h, const char* name, void** d_ptr, int32_t dims[
             if (l < 0 || l >= kLevels) throw EngineError(DD3D_ERR_INVALID, "unknown tensor: " + n);
             return l;
         };
-        if (n == "input") {
+        if (n.rfind("op", 0) == 0) {  // "op<i>" / "op<i>:<seg>": bf16 output view of engine op i (launch order)
+            const size_t colon = n.find(':');
+            const int i = atoi(n.substr(2, colon == std::string::npos ? std::string::npos : colon - 2).c_str());
+            const int sg = colon == std::string::npos ? 0 : atoi(n.substr(colon + 1).c_str());
+            if (i < 0 || i >= static_cast<int>(P.ops.size()) || sg < 0 || sg >= P.ops[i].nouts)
+                throw EngineError(DD3D_ERR_INVALID, "no such op output: " + n);
+            const View& v = P.ops[i].outs[sg];
+            *d_ptr = v.ptr;
+            const int32_t d[6] = {v.B, v.H, v.W, v.C, v.pitch, 2};
+            memcpy(dims, d, sizeof(d));
+        } else if (n == "input") {
             *d_ptr = P.input.ptr;
             const int32_t d[6] = {P.B, P.Hp, P.Wp, 4, 4, 2};
             memcpy(dims, d, sizeof(d));
@@ -263,6 +290,7 @@ int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch,
     p.block_n = block_n;
     p.relu = relu;
     p.out_mode = out_f32 ? 1 : 0;
+    p.fp16 = g_op_fp16;
     ConvSeg& g = p.seg[0];
     const int Ho = H / stride, Wo = W / stride;
     g.H = Ho;
@@ -274,14 +302,14 @@ int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch,
     if (p.halo) {
         g.th = kHaloTh;
         g.tw = kHaloTw;
-        ok = ok && make_act_map_halo(&g.in_map[0], d_in, B, H, W, cin, in_pitch);
+        ok = ok && make_act_map_halo(&g.in_map[0], d_in, B, H, W, cin, in_pitch, g_op_fp16);
     } else if (stride == 1) {
-        ok = ok && make_act_map(&g.in_map[0], d_in, B, H, W, cin, in_pitch, g.th, g.tw);
+        ok = ok && make_act_map(&g.in_map[0], d_in, B, H, W, cin, in_pitch, g.th, g.tw, g_op_fp16);
     } else {
-        ok = ok && make_act_map_s2(&g.in_map[0], d_in, 0, B, H, W, cin, in_pitch, g.th, g.tw) &&
-             make_act_map_s2(&g.in_map[1], d_in, 1, B, H, W, cin, in_pitch, g.th, g.tw);
+        ok = ok && make_act_map_s2(&g.in_map[0], d_in, 0, B, H, W, cin, in_pitch, g.th, g.tw, g_op_fp16) &&
+             make_act_map_s2(&g.in_map[1], d_in, 1, B, H, W, cin, in_pitch, g.th, g.tw, g_op_fp16);
     }
-    if (!out_f32) ok = ok && make_act_map(&g.out_map, d_out, B, Ho, Wo, cout, out_pitch, g.th, g.tw);
+    if (!out_f32) ok = ok && make_act_map(&g.out_map, d_out, B, Ho, Wo, cout, out_pitch, g.th, g.tw, g_op_fp16);
     if (!ok) {
         fprintf(stderr, "dd3d_op_conv2d: %s\n", conv_last_error());
         return DD3D_ERR_CUDA;
@@ -299,7 +327,7 @@ int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch,
         g.res_W = res_up2 ? Wo / 2 : Wo;
     }
     conv_finalize_params(&p);
-    if (!make_weight_map(&p.w_map, d_w, taps * kchunks * kBlockK, cout_pad, p.cta2 ? block_n / 2 : block_n)) {
+    if (!make_weight_map(&p.w_map, d_w, taps * kchunks * kBlockK, cout_pad, p.cta2 ? block_n / 2 : block_n, g_op_fp16)) {
         fprintf(stderr, "dd3d_op_conv2d: %s\n", conv_last_error());
         return DD3D_ERR_CUDA;
     }
@@ -310,14 +338,14 @@ int dd3d_op_stem_conv(const void* d_in4, const void* d_w, const float* d_scale, 
                       int H, int W, int ksize, int stride, int cout, int out_pitch, dd3d_stream stream) {
     return cuda_status(launch_stem_tc(static_cast<const __nv_bfloat16*>(d_in4), static_cast<const __nv_bfloat16*>(d_w),
                                       d_scale, d_bias, static_cast<__nv_bfloat16*>(d_out), B, H, W, ksize, stride, cout,
-                                      out_pitch, device_sms(), static_cast<cudaStream_t>(stream)),
+                                      out_pitch, device_sms(), static_cast<cudaStream_t>(stream), g_op_fp16),
                        nullptr);
 }
 
 int dd3d_op_preprocess(const void* d_images, int img_dtype, const int32_t* d_sizes2, void* d_out4, int B, int Hs, int Ws,
                        int Hp, int Wp, const float* h_mean, const float* h_std, dd3d_stream stream) {
     return cuda_status(launch_preprocess(d_images, img_dtype == DD3D_IMG_U8, d_sizes2, 2, static_cast<__nv_bfloat16*>(d_out4),
-                                         B, Hs, Ws, Hp, Wp, h_mean, h_std, static_cast<cudaStream_t>(stream)),
+                                         B, Hs, Ws, Hp, Wp, h_mean, h_std, static_cast<cudaStream_t>(stream), g_op_fp16),
                        nullptr);
 }
 
@@ -328,7 +356,7 @@ int dd3d_op_maxpool(const void* d_in, void* d_out, int B, int H, int W, int C, i
     const int Wo = ksize == 2 ? W / 2 : (W - 3 + 1) / 2 + 1;
     return cuda_status(launch_maxpool(static_cast<const __nv_bfloat16*>(d_in), static_cast<__nv_bfloat16*>(d_out), B, H,
                                       W, C, in_pitch, Ho, Wo, out_pitch, ksize, device_sms(),
-                                      static_cast<cudaStream_t>(stream)),
+                                      static_cast<cudaStream_t>(stream), g_op_fp16),
                        nullptr);
 }
 
@@ -344,7 +372,7 @@ int dd3d_op_ese(const void* d_x, int x_pitch, const float* d_fc_w, const float* 
     return cuda_status(launch_ese(static_cast<const __nv_bfloat16*>(d_x), x_pitch, d_fc_w, d_fc_b,
                                   static_cast<const __nv_bfloat16*>(d_identity), id_pitch,
                                   static_cast<__nv_bfloat16*>(d_out), out_pitch, partial, gate, B, HW, C, device_sms(),
-                                  static_cast<cudaStream_t>(stream)),
+                                  static_cast<cudaStream_t>(stream), g_op_fp16),
                        nullptr);
 }
 
@@ -394,7 +422,7 @@ int dd3d_op_resize_preprocess(const uint8_t* d_raw, int raw_h, int raw_w, const 
     static ResizeTables tables;  // operator-level entry point: one table cache per process (tests; not thread safe)
     return cuda_status(tables.launch(d_raw, raw_h, raw_w, h_raw_sizes, h_new_sizes, h_flip,
                                      static_cast<__nv_bfloat16*>(d_out4), B, Hp, Wp, h_mean, h_std,
-                                     static_cast<cudaStream_t>(stream)),
+                                     static_cast<cudaStream_t>(stream), g_op_fp16),
                        nullptr);
 }
 

@@ -33,6 +33,7 @@
 #include <algorithm>
 #include <string>
 
+#include "act16.cuh"
 #include "ptx.cuh"
 
 namespace dd3d {
@@ -93,11 +94,6 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work, 
     t.y0 = ty * g.th;
     t.x0 = tx * g.tw;
     return t;
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
 }
 
 // elect.sync: exactly one lane of the (converged) warp gets true.  Keeping the role loops warp-converged and
@@ -321,7 +317,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       if (!CTA2 || leader) {  // CTA pair: only the leader issues; its MMAs read both CTAs' smem and write both TMEMs
         // -------------------------------------------------------------------- warp 1: tcgen05.mma issuer
         // Descriptor high word is constant; the low word is (addr >> 4) | LBO, advanced by 2 (= 32 bytes) per K=16 step.
-        const uint32_t idesc = ptx::make_idesc_bf16(CTA2 ? 2 * kBlockM : kBlockM, p.block_n);
+        const uint32_t idesc = ptx::make_idesc_f16(CTA2 ? 2 * kBlockM : kBlockM, p.block_n, p.fp16);
         constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);                   // SBO 1024, v1, SW128
         constexpr uint32_t kHaloDescHi = ((kHaloPW * 128u) >> 4) | (1u << 14) | (2u << 29);     // SBO = 10 pixels
         const uint32_t lo0 = (ptx::smem_u32(smem) >> 4) | (1u << 16);
@@ -530,10 +526,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) {
                             if (i < cols) {
-                                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rpre[i >> 3]);
+                                const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rpre[i >> 3]);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const float2 f = __bfloat1622float2(rb[j]);
+                                    const float2 f = unpack2_act(rb[j], p.fp16);
                                     y[i + 2 * j] += f.x;
                                     y[i + 2 * j + 1] += f.y;
                                 }
@@ -550,10 +546,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         for (int i = 0; i < 32; i += 8) {
                             if (i < cols) {
                                 uint4 o;
-                                o.x = pack_bf16(y[i + 0], y[i + 1]);
-                                o.y = pack_bf16(y[i + 2], y[i + 3]);
-                                o.z = pack_bf16(y[i + 4], y[i + 5]);
-                                o.w = pack_bf16(y[i + 6], y[i + 7]);
+                                if (p.fp16) {  // warp-uniform
+                                    o.x = pack2_f16(y[i + 0], y[i + 1]);
+                                    o.y = pack2_f16(y[i + 2], y[i + 3]);
+                                    o.z = pack2_f16(y[i + 4], y[i + 5]);
+                                    o.w = pack2_f16(y[i + 6], y[i + 7]);
+                                } else {
+                                    o.x = pack2_bf16(y[i + 0], y[i + 1]);
+                                    o.y = pack2_bf16(y[i + 2], y[i + 3]);
+                                    o.z = pack2_bf16(y[i + 4], y[i + 5]);
+                                    o.w = pack2_bf16(y[i + 6], y[i + 7]);
+                                }
                                 const int c16 = (h + i) >> 3;  // 16-byte chunk within the 128-byte row
                                 *reinterpret_cast<uint4*>(stag + row * 128 + ((c16 ^ (row & 7)) << 4)) = o;
                             }
@@ -596,10 +599,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                             const int ry = t.y0 + (r >> g.tw_shift), rx = t.x0 + (r & (g.tw - 1));
                             if (ry < g.H && rx < g.W) {
                                 const uint4 u = *reinterpret_cast<const uint4*>(stag + r * 128 + ((cg ^ (r & 7)) << 4));
-                                const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+                                const uint32_t* b2 = reinterpret_cast<const uint32_t*>(&u);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const float2 f = __bfloat1622float2(b2[j]);
+                                    const float2 f = unpack2_act(b2[j], p.fp16);
                                     ps[2 * j] += f.x;
                                     ps[2 * j + 1] += f.y;
                                 }
@@ -678,11 +681,12 @@ EncodeTiledFn get_encode_fn() {
 }
 
 bool encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-            const cuuint32_t* box, CUtensorMapL2promotion promo, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+            const cuuint32_t* box, CUtensorMapL2promotion promo, int fp16,
+            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) return false;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -701,31 +705,31 @@ bool encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims
 const char* conv_last_error() { return g_conv_error.c_str(); }
 
 // NHWC bf16 activation view: C logical channels of a buffer with `pitch` channels per pixel.
-bool make_act_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch, int th, int tw) {
+bool make_act_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch, int th, int tw, int fp16) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)th, 1};
-    return encode(map, base, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    return encode(map, base, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, fp16);
 }
 
 // Parity-split view for stride-2 convs: element (b, 2*h2+hp, 2*w2+wp, c) -> coords {c, w2, hp, h2, b} of map[wp].
 bool make_act_map_s2(CUtensorMap* map, const void* base, int wp, int B, int H, int W, int C, int pitch, int th,
-                     int tw) {
+                     int tw, int fp16) {
     const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(base) + (size_t)wp * pitch;
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)(W / 2), 2, (cuuint64_t)(H / 2), (cuuint64_t)B};
     cuuint64_t strides[4] = {(cuuint64_t)2 * pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)2 * W * pitch * 2,
                              (cuuint64_t)H * W * pitch * 2};
     cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, 1, (cuuint32_t)th, 1};
-    return encode(map, b, 5, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    return encode(map, b, 5, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, fp16);
 }
 
 int conv_halo_mode() { return 2; }  // one 128B-swizzled [18][10][64ch] box per 64-channel block
 
-bool make_act_map_halo(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch) {
+bool make_act_map_halo(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch, int fp16) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kHaloPW, (cuuint32_t)kHaloPH, 1};
-    return encode(map, base, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    return encode(map, base, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, fp16);
 }
 
 bool conv_prefer_halo(int taps, int stride, int block_n, int nseg, const int* Hs, const int* Ws) {
@@ -748,11 +752,11 @@ bool conv_prefer_halo(int taps, int stride, int block_n, int nseg, const int* Hs
     return halo_tiles * 100 <= gen_tiles * 110;  // fixed 16x8 tiling may cost at most 10 % more tiles
 }
 
-bool make_weight_map(CUtensorMap* map, const void* base, int ktot, int cout_pad, int block_n) {
+bool make_weight_map(CUtensorMap* map, const void* base, int ktot, int cout_pad, int block_n, int fp16) {
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout_pad};
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
-    return encode(map, base, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    return encode(map, base, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, fp16);
 }
 
 // Pick the 128-pixel patch shape that wastes the fewest out-of-image pixels.

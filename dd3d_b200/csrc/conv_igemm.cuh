@@ -60,16 +60,17 @@ struct ConvParams {
     int total_tiles;  // sum of M-tiles over the segments
     int pair_work;    // ceil(total_tiles / 2) * n_blocks
     float inv_n_blocks;
+    int fp16;         // 16-bit storage type of activations and weights: 0 bf16, 1 fp16 (act16.cuh)
 };
 static_assert(sizeof(ConvParams) <= 4096, "kernel parameter space");
 constexpr int kConvCta2Default = 2;  // auto; DD3D_CONV_CTA2=0|1|auto overrides
 
 // Host helpers (conv_igemm.cu)
 const char* conv_last_error();
-bool make_act_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch, int th, int tw);
+bool make_act_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch, int th, int tw, int fp16 = 0);
 bool make_act_map_s2(CUtensorMap* map, const void* base, int wp, int B, int H, int W, int C, int pitch, int th,
-                     int tw);
-bool make_weight_map(CUtensorMap* map, const void* base, int ktot, int cout_pad, int block_n);
+                     int tw, int fp16 = 0);
+bool make_weight_map(CUtensorMap* map, const void* base, int ktot, int cout_pad, int block_n, int fp16 = 0);
 // CTA-pair policy for ConvParams::cta2 before conv_finalize_params: 0 never, 1 always, 2 auto (finalize decides; the
 // w_map box must then be block_n / 2 rows iff the finalized cta2 is 1)
 int conv_use_cta2();
@@ -79,7 +80,7 @@ int conv_tiles_per_image(int H, int W);  // M-tiles per image of the generic til
 // Halo variant (3x3, stride 1): one 128B-swizzled [18][10][64 ch] patch per 64-channel block serves all nine taps.
 constexpr int kHaloTh = 16, kHaloTw = 8;
 int conv_halo_mode();
-bool make_act_map_halo(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch);
+bool make_act_map_halo(CUtensorMap* map, const void* base, int B, int H, int W, int C, int pitch, int fp16 = 0);
 // Policy: use the halo variant when its fixed 16x8 tiling costs at most 10 % more tiles than the best generic
 // tiling over all segments (env DD3D_CONV_MODE=generic|halo overrides, for tests).
 bool conv_prefer_halo(int taps, int stride, int block_n, int nseg, const int* Hs, const int* Ws);

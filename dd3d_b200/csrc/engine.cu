@@ -9,6 +9,8 @@
 // concats never materialised (producers write channel slices); predictors fused per tower.
 #include "engine.cuh"
 
+#include "act16.cuh"
+
 #include <math.h>
 #include <string.h>
 
@@ -28,15 +30,6 @@ void cuda_check(cudaError_t e, const char* what) {
     if (e != cudaSuccess) fail(DD3D_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-uint16_t f32_to_bf16(float f) {  // round to nearest even (matches __float2bfloat16_rn / torch .to(bfloat16))
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
-    const uint32_t lsb = (u >> 16) & 1u;
-    u += 0x7fffu + lsb;
-    return static_cast<uint16_t>(u >> 16);
-}
-
 }  // namespace
 
 // ================================================================================================ Engine basics
@@ -46,6 +39,8 @@ Engine::Engine(const dd3d_model_desc& d) : desc(d) {
     if (d.num_classes < 1 || d.num_classes > DD3D_MAX_CLASSES) fail(DD3D_ERR_INVALID, "num_classes out of range");
     if (d.pre_nms_topk < 1 || d.pre_nms_topk * kLevels > 8192) fail(DD3D_ERR_INVALID, "pre_nms_topk out of range");
     if (d.out_cap < 1) fail(DD3D_ERR_INVALID, "out_cap must be positive");
+    if (d.act_dtype != DD3D_ACT_BF16 && d.act_dtype != DD3D_ACT_FP16) fail(DD3D_ERR_INVALID, "unknown act_dtype");
+    fp16 = d.act_dtype == DD3D_ACT_FP16 ? 1 : 0;
     cuda_check(cudaGetDevice(&device), "cudaGetDevice");
     cudaDeviceProp prop;
     cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
@@ -137,13 +132,13 @@ const ConvLayer& Engine::conv_layer(const std::string& key, const std::vector<st
             for (int ci = 0; ci < cin; ++ci)
                 for (int t = 0; t < L.taps; ++t)
                     packed[(static_cast<size_t>(co0 + co) * L.taps + t) * cin_pad + ci] =
-                        f32_to_bf16(w.data[(static_cast<size_t>(co) * cin + ci) * L.taps + t]);
+                        host_f32_to_act(w.data[(static_cast<size_t>(co) * cin + ci) * L.taps + t], fp16);
         co0 += co_n;
     }
     L.d_w = static_cast<__nv_bfloat16*>(dev_alloc(packed.size() * 2));
     cuda_check(cudaMemcpy(L.d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice), "upload conv weights");
-    if (!make_weight_map(&L.w_map, L.d_w, L.ktot, L.cout_pad, L.block_n)) fail(DD3D_ERR_CUDA, conv_last_error());
-    if (!make_weight_map(&L.w_map_half, L.d_w, L.ktot, L.cout_pad, L.block_n / 2)) fail(DD3D_ERR_CUDA, conv_last_error());
+    if (!make_weight_map(&L.w_map, L.d_w, L.ktot, L.cout_pad, L.block_n, fp16)) fail(DD3D_ERR_CUDA, conv_last_error());
+    if (!make_weight_map(&L.w_map_half, L.d_w, L.ktot, L.cout_pad, L.block_n / 2, fp16)) fail(DD3D_ERR_CUDA, conv_last_error());
     return convs.emplace(key, L).first->second;
 }
 
@@ -264,6 +259,7 @@ struct Builder {
         p.block_n = L.block_n;
         p.relu = relu ? 1 : 0;
         p.out_mode = f32_out ? 1 : 0;
+        p.fp16 = E->fp16;
         {
             int hs[kMaxSeg], ws[kMaxSeg];
             for (int s = 0; s < p.nseg; ++s) {
@@ -289,12 +285,14 @@ struct Builder {
             if (p.halo) {
                 g.th = kHaloTh;
                 g.tw = kHaloTw;
-                ok = make_act_map_halo(&g.in_map[0], sp.in.ptr, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch);
+                ok = make_act_map_halo(&g.in_map[0], sp.in.ptr, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, E->fp16);
             } else if (stride == 1) {
-                ok = make_act_map(&g.in_map[0], sp.in.ptr, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, g.th, g.tw);
+                ok = make_act_map(&g.in_map[0], sp.in.ptr, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, g.th, g.tw, E->fp16);
             } else {
-                ok = make_act_map_s2(&g.in_map[0], sp.in.ptr, 0, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, g.th, g.tw) &&
-                     make_act_map_s2(&g.in_map[1], sp.in.ptr, 1, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, g.th, g.tw);
+                ok = make_act_map_s2(&g.in_map[0], sp.in.ptr, 0, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, g.th, g.tw,
+                                     E->fp16) &&
+                     make_act_map_s2(&g.in_map[1], sp.in.ptr, 1, B, sp.in.H, sp.in.W, sp.in.C, sp.in.pitch, g.th, g.tw,
+                                     E->fp16);
             }
             if (!ok) fail(DD3D_ERR_CUDA, conv_last_error());
             g.scale = sp.epi->d_scale;
@@ -306,7 +304,7 @@ struct Builder {
             } else {
                 if (sp.out.H != Ho || sp.out.W != Wo || sp.out.C != L.cout)
                     fail(DD3D_ERR_INVALID, "conv output view mismatch");
-                if (!make_act_map(&g.out_map, sp.out.ptr, B, Ho, Wo, sp.out.C, sp.out.pitch, g.th, g.tw))
+                if (!make_act_map(&g.out_map, sp.out.ptr, B, Ho, Wo, sp.out.C, sp.out.pitch, g.th, g.tw, E->fp16))
                     fail(DD3D_ERR_CUDA, conv_last_error());
             }
             if (sp.has_res) {
@@ -321,6 +319,10 @@ struct Builder {
         p.w_map = p.cta2 ? L.w_map_half : L.w_map;
         for (int s = 0; s < p.nseg; ++s)
             op.flops += 2.0 * B * p.seg[s].H * p.seg[s].W * static_cast<double>(L.cout) * L.cin * L.taps;
+        if (!f32_out) {
+            op.nouts = p.nseg;
+            for (int s = 0; s < p.nseg; ++s) op.outs[s] = segs[s].out;
+        }
         P->ops.push_back(op);
     }
 
@@ -348,6 +350,8 @@ struct Builder {
         op.in = in;
         op.out = out;
         op.ksize = ksize;
+        op.outs[0] = out;
+        op.nouts = 1;
         P->ops.push_back(op);
     }
     void relu(View in, View out) {
@@ -356,6 +360,8 @@ struct Builder {
         op.type = Op::RELU;
         op.in = in;
         op.out = out;
+        op.outs[0] = out;
+        op.nouts = 1;
         P->ops.push_back(op);
     }
 
@@ -431,6 +437,8 @@ struct Builder {
         op.ksize = ksize;
         op.stride = stride;
         op.stem = &S;
+        op.outs[0] = out;
+        op.nouts = 1;
         P->ops.push_back(op);
     }
 
@@ -522,6 +530,8 @@ struct Builder {
         op.f1 = gate;
         op.f2 = tile_partial;
         op.ksize = T;
+        op.outs[0] = dst;
+        op.nouts = 1;
         P->ops.push_back(op);
     }
 
@@ -727,7 +737,7 @@ const StemLayer& Engine::stem_layer(const std::string& wname, const std::string&
         for (int c = 0; c < 3; ++c)
             for (int t = 0; t < ksize * ksize; ++t)
                 packed[static_cast<size_t>(co) * kpad + t * 4 + c] =
-                    f32_to_bf16(w.data[(static_cast<size_t>(co) * 3 + c) * ksize * ksize + t]);
+                    host_f32_to_act(w.data[(static_cast<size_t>(co) * 3 + c) * ksize * ksize + t], fp16);
     S.d_w = static_cast<__nv_bfloat16*>(dev_alloc(packed.size() * 2));
     cuda_check(cudaMemcpy(S.d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice), "upload stem weights");
     S.epi = bn_epilogue(wname + "|" + bn, bn, "", S.cout);
@@ -821,7 +831,9 @@ void Engine::make_plan(int B, int Hs, int Ws, void* workspace, size_t bytes) {
     if (B < 1 || Hs < 1 || Ws < 1) fail(DD3D_ERR_INVALID, "bad plan shape");
     if (slot_busy[0] || slot_busy[1]) fail(DD3D_ERR_STATE, "plan change with a pending dd3d_submit_host");
     cuda_check(cudaSetDevice(device), "cudaSetDevice");
-    if (workspace == nullptr && plan.valid && plan.owned_workspace && plan.B == B && plan.Hs == Hs && plan.Ws == Ws) return;
+    if (workspace == nullptr && plan.valid && plan.owned_workspace && plan.B == B && plan.Hs == Hs && plan.Ws == Ws &&
+        opt_workspace_fill < 0)
+        return;
     // park the active plan if it is engine-owned and small, else free it
     if (plan.valid && plan.owned_workspace && plan.owned_bytes <= kPlanCacheBytes) {
         if (plan_cache.size() >= kPlanCacheMax) {
@@ -833,7 +845,7 @@ void Engine::make_plan(int B, int Hs, int Ws, void* workspace, size_t bytes) {
     } else {
         release_plan();
     }
-    if (workspace == nullptr) {
+    if (workspace == nullptr && opt_workspace_fill < 0) {
         auto it = plan_cache.find({B, Hs, Ws});
         if (it != plan_cache.end()) {
             plan = std::move(it->second);
@@ -850,6 +862,13 @@ void Engine::make_plan(int B, int Hs, int Ws, void* workspace, size_t bytes) {
         fail(DD3D_ERR_INVALID, "workspace too small: need " + std::to_string(need) + " bytes");
     }
     if (reinterpret_cast<uintptr_t>(workspace) % 1024) fail(DD3D_ERR_INVALID, "workspace must be 1024-byte aligned");
+    // Every byte a kernel reads is written earlier in the same forward, so the arena needs no clearing.  Option
+    // "workspace_fill" (0..255; -1 = leave as is) proves it: tests plan once over 0x00 and once over 0xFF (= NaN in bf16
+    // and fp32) and require bit-identical maps and detections (tests/test_determinism_gpu.py).
+    if (opt_workspace_fill >= 0) {
+        cuda_check(cudaMemset(workspace, opt_workspace_fill, need), "cudaMemset(workspace)");
+        cuda_check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    }
     build(&plan, B, Hs, Ws, workspace, false);
     plan.valid = true;
     // decode / NMS parameter blocks
@@ -982,11 +1001,11 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
     if (raw) {
         cuda_check(resize_tables.launch(raw_args.d_raw, raw_args.raw_h, raw_args.raw_w, raw_args.h_raw_sizes,
                                         raw_args.h_new_sizes, raw_args.h_flip, P.input.ptr, P.B, P.Hp, P.Wp, desc.pixel_mean, desc.pixel_std,
-                                        stream),
+                                        stream, fp16),
                    "resize + preprocess");
     } else {
         cuda_check(launch_preprocess(d_images, img_dtype == DD3D_IMG_U8, d_sizes, 4, P.input.ptr, P.B, P.Hs, P.Ws, P.Hp,
-                                     P.Wp, desc.pixel_mean, desc.pixel_std, stream),
+                                     P.Wp, desc.pixel_mean, desc.pixel_std, stream, fp16),
                    "preprocess");
     }
     mark(0);
@@ -998,19 +1017,19 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
             case Op::STEM:
                 cuda_check(launch_stem_tc(op.in.ptr, op.stem->d_w, op.stem->epi.d_scale, op.stem->epi.d_bias, op.out.ptr,
                                           P.B, op.in.H, op.in.W, op.ksize, op.stride, op.stem->cout, op.out.pitch, num_sms,
-                                          stream),
+                                          stream, fp16),
                            "stem conv");
                 break;
             case Op::POOL:
                 cuda_check(launch_maxpool(op.in.ptr, op.out.ptr, P.B, op.in.H, op.in.W, op.in.C, op.in.pitch, op.out.H,
-                                          op.out.W, op.out.pitch, op.ksize, num_sms, stream),
+                                          op.out.W, op.out.pitch, op.ksize, num_sms, stream, fp16),
                            "maxpool");
                 break;
             case Op::ESE:
                 cuda_check(launch_ese_fused(op.in.ptr, op.in.pitch, op.f2, op.ksize, op.ese->d_w, op.ese->d_b,
                                             op.has_identity ? op.identity.ptr : nullptr,
                                             op.has_identity ? op.identity.pitch : 0, op.out.ptr, op.out.pitch, op.f0, op.f1,
-                                            P.B, op.in.H * op.in.W, op.in.C, num_sms, stream),
+                                            P.B, op.in.H * op.in.W, op.in.C, num_sms, stream, fp16),
                            "eSE");
                 break;
             case Op::RELU:

@@ -58,6 +58,8 @@ struct Op {
     enum Type { CONV, STEM, POOL, ESE, RELU } type;
     ConvParams conv;
     View in, out, identity;
+    View outs[kMaxSeg];  // bf16 output views (CONV: one per segment; others: outs[0] == out), for dd3d_get_tensor "op<i>"
+    int nouts = 0;
     bool has_identity = false;
     int ksize = 0, stride = 0;
     const StemLayer* stem = nullptr;
@@ -149,9 +151,11 @@ class Engine {
     dd3d_model_desc desc;
     int device = 0;
     int num_sms = 148;
+    int fp16 = 0;  // desc.act_dtype == DD3D_ACT_FP16: 16-bit storage of activations / weights is fp16 instead of bf16
     bool finalized = false;
     int opt_do_postprocess = 1;
     int opt_profile = 0;
+    int opt_workspace_fill = -1;  // >= 0: byte the whole arena is filled with at dd3d_plan (poison test)
     std::vector<cudaEvent_t> prof_ev;
     std::vector<int> prof_cat;
     size_t prof_used = 0;

@@ -212,11 +212,14 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
-__host__ __device__ inline uint32_t make_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+// kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A / B format (bits 7-9 / 10-12: 0 = fp16, 1 = bf16), both
+// K-major, M=m, N=n.
+__host__ __device__ inline uint32_t make_idesc_f16(int m, int n, int fp16) {
+    const uint32_t fmt = fp16 ? 0u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
 }
+__host__ __device__ inline uint32_t make_idesc_bf16(int m, int n) { return make_idesc_f16(m, n, 0); }
 
 // TMEM -> registers: each lane of the warp reads its own TMEM lane (row), 32 / 16 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {

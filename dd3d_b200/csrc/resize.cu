@@ -9,6 +9,8 @@
 // the vertical pass -- so the pixels are BIT-IDENTICAL to what the reference's dataloader produces.
 #include "resize.cuh"
 
+#include "act16.cuh"
+
 #include <math.h>
 
 #include <vector>
@@ -24,10 +26,6 @@ constexpr int kResizeThreads = 256;
 
 __device__ __forceinline__ int clip8(int acc) { return min(max(acc >> kPrecisionBits, 0), 255); }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
 
 struct ResizeParams {
     const uint8_t* raw;      // [B][raw_h][raw_w][3]
@@ -35,6 +33,7 @@ struct ResizeParams {
     __nv_bfloat16* dst;      // [B][Hp][Wp][4]
     int raw_h, raw_w, Hp, Wp, rows_cap;
     float m0, m1, m2, s0, s1, s2;
+    int fp16;  // 16-bit output format (act16.cuh)
 };
 
 __global__ void __launch_bounds__(kResizeThreads) resize_preprocess_kernel(const ResizeParams p) {
@@ -96,8 +95,8 @@ __global__ void __launch_bounds__(kResizeThreads) resize_preprocess_kernel(const
             v2 = (static_cast<float>(clip8(a2)) - p.m2) / p.s2;
         }
         uint2 o;
-        o.x = pack_bf16x2(v0, v1);
-        o.y = pack_bf16x2(v2, 0.f);
+        o.x = pack2_act(v0, v1, p.fp16);
+        o.y = pack2_act(v2, 0.f, p.fp16);
         *reinterpret_cast<uint2*>(dst + (static_cast<size_t>(y) * p.Wp + x) * 4) = o;
     }
 }
@@ -189,7 +188,7 @@ const ResizeTables::Axis* ResizeTables::axis(int in_size, int out_size, cudaErro
 
 cudaError_t ResizeTables::launch(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes,
                                  const int32_t* h_new_sizes, const int32_t* h_flip, __nv_bfloat16* d_out4, int B, int Hp,
-                                 int Wp, const float mean[3], const float std[3], cudaStream_t stream) {
+                                 int Wp, const float mean[3], const float std[3], cudaStream_t stream, int fp16) {
     cudaError_t err = cudaSuccess;
     h_img.resize(B);
     int rows_cap = 1;
@@ -234,6 +233,7 @@ cudaError_t ResizeTables::launch(const uint8_t* d_raw, int raw_h, int raw_w, con
     p.raw_h = raw_h; p.raw_w = raw_w; p.Hp = Hp; p.Wp = Wp; p.rows_cap = rows_cap;
     p.m0 = mean[0]; p.m1 = mean[1]; p.m2 = mean[2];
     p.s0 = std[0]; p.s1 = std[1]; p.s2 = std[2];
+    p.fp16 = fp16;
     dim3 grid((Wp + kTileW - 1) / kTileW, (Hp + kTileH - 1) / kTileH, B);
     resize_preprocess_kernel<<<grid, kResizeThreads, smem, stream>>>(p);
     return cudaGetLastError();

@@ -33,7 +33,7 @@ class ResizeTables {
     // h_flip: [B] flags or nullptr.
     cudaError_t launch(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes, const int32_t* h_new_sizes,
                        const int32_t* h_flip, __nv_bfloat16* d_out4, int B, int Hp, int Wp, const float mean[3],
-                       const float std[3], cudaStream_t stream);
+                       const float std[3], cudaStream_t stream, int fp16 = 0);
 
   private:
     struct Axis {

@@ -6,6 +6,8 @@
 //   relu         : p7 input (detectron2 LastLevelP6P7)
 #include "small_kernels.cuh"
 
+#include "act16.cuh"
+
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -13,19 +15,11 @@ namespace dd3d {
 
 namespace {
 
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ float2 unpack2(uint32_t u) {
-    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
-}
-
 // ------------------------------------------------------------------------------------------ preprocess
 template <typename T>
 __global__ void preprocess_kernel(const T* __restrict__ src, const int* __restrict__ sizes, __nv_bfloat16* __restrict__ dst,
                                   int B, int Hs, int Ws, int Hp, int Wp, int size_stride, float m0, float m1, float m2,
-                                  float s0, float s1, float s2) {
+                                  float s0, float s1, float s2, int fp16) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int b = blockIdx.z;
@@ -40,24 +34,28 @@ __global__ void preprocess_kernel(const T* __restrict__ src, const int* __restri
         v2 = (static_cast<float>(p[2 * plane]) - m2) / s2;
     }
     uint2 o;
-    o.x = pack2(v0, v1);
-    o.y = pack2(v2, 0.f);
+    o.x = pack2_act(v0, v1, fp16);
+    o.y = pack2_act(v2, 0.f, fp16);
     *reinterpret_cast<uint2*>(dst + (static_cast<size_t>(b * Hp + y) * Wp + x) * 4) = o;
 }
 
 // ------------------------------------------------------------------------------------------ max-pool
-__device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
+// element-wise maximum of 8 packed 16-bit values; through fp32, which is exact for bf16 and fp16 alike
+__device__ __forceinline__ uint4 max8(uint4 a, uint4 b, int fp16) {
     uint4 r;
-    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-    __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+    const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+    const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+    uint32_t* pr = reinterpret_cast<uint32_t*>(&r);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+    for (int i = 0; i < 4; ++i) {
+        const float2 x = unpack2_act(pa[i], fp16), y = unpack2_act(pb[i], fp16);
+        pr[i] = pack2_act(fmaxf(x.x, y.x), fmaxf(x.y, y.y), fp16);
+    }
     return r;
 }
 
 __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W,
-                               int C, int in_pitch, int Ho, int Wo, int out_pitch, int ksize) {
+                               int C, int in_pitch, int Ho, int Wo, int out_pitch, int ksize, int fp16) {
     const int vc = C >> 3;
     const size_t total = static_cast<size_t>(B) * Ho * Wo * vc;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -78,7 +76,7 @@ __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat
                 if (ix >= W) break;
                 const uint4 x = __ldg(reinterpret_cast<const uint4*>(
                     in + (static_cast<size_t>(b * H + iy) * W + ix) * in_pitch + v * 8));
-                m = first ? x : max8(m, x);
+                m = first ? x : max8(m, x, fp16);
                 first = false;
             }
         }
@@ -89,7 +87,7 @@ __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat
 // ------------------------------------------------------------------------------------------ eSE
 // partial[b][split][c] = sum over the split's pixels (fixed order -> deterministic).
 __global__ void ese_pool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C,
-                                int pitch, int nsplit, int rows) {
+                                int pitch, int nsplit, int rows, int fp16) {
     extern __shared__ float red[];  // [rows][C]
     const int vc = C >> 3;
     const int b = blockIdx.y, split = blockIdx.x;
@@ -101,7 +99,7 @@ __global__ void ese_pool_kernel(const __nv_bfloat16* __restrict__ x, float* __re
         for (int p = p0 + r; p < p1; p += rows) {
             const uint4 u =
                 __ldg(reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * HW + p) * pitch + v * 8));
-            const float2 a = unpack2(u.x), c = unpack2(u.y), d = unpack2(u.z), e = unpack2(u.w);
+            const float2 a = unpack2_act(u.x, fp16), c = unpack2_act(u.y, fp16), d = unpack2_act(u.z, fp16), e = unpack2_act(u.w, fp16);
             acc[0] += a.x; acc[1] += a.y; acc[2] += c.x; acc[3] += c.y;
             acc[4] += d.x; acc[5] += d.y; acc[6] += e.x; acc[7] += e.y;
         }
@@ -168,7 +166,7 @@ __global__ void ese_fc_kernel(const float* __restrict__ partial, const float* __
 // out = bf16(x * gate[b][c] (+ identity))
 __global__ void ese_scale_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gate,
                                  const __nv_bfloat16* __restrict__ identity, __nv_bfloat16* __restrict__ out, int B, int HW,
-                                 int C, int x_pitch, int id_pitch, int out_pitch) {
+                                 int C, int x_pitch, int id_pitch, int out_pitch, int fp16) {
     const int vc = C >> 3;
     const size_t total = static_cast<size_t>(B) * HW * vc;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -181,31 +179,35 @@ __global__ void ese_scale_kernel(const __nv_bfloat16* __restrict__ x, const floa
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * C + v * 8 + 4));
         float f[8];
         float2 t;
-        t = unpack2(u.x); f[0] = t.x * g0.x; f[1] = t.y * g0.y;
-        t = unpack2(u.y); f[2] = t.x * g0.z; f[3] = t.y * g0.w;
-        t = unpack2(u.z); f[4] = t.x * g1.x; f[5] = t.y * g1.y;
-        t = unpack2(u.w); f[6] = t.x * g1.z; f[7] = t.y * g1.w;
+        t = unpack2_act(u.x, fp16); f[0] = t.x * g0.x; f[1] = t.y * g0.y;
+        t = unpack2_act(u.y, fp16); f[2] = t.x * g0.z; f[3] = t.y * g0.w;
+        t = unpack2_act(u.z, fp16); f[4] = t.x * g1.x; f[5] = t.y * g1.y;
+        t = unpack2_act(u.w, fp16); f[6] = t.x * g1.z; f[7] = t.y * g1.w;
         if (identity != nullptr) {
             const uint4 q = __ldg(reinterpret_cast<const uint4*>(identity + pix * id_pitch + v * 8));
-            t = unpack2(q.x); f[0] += t.x; f[1] += t.y;
-            t = unpack2(q.y); f[2] += t.x; f[3] += t.y;
-            t = unpack2(q.z); f[4] += t.x; f[5] += t.y;
-            t = unpack2(q.w); f[6] += t.x; f[7] += t.y;
+            t = unpack2_act(q.x, fp16); f[0] += t.x; f[1] += t.y;
+            t = unpack2_act(q.y, fp16); f[2] += t.x; f[3] += t.y;
+            t = unpack2_act(q.z, fp16); f[4] += t.x; f[5] += t.y;
+            t = unpack2_act(q.w, fp16); f[6] += t.x; f[7] += t.y;
         }
         uint4 o;
-        o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
+        o.x = pack2_act(f[0], f[1], fp16); o.y = pack2_act(f[2], f[3], fp16); o.z = pack2_act(f[4], f[5], fp16);
+        o.w = pack2_act(f[6], f[7], fp16);
         *reinterpret_cast<uint4*>(out + pix * out_pitch + v * 8) = o;
     }
 }
 
+// relu on packed 16-bit floats: a set sign bit (negative, -0) -> +0; identical for bf16 and fp16
 __global__ void relu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t nvec) {
-    const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + i);
-        __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+        uint32_t* p = reinterpret_cast<uint32_t*>(&u);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) p[j] = __hmax2(p[j], z);
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t neg = p[j] & 0x80008000u;             // sign bits of the two halves
+            p[j] &= ~(((neg >> 15) * 0xFFFFu));                   // 0x8000 -> 0xFFFF mask per half
+        }
         reinterpret_cast<uint4*>(out)[i] = u;
     }
 }
@@ -220,25 +222,25 @@ inline int grid_for(size_t total, int block, int num_sms) {
 
 cudaError_t launch_preprocess(const void* src, int src_is_u8, const int* d_sizes, int size_stride, __nv_bfloat16* dst,
                               int B, int Hs, int Ws, int Hp, int Wp, const float mean[3], const float std[3],
-                              cudaStream_t stream) {
+                              cudaStream_t stream, int fp16) {
     dim3 block(256), grid((Wp + 255) / 256, Hp, B);
     if (src_is_u8) {
         preprocess_kernel<uint8_t><<<grid, block, 0, stream>>>(static_cast<const uint8_t*>(src), d_sizes, dst, B, Hs,
                                                                Ws, Hp, Wp, size_stride, mean[0], mean[1], mean[2], std[0],
-                                                               std[1], std[2]);
+                                                               std[1], std[2], fp16);
     } else {
         preprocess_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(src), d_sizes, dst, B, Hs, Ws,
                                                              Hp, Wp, size_stride, mean[0], mean[1], mean[2], std[0], std[1],
-                                                             std[2]);
+                                                             std[2], fp16);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_maxpool(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, int in_pitch,
-                           int Ho, int Wo, int out_pitch, int ksize, int num_sms, cudaStream_t stream) {
+                           int Ho, int Wo, int out_pitch, int ksize, int num_sms, cudaStream_t stream, int fp16) {
     const size_t total = static_cast<size_t>(B) * Ho * Wo * (C / 8);
     maxpool_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, out, B, H, W, C, in_pitch, Ho, Wo, out_pitch,
-                                                                    ksize);
+                                                                    ksize, fp16);
     return cudaGetLastError();
 }
 
@@ -251,13 +253,13 @@ int ese_nsplit(int HW) {
 
 cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, const float* fc_b,
                        const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out, int out_pitch, float* partial,
-                       float* gate, int B, int HW, int C, int num_sms, cudaStream_t stream) {
+                       float* gate, int B, int HW, int C, int num_sms, cudaStream_t stream, int fp16) {
     const int vc = C / 8;
     int rows = 256 / vc;
     if (rows < 1) rows = 1;
     const int nsplit = ese_nsplit(HW);
     ese_pool_kernel<<<dim3(nsplit, B), vc * rows, static_cast<size_t>(rows) * C * sizeof(float), stream>>>(
-        x, partial, HW, C, x_pitch, nsplit, rows);
+        x, partial, HW, C, x_pitch, nsplit, rows, fp16);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ese_fc_kernel<<<dim3((C + 7) / 8, B), 256, C * sizeof(float), stream>>>(partial, fc_w, fc_b, gate, C, nsplit,
@@ -266,7 +268,7 @@ cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, c
     if (e != cudaSuccess) return e;
     const size_t total = static_cast<size_t>(B) * HW * vc;
     ese_scale_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
-                                                                      id_pitch, out_pitch);
+                                                                      id_pitch, out_pitch, fp16);
     return cudaGetLastError();
 }
 
@@ -274,7 +276,7 @@ cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, c
 cudaError_t launch_ese_fused(const __nv_bfloat16* x, int x_pitch, const float* tile_partial, int T, const float* fc_w,
                              const float* fc_b, const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out,
                              int out_pitch, float* sums, float* gate, int B, int HW, int C, int num_sms,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int fp16) {
     ese_reduce_kernel<<<dim3((C + 63) / 64, B), 256, 0, stream>>>(tile_partial, sums, T, C, C);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -284,7 +286,7 @@ cudaError_t launch_ese_fused(const __nv_bfloat16* x, int x_pitch, const float* t
     if (e != cudaSuccess) return e;
     const size_t total = static_cast<size_t>(B) * HW * (C / 8);
     ese_scale_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
-                                                                      id_pitch, out_pitch);
+                                                                      id_pitch, out_pitch, fp16);
     return cudaGetLastError();
 }
 

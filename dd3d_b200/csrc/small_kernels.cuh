@@ -7,32 +7,33 @@
 namespace dd3d {
 
 // images: [B][3][Hs][Ws] uint8 or fp32 (each image top-left aligned, valid size sizes[b] = (h, w));
+// All 16-bit activation buffers are bf16 or fp16 (trailing `fp16` flag, act16.cuh); typed __nv_bfloat16* either way.
 // dst: [B][Hp][Wp][4] bf16, zero outside the valid region (pad AFTER normalisation, image_list.py:124-148).
 cudaError_t launch_preprocess(const void* src, int src_is_u8, const int* d_sizes, int size_stride, __nv_bfloat16* dst,
                               int B, int Hs, int Ws, int Hp, int Wp, const float mean[3], const float std[3],
-                              cudaStream_t stream);
+                              cudaStream_t stream, int fp16 = 0);
 
 // Stem conv (Cin = 3) on tensor cores (stem_tc.cu).  in: bf16 [B][H][W][4]; w: bf16 [cout][stem_tc_kpad(ksize)] with
 // k = (ky*ksize + kx)*4 + c (zero padded); out NHWC bf16 with `out_pitch` channels per pixel.
 int stem_tc_kpad(int ksize);
 cudaError_t launch_stem_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const float* scale, const float* bias,
                            __nv_bfloat16* out, int B, int H, int W, int ksize, int stride, int cout, int out_pitch,
-                           int num_sms, cudaStream_t stream);
+                           int num_sms, cudaStream_t stream, int fp16 = 0);
 
 cudaError_t launch_maxpool(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, int in_pitch,
-                           int Ho, int Wo, int out_pitch, int ksize, int num_sms, cudaStream_t stream);
+                           int Ho, int Wo, int out_pitch, int ksize, int num_sms, cudaStream_t stream, int fp16 = 0);
 
 int ese_nsplit(int HW);
 // partial: [B][ese_nsplit(HW)][C] fp32 scratch, gate: [B][C] fp32 scratch.
 cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, const float* fc_b,
                        const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out, int out_pitch, float* partial,
-                       float* gate, int B, int HW, int C, int num_sms, cudaStream_t stream);
+                       float* gate, int B, int HW, int C, int num_sms, cudaStream_t stream, int fp16 = 0);
 
 // tile_partial: [B][T][C] fp32 rows written by the concat-conv epilogue (T = 4 * tiles per image); sums: [B][C] scratch.
 cudaError_t launch_ese_fused(const __nv_bfloat16* x, int x_pitch, const float* tile_partial, int T, const float* fc_w,
                              const float* fc_b, const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out,
                              int out_pitch, float* sums, float* gate, int B, int HW, int C, int num_sms,
-                             cudaStream_t stream);
+                             cudaStream_t stream, int fp16 = 0);
 
 cudaError_t launch_relu(const __nv_bfloat16* x, __nv_bfloat16* out, size_t n_elems, int num_sms, cudaStream_t stream);
 

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 
+#include "act16.cuh"
 #include "ptx.cuh"
 #include "small_kernels.cuh"
 
@@ -36,7 +37,7 @@ template <int KS, int STRIDE, int COUT>
 __global__ void __launch_bounds__(160) stem_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ w,
                                                       const float* __restrict__ scale, const float* __restrict__ bias,
                                                       __nv_bfloat16* __restrict__ out, int B, int H, int W, int Ho, int Wo,
-                                                      int out_pitch, int tiles_x, int tiles_y) {
+                                                      int out_pitch, int tiles_x, int tiles_y, int fp16) {
     constexpr int PAD = (KS - 1) / 2;
     constexpr int K = KS * KS * 4;            // 36 / 196
     constexpr int KB = (K + 63) / 64;         // 64-element k-blocks: 1 / 4
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(160) stem_tc_kernel(const __nv_bfloat16* __res
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    const uint32_t idesc = ptx::make_idesc_bf16(128, COUT);
+    const uint32_t idesc = ptx::make_idesc_f16(128, COUT, fp16);
     constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t a_lo = (ptx::smem_u32(sA) >> 4) | (1u << 16);
     const uint32_t b_lo = (ptx::smem_u32(sB) >> 4) | (1u << 16);
@@ -155,8 +156,7 @@ __global__ void __launch_bounds__(160) stem_tc_kernel(const __nv_bfloat16* __res
                             const float y0 = fmaxf(fmaf(__uint_as_float(v[i + 2 * j]), __ldg(scale + n), __ldg(bias + n)), 0.f);
                             const float y1 =
                                 fmaxf(fmaf(__uint_as_float(v[i + 2 * j + 1]), __ldg(scale + n + 1), __ldg(bias + n + 1)), 0.f);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(y0, y1);
-                            o[j] = *reinterpret_cast<uint32_t*>(&p2);
+                            o[j] = pack2_act(y0, y1, fp16);
                         }
                         *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(o[0], o[1], o[2], o[3]);
                     }
@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(160) stem_tc_kernel(const __nv_bfloat16* __res
 
 template <int KS, int STRIDE, int COUT>
 cudaError_t launch_one(const __nv_bfloat16* in, const __nv_bfloat16* w, const float* scale, const float* bias,
-                       __nv_bfloat16* out, int B, int H, int W, int out_pitch, int num_sms, cudaStream_t stream) {
+                       __nv_bfloat16* out, int B, int H, int W, int out_pitch, int num_sms, cudaStream_t stream,
+                       int fp16) {
     constexpr int PAD = (KS - 1) / 2;
     constexpr int KB = (KS * KS * 4 + 63) / 64;
     const int Ho = (H + 2 * PAD - KS) / STRIDE + 1, Wo = (W + 2 * PAD - KS) / STRIDE + 1;
@@ -204,7 +205,7 @@ cudaError_t launch_one(const __nv_bfloat16* in, const __nv_bfloat16* w, const fl
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, stem_tc_kernel<KS, STRIDE, COUT>, in, w, scale, bias, out, B, H, W, Ho, Wo, out_pitch,
-                              tiles_x, tiles_y);
+                              tiles_x, tiles_y, fp16);
 }
 
 }  // namespace
@@ -214,11 +215,11 @@ int stem_tc_kpad(int ksize) { return (ksize * ksize * 4 + 63) / 64 * 64; }
 // in: bf16 [B][H][W][4]; w: bf16 [cout][stem_tc_kpad(ksize)] with k = (ky*ksize + kx)*4 + c; out: NHWC bf16.
 cudaError_t launch_stem_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const float* scale, const float* bias,
                            __nv_bfloat16* out, int B, int H, int W, int ksize, int stride, int cout, int out_pitch,
-                           int num_sms, cudaStream_t stream) {
+                           int num_sms, cudaStream_t stream, int fp16) {
     if (ksize == 7 && stride == 1 && cout == 16)
-        return launch_one<7, 1, 16>(in, w, scale, bias, out, B, H, W, out_pitch, num_sms, stream);
+        return launch_one<7, 1, 16>(in, w, scale, bias, out, B, H, W, out_pitch, num_sms, stream, fp16);
     if (ksize == 3 && stride == 2 && cout == 64)
-        return launch_one<3, 2, 64>(in, w, scale, bias, out, B, H, W, out_pitch, num_sms, stream);
+        return launch_one<3, 2, 64>(in, w, scale, bias, out, B, H, W, out_pitch, num_sms, stream, fp16);
     return cudaErrorInvalidValue;
 }
 

@@ -13,6 +13,7 @@ MAX_CLASSES = 16
 NUM_LEVELS = 5
 ARCH_DLA34, ARCH_V2_99 = 0, 1
 IMG_U8, IMG_F32 = 0, 1
+ACT_BF16, ACT_FP16 = 0, 1
 DET_WORDS = 24  # sizeof(dd3d_det) / 4
 
 
@@ -37,6 +38,7 @@ class ModelDesc(C.Structure):
         ("canonical_box3d_sizes", C.c_float * (MAX_CLASSES * 3)),
         ("out_cap", C.c_int32),
         ("nuscenes_heads", C.c_int32),
+        ("act_dtype", C.c_int32),
     ]
 
 
@@ -65,6 +67,7 @@ SIGNATURES = {
     "dd3d_overflow_flags": (_I, [_P, _P, C.POINTER(C.c_int32)]),
     "dd3d_set_option": (_I, [_P, C.c_char_p, _I]),
     "dd3d_launches_per_forward": (_I, [_P]),
+    "dd3d_num_ops": (_I, [_P]),
     "dd3d_get_profile": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                C.POINTER(C.c_int32)]),
     "dd3d_get_op_times": (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_double), _I]),
@@ -146,7 +149,18 @@ def desc_from_cfg(cfg, out_cap=None):
     d.out_cap = out_cap
     from .arch import is_nuscenes_arch
     d.nuscenes_heads = int(is_nuscenes_arch(cfg))
+    d.act_dtype = act_dtype_of(cfg)
     return d
+
+
+def act_dtype_of(cfg):
+    """cfg.B200.ACT_DTYPE ("bf16" default | "fp16"): the engine's 16-bit storage type; an engine-side key that reference
+    configs do not carry (absent -> bf16)."""
+    node = cfg.get("B200") if hasattr(cfg, "get") else getattr(cfg, "B200", None)
+    name = str((node or {}).get("ACT_DTYPE", "bf16")).lower()
+    if name not in ("bf16", "fp16"):
+        raise ValueError(f"B200.ACT_DTYPE must be 'bf16' or 'fp16', got {name!r}")
+    return ACT_FP16 if name == "fp16" else ACT_BF16
 
 
 def check(status, handle=None):

@@ -133,8 +133,9 @@ class DD3DB200(nn.Module):
         key = (B, Hs, Ws)
         if self._plan_key != key:
             L = _lib.load()
+            handle = self._engine()  # raises (no CPU path / weights not loaded) before any CUDA call
             with torch.cuda.device(self._device):
-                _lib.check(L.dd3d_plan(self._engine(), B, Hs, Ws, None, 0), self._handle)
+                _lib.check(L.dd3d_plan(handle, B, Hs, Ws, None, 0), self._handle)
             self._plan_key = key
             self._host_bufs = None
 
@@ -386,11 +387,10 @@ class DD3DB200(nn.Module):
         dims = (C.c_int32 * 6)()
         _lib.check(L.dd3d_get_tensor(self._handle, name.encode(), C.byref(ptr), C.byref(dims)), self._handle)
         B, H, W, Cc, pitch, eb = list(dims)
-        dtype = torch.bfloat16 if eb == 2 else torch.float32
         # wrap device memory without copying through the CUDA array interface
         t = torch.as_tensor(_DevArray(ptr.value, (B, H, W, pitch), "<f4" if eb == 4 else "<i2"), device=self._device)
         if eb == 2:
-            t = t.view(torch.bfloat16)
+            t = t.view(torch.float16 if self._desc.act_dtype == _lib.ACT_FP16 else torch.bfloat16)
         return t[..., :Cc]
 
     PROFILE_CATEGORIES = ("preprocess", "stem_conv", "conv_igemm", "maxpool", "ese", "relu", "decode", "nms")

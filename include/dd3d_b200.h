@@ -37,6 +37,10 @@ enum dd3d_status {
 
 enum dd3d_arch { DD3D_ARCH_DLA34 = 0, DD3D_ARCH_V2_99 = 1 };
 enum dd3d_image_dtype { DD3D_IMG_U8 = 0, DD3D_IMG_F32 = 1 };
+/* 16-bit storage type of activations and conv weights (accumulation, BN affine, head maps, decode and NMS are fp32
+ * either way).  bf16 is the default; fp16 is the reference's mixed-precision type (amp.autocast, scripts/train.py:121;
+ * BASELINE.json configs[4]) -- 3 more mantissa bits, range +-65504. */
+enum dd3d_act_dtype { DD3D_ACT_BF16 = 0, DD3D_ACT_FP16 = 1 };
 
 #define DD3D_MAX_CLASSES 16
 #define DD3D_NUM_LEVELS 5
@@ -63,6 +67,7 @@ typedef struct dd3d_model_desc {
     int32_t out_cap;        /* detection slots per image in the output buffer (>= post_nms_topk; ties may exceed it) */
     int32_t nuscenes_heads; /* MODEL.META_ARCHITECTURE == NuscenesDD3D: attr_logits (3) + speed (1, relu) predictor convs
                              * on the cls tower (nuscenes_dd3d.py:311-312,380-383) */
+    int32_t act_dtype;      /* dd3d_act_dtype */
 } dd3d_model_desc;
 
 /* One detection = the fields the reference returns in Instances (fcos2d.py:331-335,263; fcos3d.py:398-399). */
@@ -139,12 +144,14 @@ int dd3d_wait_host(dd3d_handle h, int slot);
  * out_cap detections survived.  Reads a device word (synchronises `stream`). */
 int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags);
 /* Runtime switches the reference's callers toggle on the meta-arch: "do_postprocess" (postprocess_in_inference,
- * scripts/train.py:206-209, test_time_augmentation.py:107), "do_nms" (core.py:134), and "profile" (see
- * dd3d_get_profile). */
+ * scripts/train.py:206-209, test_time_augmentation.py:107), "do_nms" (core.py:134), "profile" (see
+ * dd3d_get_profile), and "workspace_fill" (0..255: dd3d_plan fills the whole workspace with that byte first, -1 = off;
+ * the poison test of tests/test_determinism_gpu.py: results must not depend on what the arena held). */
 int dd3d_set_option(dd3d_handle h, const char* name, int value);
 /* Process-wide kernel-selection policy for plans / operator calls made afterwards (tests, A/B measurements):
  * "cta2" = 0 single-CTA conv kernel everywhere, 1 CTA pairs (tcgen05.mma.cta_group::2) wherever legal, 2 auto (default:
- * pairs for block_n >= 160 and >= 296 tiles), -1 back to the DD3D_CONV_CTA2 environment setting. */
+ * pairs for block_n >= 160 and >= 296 tiles), -1 back to the DD3D_CONV_CTA2 environment setting.
+ * "op_fp16" = 1: the dd3d_op_* entry points below treat their 16-bit buffers as fp16 (default 0: bf16). */
 int dd3d_set_conv_policy(const char* name, int value);
 /* Number of kernel launches one dd3d_forward enqueues (for the bench's gpu_launches claim). */
 int dd3d_launches_per_forward(dd3d_handle h);
@@ -185,8 +192,12 @@ int dd3d_forward_resized(dd3d_handle h, const uint8_t* d_raw, int raw_h, int raw
 /* name: "p0".."p4" (FPN outputs, bf16 NHWC), "cls0".."cls4", "box0".."box4", "b3d0".."b3d4" (fp32 NHWC head maps),
  * "input" (bf16 [B][Hp][Wp][4]).  Returns the device pointer and fills dims = {B, H, W, C, pitch, elem_bytes}. */
 int dd3d_get_tensor(dd3d_handle h, const char* name, void** d_ptr, int32_t dims[6]);
+/* Also "op<i>" / "op<i>:<seg>": the bf16 NHWC output view of engine op i in launch order (segment seg of a multi-level
+ * tower conv), 0 <= i < dd3d_num_ops; fp32 predictor outputs are the "cls"/"box"/"b3d" maps above. */
+int dd3d_num_ops(dd3d_handle h);
 
 /* ---- single operators (same kernels the engine launches; used by the kernel-level parity tests) ----------- */
+/* The 16-bit element type of the operator entry points is process-wide: dd3d_set_conv_policy("op_fp16", 0 | 1). */
 /* dd3d_op_stem_conv: Cin=3 stem conv on tensor cores; d_in4 = bf16 [B][H][W][4] (dd3d_op_preprocess output), d_w =
  * bf16 [cout][kpad] with k = (ky*ksize + kx)*4 + c, kpad = ksize*ksize*4 rounded up to 64; (ksize, stride, cout) in
  * {(7,1,16), (3,2,64)}. */

@@ -16,9 +16,10 @@ the reference's OWN modules executed in the build container under oracle/ref_sta
 runs produced (tests/golden/*.npz, written by oracle/gen_golden.py).  The third-party pieces themselves remain
 "parity unpinned" upstream (no pinned versions in the reference's Dockerfile) -- see DESIGN.md.
 
-``emulate_bf16=True`` reproduces the B200 engine's storage precision: conv weights and every stored
-activation are rounded to bf16 at the points where the engine stores bf16 (after each conv epilogue, after
-eSE scaling, after preprocessing); accumulation, BN affine, predictors' outputs, decode and NMS stay fp32.
+``emulate="bf16" | "fp16"`` (``emulate_bf16=True``) reproduces the B200 engine's storage precision: conv weights
+and every stored activation are rounded to that 16-bit type at the points where the engine stores it (after each conv
+epilogue, after eSE scaling, after preprocessing); accumulation, BN affine, predictors' outputs, decode and NMS stay
+fp32.  ``threads=1`` makes that emulation reproducible across processes.
 """
 import math
 
@@ -30,16 +31,22 @@ EPS = 1e-7
 BN_EPS = 1e-5
 
 
-def _bf16(x):
-    return x.to(torch.bfloat16).to(torch.float32)
+_EMU_DTYPES = {"bf16": torch.bfloat16, "fp16": torch.float16}
 
 
 class DD3DOracle:
-    def __init__(self, cfg, state_dict, emulate_bf16=False):
+    def __init__(self, cfg, state_dict, emulate_bf16=False, emulate=None, threads=None):
+        """emulate: None (pure fp32 = the reference), "bf16" or "fp16" (storage emulation of the engine's act_dtype;
+        emulate_bf16=True is the older spelling of emulate="bf16").  threads: run forward() with this many intra-op
+        threads (1 = accumulation order independent of the host's core count, so the storage emulation -- which amplifies
+        1-ulp fp32 differences into 16-bit rounding flips -- reproduces bit for bit across processes and boxes)."""
         self.cfg = cfg
         self.sd = {k: v.detach().to(torch.float32).cpu() if v.is_floating_point() else v.detach().cpu()
                    for k, v in state_dict.items()}
-        self.emu = emulate_bf16
+        self.emu = emulate if emulate is not None else ("bf16" if emulate_bf16 else None)
+        if self.emu is not None and self.emu not in _EMU_DTYPES:
+            raise ValueError(f"emulate must be None, 'bf16' or 'fp16', got {self.emu!r}")
+        self.threads = threads
         self.arch = "dla34" if cfg.FE.BUILDER == "build_fcos_dla_fpn_backbone_p67" else "v2_99"
         self.num_classes = cfg.DD3D.NUM_CLASSES
         if self.arch == "dla34":
@@ -55,7 +62,7 @@ class DD3DOracle:
     # primitives
     # ------------------------------------------------------------------------------------------
     def _q(self, x):
-        return _bf16(x) if self.emu else x
+        return x.to(_EMU_DTYPES[self.emu]).to(torch.float32) if self.emu else x
 
     def _bn_affine(self, prefix):
         """FrozenBatchNorm2d / eval BatchNorm2d -> (scale, bias); detectron2 FrozenBatchNorm2d, eps=1e-5."""
@@ -71,7 +78,7 @@ class DD3DOracle:
         w = sd[(wkey or prefix) + ".weight"]
         k = w.shape[-1]
         if self.emu:
-            w = _bf16(w)
+            w = self._q(w)
         y = F.conv2d(x, w, None, stride, (k - 1) // 2)
         cout = w.shape[0]
         scale = torch.ones(cout)
@@ -354,6 +361,16 @@ class DD3DOracle:
 
     @torch.no_grad()
     def forward(self, batched_inputs, return_intermediates=False, do_postprocess=True):
+        if self.threads is None:
+            return self._forward(batched_inputs, return_intermediates, do_postprocess)
+        prev = torch.get_num_threads()
+        torch.set_num_threads(int(self.threads))
+        try:
+            return self._forward(batched_inputs, return_intermediates, do_postprocess)
+        finally:
+            torch.set_num_threads(prev)
+
+    def _forward(self, batched_inputs, return_intermediates=False, do_postprocess=True):
         batch, sizes, K = self.preprocess(batched_inputs)
         feats = self.backbone(batch)
         maps = self.heads(feats)

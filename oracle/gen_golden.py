@@ -27,6 +27,12 @@ CASES = {
     "dla34": ("kitti_3d", 2, 192, 320, 721.5, (21, 34), 2.0),
     "v2_99": ("nuscenes", 2, 128, 192, 1266.4, (0, 0), 1.0),
 }
+# BASELINE.json shapes (configs[1] / configs[2]), one image each: the full-size parity cases of tests/test_parity_full_gpu.py
+FULL_CASES = {
+    # name: (arch, dataset, B, H, W, focal)
+    "dla34_full": ("dla34", "kitti_3d", 1, 384, 1280, 721.5),
+    "v2_99_full": ("v2_99", "nuscenes", 1, 900, 1600, 1266.4),
+}
 NUSC_CASE = ("v2_99", 1, 128, 192, 1266.4)  # NuscenesDD3D: backbone, samples (x 6 cameras), H, W, focal
 
 
@@ -101,7 +107,17 @@ def reference_sample_aggregate(dets, group_ids, poses, thr, max_dets):
     return [(o.orig_index, o.pred_boxes3d_global.quat, o.pred_boxes3d_global.tvec) for o in out]
 
 
+def case_cfg(name, **kw):
+    """cfg of a golden case: "dla34" / "v2_99" (small, ragged) or "dla34_full" / "v2_99_full" (BASELINE shapes)."""
+    if name in FULL_CASES:
+        return get_cfg(FULL_CASES[name][0], FULL_CASES[name][1], **kw)
+    return get_cfg(name, CASES[name][0], **kw)
+
+
 def case_inputs(arch):
+    if arch in FULL_CASES:
+        _, _, B, H, W, focal = FULL_CASES[arch]
+        return make_inputs(B, H, W, focal, with_size=True)
     ds, B, H, W, focal, (dh, dw), fac = CASES[arch]
     inputs = make_inputs(B, H, W, focal)
     if dh or dw:
@@ -144,11 +160,10 @@ def reference_bev_keep(det, pose_quat, pose_tvec, thr):
     return out.orig_index, rot
 
 
-def main():
-    out_dir = os.path.join(ROOT, "tests", "golden")
-    os.makedirs(out_dir, exist_ok=True)
-    for arch, (ds, *_rest) in CASES.items():
-        cfg = get_cfg(arch, ds)
+def gen_dd3d_goldens(names, out_dir):
+    """golden_<name>.npz: the reference's own DD3D.forward (fp32, CPU) on the seeded case."""
+    for arch in names:
+        cfg = case_cfg(arch)
         model = ref_standin.build_reference_model(cfg).eval()
         model.load_state_dict(make_state_dict(cfg))
         inputs = case_inputs(arch)
@@ -168,6 +183,15 @@ def main():
             })
             print(arch, "image", b, "detections", len(inst))
         np.savez_compressed(os.path.join(out_dir, f"golden_{arch}.npz"), **blob)
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    if "--full" in sys.argv:  # only the BASELINE-shape cases (a V2-99 900x1600 reference forward takes ~10 s here)
+        gen_dd3d_goldens(list(FULL_CASES), out_dir)
+        return
+    gen_dd3d_goldens(list(CASES) + list(FULL_CASES), out_dir)
 
     # NuscenesDD3D: the reference's own meta-arch on one 6-camera sample
     arch = NUSC_CASE[0]

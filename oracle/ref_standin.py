@@ -536,10 +536,24 @@ def matrix_to_quaternion(matrix):
 
 
 class Quaternion:
-    """Minimal pyquaternion.Quaternion (w, x, y, z) -- the subset tridet/structures/pose.py uses."""
-    def __init__(self, *args, matrix=None):
+    """Minimal pyquaternion.Quaternion (w, x, y, z) -- the subset tridet/structures/pose.py and
+    tridet/evaluators/kitti_3d_evaluator.py (convert_3d_box_to_kitti) use; semantics restated from pyquaternion 0.9.9
+    (axis-angle constructor normalises the axis; `axis` = vector part / its norm, zeros when the rotation is the identity;
+    `angle` = 2 * atan2(|vector|, scalar) wrapped to (-pi, pi])."""
+    def __init__(self, *args, matrix=None, axis=None, radians=None, angle=None):
         import numpy as np
-        if matrix is not None:
+        if axis is not None:
+            a = np.asarray(axis, dtype=np.float64)
+            m2 = float(np.dot(a, a))
+            if m2 == 0.0:
+                raise ZeroDivisionError("Provided rotation axis has no length")
+            if abs(1.0 - m2) > 1e-12:
+                a = a / np.sqrt(m2)
+            th = float(radians if radians is not None else angle) / 2.0
+            self.q = np.concatenate([[np.cos(th)], a * np.sin(th)])
+        elif len(args) == 4:
+            self.q = np.asarray(args, dtype=np.float64)
+        elif matrix is not None:
             m = np.asarray(matrix, dtype=np.float64)[:3, :3]
             q = matrix_to_quaternion(torch.tensor(m, dtype=torch.float64)[None])[0].numpy()
             if q[0] < 0:
@@ -559,6 +573,27 @@ class Quaternion:
     @property
     def rotation_matrix(self):
         return quaternion_to_matrix(torch.tensor(self.q)[None])[0].numpy()
+
+    def _unit(self):
+        import numpy as np
+        n = np.linalg.norm(self.q)
+        return self.q / n if n > 0 else self.q
+
+    @property
+    def axis(self):
+        import numpy as np
+        v = self._unit()[1:]
+        n = np.linalg.norm(v)
+        return np.zeros(3) if n < 1e-17 else v / n
+
+    @property
+    def angle(self):
+        import math
+        import numpy as np
+        u = self._unit()
+        th = 2.0 * math.atan2(float(np.linalg.norm(u[1:])), float(u[0]))
+        r = ((th + math.pi) % (2.0 * math.pi)) - math.pi
+        return math.pi if r == -math.pi else r
 
     @property
     def transformation_matrix(self):
@@ -933,3 +968,72 @@ def build_reference_model(cfg):
         return NuscenesDD3D(cfg)
     from tridet.modeling.dd3d.core import DD3D
     return DD3D(cfg)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Evaluator side (tridet/evaluators/kitti_3d_evaluator.py): the detectron2 / iopath names it imports, and the dataset
+# catalog it reads.  Only process() is exercised (the CPU half of the evaluator: per-detection conversion to KITTI
+# rows); evaluate() needs numba.cuda (rotate_iou.py selects a CUDA device at import), so that module is stubbed.
+# ------------------------------------------------------------------------------------------------------------------
+class BoxMode:
+    """detectron2.structures.BoxMode subset: the two modes the KITTI evaluator converts between."""
+    XYXY_ABS, XYWH_ABS = 0, 1
+
+    @staticmethod
+    def convert(box, from_mode, to_mode):
+        if from_mode == to_mode:
+            return box
+        x0, y0, a, b = [float(v) for v in box]
+        if from_mode == BoxMode.XYXY_ABS and to_mode == BoxMode.XYWH_ABS:
+            return type(box)([x0, y0, a - x0, b - y0]) if isinstance(box, (list, tuple)) else [x0, y0, a - x0, b - y0]
+        if from_mode == BoxMode.XYWH_ABS and to_mode == BoxMode.XYXY_ABS:
+            return type(box)([x0, y0, x0 + a, y0 + b]) if isinstance(box, (list, tuple)) else [x0, y0, x0 + a, y0 + b]
+        raise NotImplementedError((from_mode, to_mode))
+
+
+class _Catalog(dict):
+    def register(self, name, value):
+        self[name] = value
+
+    def get(self, name):  # DatasetCatalog: callable -> list[dict]; MetadataCatalog: metadata object
+        v = self[name]
+        return v() if callable(v) else v
+
+
+DatasetCatalog = _Catalog()
+MetadataCatalog = _Catalog()
+
+
+class DatasetEvaluator:
+    def reset(self):
+        pass
+
+    def process(self, inputs, outputs):
+        pass
+
+    def evaluate(self):
+        pass
+
+
+def install_evaluator_stubs():
+    install()
+    _mod("detectron2.data.catalog", DatasetCatalog=DatasetCatalog, MetadataCatalog=MetadataCatalog)
+    _mod("detectron2.evaluation")
+    _mod("detectron2.evaluation.evaluator", DatasetEvaluator=DatasetEvaluator)
+    _mod("detectron2.structures.boxes", BoxMode=BoxMode, Boxes=Boxes)
+
+    class _PathManager:
+        def mkdirs(self, path):
+            import os
+            os.makedirs(path, exist_ok=True)
+
+    _mod("iopath")
+    _mod("iopath.common")
+    _mod("iopath.common.file_io", PathManager=_PathManager)
+    import os
+    m = types.ModuleType("tridet.evaluators")
+    m.__path__ = [os.path.join(REFERENCE_ROOT, "tridet", "evaluators")]
+    m.__spec__ = importlib.machinery.ModuleSpec("tridet.evaluators", None, is_package=True)
+    sys.modules["tridet.evaluators"] = m
+    _mod("tridet.evaluators.rotate_iou", d3_box_overlap_kernel=None, rotate_iou_gpu_eval=None)
+    # detectron2.utils.comm.gather / synchronize are only reached from evaluate()

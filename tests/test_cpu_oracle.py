@@ -232,7 +232,7 @@ def test_cabi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name)
     import ctypes
-    assert ctypes.sizeof(lib.ModelDesc) == 4 * (2 + 3 + 3 + 1 + 1 + 3 + 1 + 2 + 1 + 1 + 1 + 1 + 48 + 1 + 1)
+    assert ctypes.sizeof(lib.ModelDesc) == 4 * (2 + 3 + 3 + 1 + 1 + 3 + 1 + 2 + 1 + 1 + 1 + 1 + 48 + 1 + 1 + 1)  # + act_dtype
     assert ctypes.sizeof(lib.TtaView) == 4 * (1 + 1 + 2 + 2 + 9 + 9)  # dd3d_tta_view
     assert lib.DET_WORDS * 4 == 96  # dd3d_det
 
