@@ -7,6 +7,7 @@
 // Runs after the 2-D NMS / top-k kernel on its <= out_cap survivors (already sorted by scores_3d) and, like the
 // reference, BEFORE detector_postprocess -- which this kernel then applies itself (scale, clip, drop empty).
 #include "detect.cuh"
+#include "device_once.cuh"
 
 #include <math.h>
 
@@ -537,12 +538,11 @@ cudaError_t launch_sample_aggregate(Det* dets, int32_t* counts, const float* K, 
     p.cap = cap;
     p.max_dets = max_dets;
     p.thr = thr;
-    static bool configured = false;
-    if (!configured) {
+    static uint64_t configured_devices = 0;
+    if (first_use_on_device(&configured_devices)) {
         const cudaError_t e = cudaFuncSetAttribute(sample_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(sizeof(GrpSmem)));
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     sample_nms_kernel<<<num_groups, kGrpThreads, sizeof(GrpSmem), stream>>>(p);
     sample_compact_kernel<<<B, kBevThreads, 0, stream>>>(p);

@@ -170,12 +170,27 @@ int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags) {
     });
 }
 
+int dd3d_copy_flags(dd3d_handle h, int32_t* d_dst, dd3d_stream stream) {
+    if (!d_dst) return DD3D_ERR_INVALID;
+    return guarded(h, [&](Engine& e) {
+        if (!e.plan.valid) throw EngineError(DD3D_ERR_STATE, "no plan");
+        cudaError_t c = cudaMemcpyAsync(d_dst, e.plan.decode.flags, 4, cudaMemcpyDeviceToDevice,
+                                        static_cast<cudaStream_t>(stream));
+        if (c != cudaSuccess) throw EngineError(DD3D_ERR_CUDA, cudaGetErrorString(c));
+    });
+}
+
 int dd3d_set_option(dd3d_handle h, const char* name, int value) {
     return guarded(h, [&](Engine& e) {
         const std::string n(name ? name : "");
         if (n == "do_postprocess") {
             e.opt_do_postprocess = value ? 1 : 0;
         } else if (n == "do_nms") {
+            // without NMS up to 5 * PRE_NMS_TOPK detections per image survive: refuse a buffer that would truncate them
+            if (!value && e.desc.out_cap < kLevels * e.desc.pre_nms_topk)
+                throw EngineError(DD3D_ERR_INVALID, "do_nms = 0 needs out_cap >= 5 * pre_nms_topk (" +
+                                                        std::to_string(kLevels * e.desc.pre_nms_topk) + "), engine has " +
+                                                        std::to_string(e.desc.out_cap) + ": recreate the engine");
             e.desc.do_nms = value ? 1 : 0;
         } else if (n == "profile") {
             e.opt_profile = value ? 1 : 0;

@@ -16,13 +16,16 @@
 // Halo variant (3x3, stride 1): the A operand of a 64-channel block is ONE box [18][10][64ch] (tile + halo); the nine
 // taps are descriptor views of it shifted by whole 128-byte pixel rows, so A is fetched once instead of nine times.
 //
-// Warp roles (224 threads, 1 CTA/SM, persistent over tiles); every role loop is warp-converged and only the issue
+// Warp roles (352 threads, 1 CTA/SM, persistent over tiles); every role loop is warp-converged and only the issue
 // instructions are predicated on elect.sync, which keeps TMA / UMMA operands in uniform registers:
 //   warp 0 : TMA producer of the activation tiles (generic) / of the weight tiles (halo)
-//   warp 6 : TMA producer of the weight tiles (generic) / of the halo patches (halo)
+//   warp 2 : TMA producer of the weight tiles (generic) / of the halo patches (halo)
 //   warp 1 : tcgen05.mma issuer (accumulators double-buffered in TMEM: 2 x block_n columns)
-//   warps 2..5 : epilogue (tcgen05.ld -> scale/bias/residual/ReLU -> bf16 -> swizzled smem -> TMA store, optional eSE
-//                pooling partial sums; or fp32 direct stores for the predictor heads)
+//   warps 3..10 : epilogue, TWO warps per TMEM lane quarter (a warp reads lanes 32 * (warp % 4) ..): the pair splits every
+//                64-column chunk into its two 32-column steps (tcgen05.ld -> scale/bias/residual/ReLU -> bf16/fp16 ->
+//                swizzled smem -> TMA store, optional eSE pooling partial sums; or fp32 direct stores for the predictor
+//                heads).  With one epilogue warp per scheduler every dependent instruction paid its full latency and the
+//                small-K layers (stem, OSA2, 1x1 concats / laterals) were epilogue-bound (profiles/r02_epilogue.md).
 // Launched with programmatic dependent launch: the prologue overlaps the previous kernel's tail.
 #include "conv_igemm.cuh"
 
@@ -34,6 +37,7 @@
 #include <string>
 
 #include "act16.cuh"
+#include "device_once.cuh"
 #include "ptx.cuh"
 
 namespace dd3d {
@@ -50,6 +54,8 @@ constexpr int kHaloPW = kHaloTw + 2, kHaloPH = kHaloTh + 2;
 constexpr int kHaloABytes = (kHaloPW * kHaloPH * 128 + 1023) / 1024 * 1024;  // 23552
 constexpr int kHaloAStages = 3;
 constexpr int kBarBytes = 512;
+constexpr int kSbBytes = 2 * 256 * 4;  // staged (scale, bias) vectors of the current (segment, n-block)
+constexpr int kFirstEpiWarp = 3, kEpiWarps = 8, kEpiThreads = kEpiWarps * 32;
 
 struct TileCoord {
     int seg, img, y0, x0, n_blk;
@@ -96,6 +102,78 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work, 
     return t;
 }
 
+// (a, b) -> packed 16-bit pair; MODE bit 0: ReLU fused into the conversion (cvt.rn.relu), bit 1: fp16 instead of bf16.
+template <int MODE>
+__device__ __forceinline__ uint32_t pack2_mode(float a, float b) {
+    uint32_t r;
+    if (MODE == 0) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    } else if (MODE == 1) {
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    } else if (MODE == 2) {
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    } else {
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    }
+    return r;
+}
+
+// One full 32-column epilogue step of the 16-bit output path: v = this thread's accumulator row (32 fp32 columns, already
+// loaded from TMEM), y = v * scale + bias (+ residual) -> (ReLU) -> bf16 / fp16 -> the thread's row of the 128B-swizzled
+// staging tile.  (scale, bias) come from shared memory as broadcast LDS.128; two sub-steps of 16 columns keep the live
+// register set small (168-register cap with 11 warps).  MODE as in pack2_mode; HAS_RES: rpre holds the 32 residual values.
+template <int MODE, bool HAS_RES>
+__device__ __forceinline__ void epi_fast_step(uint32_t (&v)[32], uint32_t ssc, uint32_t sbi, const uint4 (&rpre)[4],
+                                              uint32_t stag_row, int c16_0, int row7) {
+    float4 sc[4], bi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sc[i] = ptx::ld_shared_f4(ssc + 16 * i);
+        bi[i] = ptx::ld_shared_f4(sbi + 16 * i);
+    }
+    ptx::tmem_ld_wait(v);  // the LDS above are in flight together with the TMEM load
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        float y[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            y[4 * i + 0] = fmaf(__uint_as_float(v[16 * hh + 4 * i + 0]), sc[i].x, bi[i].x);
+            y[4 * i + 1] = fmaf(__uint_as_float(v[16 * hh + 4 * i + 1]), sc[i].y, bi[i].y);
+            y[4 * i + 2] = fmaf(__uint_as_float(v[16 * hh + 4 * i + 2]), sc[i].z, bi[i].z);
+            y[4 * i + 3] = fmaf(__uint_as_float(v[16 * hh + 4 * i + 3]), sc[i].w, bi[i].w);
+        }
+        if (hh == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sc[i] = ptx::ld_shared_f4(ssc + 64 + 16 * i);
+                bi[i] = ptx::ld_shared_f4(sbi + 64 + 16 * i);
+            }
+        }
+        if (HAS_RES) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rpre[2 * hh + i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = (MODE & 2) ? unpack2_f16(rb[j]) : unpack2_bf16(rb[j]);
+                    y[8 * i + 2 * j] += f.x;
+                    y[8 * i + 2 * j + 1] += f.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            uint4 o;
+            o.x = pack2_mode<MODE>(y[8 * i + 0], y[8 * i + 1]);
+            o.y = pack2_mode<MODE>(y[8 * i + 2], y[8 * i + 3]);
+            o.z = pack2_mode<MODE>(y[8 * i + 4], y[8 * i + 5]);
+            o.w = pack2_mode<MODE>(y[8 * i + 6], y[8 * i + 7]);
+            const int c16 = c16_0 + 2 * hh + i;  // 16-byte chunk within the 128-byte row
+            ptx::st_shared_v4(stag_row + ((c16 ^ row7) << 4), o);
+        }
+    }
+}
+
 // elect.sync: exactly one lane of the (converged) warp gets true.  Keeping the role loops warp-converged and
 // predicating only the issue instructions on the elected lane lets the compiler keep TMA / UMMA operands in
 // uniform registers; a `lane == 0` branch instead forces an R2UR + election loop around every UTMALDG / UTCHMMA
@@ -136,6 +214,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     uint64_t* afull_bar = tempty_bar + 2;          // [kHaloAStages]
     uint64_t* aempty_bar = afull_bar + kHaloAStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + kHaloAStages);
+    // shared-window addresses of the epilogue's staging tiles and of the staged folded-BN vectors (explicit LDS / STS)
+    const uint32_t staging_u32 = ptx::smem_u32(staging);
+    const uint32_t s_scale_u32 = ptx::smem_u32(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [256] fp32 scale
+    const uint32_t s_bias_u32 = s_scale_u32 + 256 * 4;                                          // [256] fp32 bias
 
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
     const int lane = threadIdx.x & 31;
@@ -147,12 +229,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             if (p.out_mode == 0) ptx::prefetch_tensormap(&p.seg[s].out_map);
         }
         for (int i = 0; i < p.num_stages; ++i) {
-            ptx::mbar_init(&full_bar[i], HALO ? 1 : 2);  // generic: A (warp 0) + B (warp 6) each arrive.expect_tx
+            ptx::mbar_init(&full_bar[i], HALO ? 1 : 2);  // generic: A (warp 0) + B (warp 2) each arrive.expect_tx
             ptx::mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], CTA2 ? 8 : 4);  // one arrival per epilogue warp (of both CTAs of a pair)
+            ptx::mbar_init(&tempty_bar[i], (CTA2 ? 2 : 1) * kEpiWarps);  // one arrival per epilogue warp (of both CTAs of a pair)
         }
         for (int i = 0; i < kHaloAStages; ++i) {
             ptx::mbar_init(&afull_bar[i], 1);
@@ -225,7 +307,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                     if (elect_one()) {
                         uint8_t* a_dst = smem + stage * stage_bytes;
-                        // the weight tile is armed + issued by warp 6; in a CTA pair the leader arms for both CTAs
+                        // the weight tile is armed + issued by warp 2; in a CTA pair the leader arms for both CTAs
                         if (!CTA2 || leader) ptx::mbar_expect_tx(&full_bar[stage], CTA2 ? 2 * kABytes : kABytes);
                         // stride 2: input (2*oy + r - 1, 2*ox + s - 1) in the parity-split view [B][H/2][2][W/2][wp*C..]
                         const int wp = (s == 1) ? 0 : 1;
@@ -256,9 +338,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                 }
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 2) {
         if (!HALO) {
-            // ------------------------------------------------------------ warp 6: weight-tile (B) producer (generic)
+            // ------------------------------------------------------------ warp 2: weight-tile (B) producer (generic)
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t b_bytes = p.block_n * 128;
@@ -285,7 +367,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                 }
             }
         } else {
-            // ------------------------------------------------------------ warp 6: halo A-patch producer: one box
+            // ------------------------------------------------------------ warp 2: halo A-patch producer: one box
             // [18][10][64 ch] (180 rows of 128 B, 128B-swizzled, zero-filled outside the image) per 64-channel block
             int as = 0;
             uint32_t aphase = 0;
@@ -332,7 +414,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         for (int work = w_first; work < w_total; work += w_step) {
             ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
             ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * p.chains * p.block_n;  // chain c lives at + c * block_n
+            const uint32_t d_tmem = tmem_base + acc * p.block_n;
             if (HALO) {
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(&afull_bar[as], aphase, 6);
@@ -391,12 +473,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                             if (k < ksteps) {  // channels beyond cin are zero padding: skip their K steps
                                 const uint64_t adesc = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2 * k);
                                 const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
-                                const int j = kb * (kBlockK / 16) + k;  // MMA index within the tile
-                                const int chain = j & (p.chains - 1);   // optional split-K accumulator chains
                                 if (CTA2) {
-                                    ptx::umma2_bf16(d_tmem + chain * p.block_n, adesc, bdesc, idesc, j >= p.chains ? 1u : 0u);
+                                    ptx::umma2_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                                 } else {
-                                    ptx::umma_bf16(d_tmem + chain * p.block_n, adesc, bdesc, idesc, j >= p.chains ? 1u : 0u);
+                                    ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                                 }
                             }
                         }
@@ -428,14 +508,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             }
         }
       }
-    } else {
-        // ---------------------------------------------------------------- epilogue (warps 2..5)
-        const int q = warp & 3;  // TMEM lane quarter accessible to this warp
+    } else if (warp >= kFirstEpiWarp) {
+        // ---------------------------------------------------------------- epilogue (warps 3..10)
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access (hardware: warp id % 4)
+        const int half = (warp - kFirstEpiWarp) >> 2;  // which 32-column step of every 64-column chunk this warp owns
         const int row = q * 32 + lane;
-        const bool store_leader = (threadIdx.x == 64);
+        const int et = static_cast<int>(threadIdx.x) - kFirstEpiWarp * 32;  // 0 .. kEpiThreads - 1
+        const bool store_leader = (et == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
         int sbuf = 0;
+        int sb_key = -1;  // (segment, n-block) whose folded-BN vectors are staged in s_scale / s_bias
         for (int work = w_first; work < w_total; work += w_step) {
             const TileCoord t = decode_tile<CTA2>(p, work, rank);
             const ConvSeg& g = p.seg[t.seg];
@@ -444,6 +527,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             const int oy = t.y0 + ly, ox = t.x0 + lx;
             const bool in_img = t.valid && (oy < g.H) && (ox < g.W);
             const int n_base = t.n_blk * p.block_n;
+
+            // bf16 output path: the per-channel (scale, bias) of this (segment, n-block) live in shared memory -- 16
+            // broadcast LDS.128 per 32-column step instead of 16 LDG.128 with their 64-bit address arithmetic.  All epilogue
+            // threads are past the last use of the previous vectors (the closing named barrier of the previous tile), and
+            // the opening named barrier of the first chunk below publishes the new ones.
+            if (p.out_mode == 0) {
+                const int key = t.seg * 8 + t.n_blk;
+                if (key != sb_key) {
+                    sb_key = key;
+                    if (et < p.block_n) {
+                        ptx::st_shared_f32(s_scale_u32 + et * 4, __ldg(g.scale + n_base + et));
+                        ptx::st_shared_f32(s_bias_u32 + et * 4, __ldg(g.bias + n_base + et));
+                    }
+                }
+            }
 
             const __nv_bfloat16* res_ptr = nullptr;
             if (g.residual != nullptr && in_img) {
@@ -455,13 +553,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             if (p.out_mode == 1 && in_img) {
                 f32_ptr = g.out_f32 + (static_cast<size_t>(t.img * g.H + oy) * g.W + ox) * g.out_pitch + n_base;
             }
-
-            ptx::mbar_wait(&tfull_bar[acc], acc_phase, 4);
-            ptx::tc_fence_after();
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.chains * p.block_n;
-
-            // residual (BasicBlock identity / FPN top-down map): fetched ONE 32-column step ahead, so the L2 / DRAM latency
-            // of this thread's row is paid once per tile instead of once per step (the FPN laterals were bound by it)
+            // residual (BasicBlock identity / FPN top-down map) of this warp's FIRST step, fetched before the accumulator
+            // wait; every later step's columns are fetched one step ahead (L2 / DRAM latency paid once per tile)
             uint4 rpre[4];
             auto load_res = [&](int col) {
 #pragma unroll
@@ -470,127 +563,130 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                                                         : make_uint4(0u, 0u, 0u, 0u);
                 }
             };
-            if (res_ptr != nullptr) load_res(0);
+            if (res_ptr != nullptr && half * 32 < p.block_n) load_res(half * 32);
+
+            ptx::mbar_wait(&tfull_bar[acc], acc_phase, 4);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
 
             for (int c0 = 0; c0 < p.block_n; c0 += 64) {
                 const int chunk_cols = min(64, p.block_n - c0);
                 uint8_t* stag = staging + sbuf * kStagingBytes;
+                const uint32_t stag_u32 = staging_u32 + sbuf * kStagingBytes;
                 if (p.out_mode == 0) {
                     // the TMA store that last read this staging buffer must have drained
                     if (store_leader) ptx::tma_store_wait_read<1>();
-                    ptx::named_bar_sync(1, 128);
+                    ptx::named_bar_sync(1, kEpiThreads);
                 }
-                for (int h = 0; h < chunk_cols; h += 32) {
+                const int h = half * 32;  // this warp's step of the chunk
+                if (h < chunk_cols) {
                     const int cols = min(32, chunk_cols - h);
+                    const int n0 = n_base + c0 + h;  // absolute output channel of v[0]
                     uint32_t v[32];
                     if (cols == 32) {
                         ptx::tmem_ld32(t_addr + c0 + h, v);
                     } else {
                         ptx::tmem_ld16(t_addr + c0 + h, v);
                     }
-                    // fetch the BN affine of these columns while the TMEM load is in flight (both latencies used to be
-                    // paid back to back by the single epilogue warp of each scheduler: ncu, profiles/r01d_cta2_ab.md)
-                    const int n0 = n_base + c0 + h;  // absolute output channel of v[0]
-                    float4 sc[8], bi[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (4 * i < cols) {
-                            sc[i] = __ldg(reinterpret_cast<const float4*>(g.scale + n0 + 4 * i));
-                            bi[i] = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 4 * i));
-                        }
-                    }
-                    ptx::tmem_ld_wait();
-                    for (int ch = 1; ch < p.chains; ++ch) {  // add the other split-K chains (fp32)
-                        uint32_t w[32];
-                        if (cols == 32) {
-                            ptx::tmem_ld32(t_addr + ch * p.block_n + c0 + h, w);
+                    if (p.out_mode == 0 && cols == 32) {
+                        // ---- fast path: full 32-column step, bf16 / fp16 output through the staging tile
+                        const uint32_t ssc = s_scale_u32 + (c0 + h) * 4, sbi = s_bias_u32 + (c0 + h) * 4;
+                        const uint32_t stag_row = stag_u32 + row * 128;
+                        const int mode = (p.relu ? 1 : 0) | (p.fp16 ? 2 : 0);  // warp-uniform: one branch per step
+                        if (res_ptr != nullptr) {
+                            switch (mode) {
+                                case 0: epi_fast_step<0, true>(v, ssc, sbi, rpre, stag_row, h >> 3, row & 7); break;
+                                case 1: epi_fast_step<1, true>(v, ssc, sbi, rpre, stag_row, h >> 3, row & 7); break;
+                                case 2: epi_fast_step<2, true>(v, ssc, sbi, rpre, stag_row, h >> 3, row & 7); break;
+                                default: epi_fast_step<3, true>(v, ssc, sbi, rpre, stag_row, h >> 3, row & 7); break;
+                            }
+                            if (c0 + 64 + h < p.block_n) load_res(c0 + 64 + h);  // this warp's step of the next chunk
                         } else {
-                            ptx::tmem_ld16(t_addr + ch * p.block_n + c0 + h, w);
-                        }
-                        ptx::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i < cols) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
-                    }
-                    float y[32];
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        if (i < cols) {
-                            y[i + 0] = fmaf(__uint_as_float(v[i + 0]), sc[i >> 2].x, bi[i >> 2].x);
-                            y[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc[i >> 2].y, bi[i >> 2].y);
-                            y[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc[i >> 2].z, bi[i >> 2].z);
-                            y[i + 3] = fmaf(__uint_as_float(v[i + 3]), sc[i >> 2].w, bi[i >> 2].w);
-                        }
-                    }
-                    if (res_ptr != nullptr) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            if (i < cols) {
-                                const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rpre[i >> 3]);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 f = unpack2_act(rb[j], p.fp16);
-                                    y[i + 2 * j] += f.x;
-                                    y[i + 2 * j + 1] += f.y;
-                                }
+                            switch (mode) {
+                                case 0: epi_fast_step<0, false>(v, ssc, sbi, rpre, stag_row, h >> 3, row & 7); break;
+                                case 1: epi_fast_step<1, false>(v, ssc, sbi, rpre, stag_row, h >> 3, row & 7); break;
+                                case 2: epi_fast_step<2, false>(v, ssc, sbi, rpre, stag_row, h >> 3, row & 7); break;
+                                default: epi_fast_step<3, false>(v, ssc, sbi, rpre, stag_row, h >> 3, row & 7); break;
                             }
                         }
-                        if (c0 + h + 32 < p.block_n) load_res(c0 + h + 32);  // next step's columns, consumed next iteration
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.0f);
-                    }
-                    if (p.out_mode == 0) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            if (i < cols) {
-                                uint4 o;
-                                if (p.fp16) {  // warp-uniform
-                                    o.x = pack2_f16(y[i + 0], y[i + 1]);
-                                    o.y = pack2_f16(y[i + 2], y[i + 3]);
-                                    o.z = pack2_f16(y[i + 4], y[i + 5]);
-                                    o.w = pack2_f16(y[i + 6], y[i + 7]);
-                                } else {
-                                    o.x = pack2_bf16(y[i + 0], y[i + 1]);
-                                    o.y = pack2_bf16(y[i + 2], y[i + 3]);
-                                    o.z = pack2_bf16(y[i + 4], y[i + 5]);
-                                    o.w = pack2_bf16(y[i + 6], y[i + 7]);
-                                }
-                                const int c16 = (h + i) >> 3;  // 16-byte chunk within the 128-byte row
-                                *reinterpret_cast<uint4*>(stag + row * 128 + ((c16 ^ (row & 7)) << 4)) = o;
-                            }
-                        }
-                    } else if (f32_ptr != nullptr) {
+                    } else {
+                        // ---- general path: fp32 predictor outputs, 16-column tails
+                        ptx::tmem_ld_wait(v);
+                        float y[32];
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             if (i < cols) {
-                                float4 o = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
-                                if (g.lo != nullptr) {
-                                    const float4 lo = __ldg(reinterpret_cast<const float4*>(g.lo + n0 + i));
-                                    o.x = fmaxf(o.x, lo.x);
-                                    o.y = fmaxf(o.y, lo.y);
-                                    o.z = fmaxf(o.z, lo.z);
-                                    o.w = fmaxf(o.w, lo.w);
+                                const float4 sc = __ldg(reinterpret_cast<const float4*>(g.scale + n0 + i));
+                                const float4 bi = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+                                y[i + 0] = fmaf(__uint_as_float(v[i + 0]), sc.x, bi.x);
+                                y[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc.y, bi.y);
+                                y[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc.z, bi.z);
+                                y[i + 3] = fmaf(__uint_as_float(v[i + 3]), sc.w, bi.w);
+                            }
+                        }
+                        if (res_ptr != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                if (i < cols) {
+                                    const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rpre[i >> 3]);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float2 f = unpack2_act(rb[j], p.fp16);
+                                        y[i + 2 * j] += f.x;
+                                        y[i + 2 * j + 1] += f.y;
+                                    }
                                 }
-                                *reinterpret_cast<float4*>(f32_ptr + c0 + h + i) = o;
+                            }
+                            if (c0 + 64 + h < p.block_n) load_res(c0 + 64 + h);
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], 0.0f);
+                        }
+                        if (p.out_mode == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                if (i < cols) {
+                                    uint4 o;
+                                    o.x = pack2_act(y[i + 0], y[i + 1], p.fp16);
+                                    o.y = pack2_act(y[i + 2], y[i + 3], p.fp16);
+                                    o.z = pack2_act(y[i + 4], y[i + 5], p.fp16);
+                                    o.w = pack2_act(y[i + 6], y[i + 7], p.fp16);
+                                    const int c16 = (h + i) >> 3;  // 16-byte chunk within the 128-byte row
+                                    ptx::st_shared_v4(stag_u32 + row * 128 + ((c16 ^ (row & 7)) << 4), o);
+                                }
+                            }
+                        } else if (f32_ptr != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                if (i < cols) {
+                                    float4 o = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+                                    if (g.lo != nullptr) {
+                                        const float4 lo = __ldg(reinterpret_cast<const float4*>(g.lo + n0 + i));
+                                        o.x = fmaxf(o.x, lo.x);
+                                        o.y = fmaxf(o.y, lo.y);
+                                        o.z = fmaxf(o.z, lo.z);
+                                        o.w = fmaxf(o.w, lo.w);
+                                    }
+                                    *reinterpret_cast<float4*>(f32_ptr + c0 + h + i) = o;
+                                }
                             }
                         }
                     }
                 }
                 if (p.out_mode == 0) {
                     ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
-                    ptx::named_bar_sync(1, 128);
+                    ptx::named_bar_sync(1, kEpiThreads);
                     if (store_leader) {
                         if (t.valid) ptx::tma_store_4d(&g.out_map, stag, n_base + c0, t.x0, t.y0, t.img);
                         ptx::tma_store_commit();
                     }
-                    if (g.pool_partial != nullptr && t.valid) {
-                        // eSE global-average-pool, fused: per-tile channel sums of the bf16 tile just staged (exactly the
+                    if (g.pool_partial != nullptr && t.valid && et < 128) {
+                        // eSE global-average-pool, fused: per-tile channel sums of the 16-bit tile just staged (exactly the
                         // values the reference pools, vovnet.py:181).  Thread e covers channels 8*(e&7).. of rows
                         // (e>>3) + 16*i; the 4 row-groups of a warp are shuffle-reduced; one fp32 partial per
                         // (tile, warp, channel) -> deterministic reduction later (no atomics).
-                        const int e = threadIdx.x - 64;
+                        const int e = et;
                         const int cg = e & 7;
                         float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -598,7 +694,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                             const int r = (e >> 3) + 16 * i;
                             const int ry = t.y0 + (r >> g.tw_shift), rx = t.x0 + (r & (g.tw - 1));
                             if (ry < g.H && rx < g.W) {
-                                const uint4 u = *reinterpret_cast<const uint4*>(stag + r * 128 + ((cg ^ (r & 7)) << 4));
+                                const uint4 u = ptx::ld_shared_v4(stag_u32 + r * 128 + ((cg ^ (r & 7)) << 4));
                                 const uint32_t* b2 = reinterpret_cast<const uint32_t*>(&u);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
@@ -616,7 +712,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         if (lane < 8 && c0 + cg * 8 < p.block_n) {
                             const int tile_in_img = (t.y0 / g.th) * g.tiles_x + (t.x0 / g.tw);
                             float* dst = g.pool_partial +
-                                         ((static_cast<size_t>(t.img) * (g.tiles_x * g.tiles_y) + tile_in_img) * 4 + (warp - 2)) *
+                                         ((static_cast<size_t>(t.img) * (g.tiles_x * g.tiles_y) + tile_in_img) * 4 + (et >> 5)) *
                                              g.pool_pitch +
                                          n_base + c0 + cg * 8;
                             *reinterpret_cast<float4*>(dst) = make_float4(ps[0], ps[1], ps[2], ps[3]);
@@ -808,24 +904,11 @@ void conv_finalize_params(ConvParams* p) {
     if (p->cta2 && (tile < 2 || (p->block_n % 16) != 0)) p->cta2 = 0;
     p->pair_work = ((tile + 1) / 2) * p->n_blocks;
     const int stage_bytes = (p->halo ? 0 : kABytes) + (p->cta2 ? p->block_n / 2 : p->block_n) * 128;
-    const int fixed = 2 * kStagingBytes + 1024 /*alignment slack*/ + kBarBytes +
+    const int fixed = 2 * kStagingBytes + 1024 /*alignment slack*/ + kBarBytes + kSbBytes +
                       (p->halo ? kHaloAStages * kHaloABytes : 0);
     int stages = (kSmemBudget - fixed) / stage_bytes;
     p->num_stages = std::max(2, std::min(kMaxStages, stages));
-    // split-K chains: enough independent accumulators to cover the ~160-cycle dependent-MMA latency
-    // (one MMA of N columns occupies the pipe for N/2 cycles), within 512 TMEM columns.
-    static int force_chains = -1;
-    if (force_chains < 0) {
-        const char* e = getenv("DD3D_CONV_CHAINS");
-        force_chains = e ? atoi(e) : 0;
-    }
-    int chains = 1;
-    if (!p->halo) {
-        if (force_chains > 0) chains = force_chains;  // default 1: no measured benefit
-        while (chains > 1 && chains * p->block_n > 512) chains /= 2;
-        const int kmmas = p->taps * p->kchunks * (kBlockK / 16);
-        while (chains > 1 && chains > kmmas) chains /= 2;
-    }
+    const int chains = 1;  // split-K accumulator chains were measured and dropped; field kept = 1
     p->chains = chains;
     p->acc_stages = (2 * chains * p->block_n <= 512) ? 2 : 1;
     {
@@ -851,10 +934,10 @@ void conv_set_cta2(int mode) { g_cta2_mode = (mode >= 0 && mode <= 2) ? mode : -
 
 cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
     const int stage_bytes = (p.halo ? 0 : kABytes) + (p.cta2 ? p.block_n / 2 : p.block_n) * 128;
-    const int smem_bytes = p.num_stages * stage_bytes + 2 * kStagingBytes + 1024 + kBarBytes +
+    const int smem_bytes = p.num_stages * stage_bytes + 2 * kStagingBytes + 1024 + kBarBytes + kSbBytes +
                            (p.halo ? kHaloAStages * kHaloABytes : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static uint64_t attr_devices = 0;  // per-device opt-in to > 48 KB dynamic shared memory
+    if (first_use_on_device(&attr_devices)) {
         cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kSmemBudget);
         if (e == cudaSuccess)
@@ -864,7 +947,6 @@ cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(conv_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     if (p.total_work <= 0) return cudaSuccess;
     if (p.total_work >= (1 << 24)) return cudaErrorInvalidValue;  // fast_div range of the tile decode

@@ -14,7 +14,7 @@ namespace dd3d {
 constexpr int kMaxSeg = 5;
 constexpr int kBlockM = 128;  // output pixels per tile (th * tw)
 constexpr int kBlockK = 64;   // bf16 channels per k-block = one 128-byte swizzle row
-constexpr int kConvThreads = 224;  // warps: 0 TMA, 1 MMA, 2-5 epilogue, 6 halo A-patch producer
+constexpr int kConvThreads = 352;  // warps: 0 TMA, 1 MMA, 2 second TMA producer, 3-10 epilogue (two per TMEM lane quarter)
 
 struct ConvSeg {
     CUtensorMap in_map[2];  // NHWC bf16 input.  stride 1: [0] (4-D).  stride 2: [w-parity] (5-D parity split)

@@ -10,6 +10,7 @@
 //   3. if more than POST_NMS_TOPK remain keep those whose 2-D score >= the k-th largest 2-D score (fcos2d.py:359-365);
 //   4. scale boxes to the requested output size, clip, drop empty boxes (detector_postprocess).
 #include "detect.cuh"
+#include "device_once.cuh"
 
 namespace dd3d {
 
@@ -293,7 +294,8 @@ cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream) {
     if (cap > kMaxCand || p.B <= 0) return cudaErrorInvalidValue;
     const size_t smem = static_cast<size_t>(kMaxCand) * 8 + static_cast<size_t>(cap) * 16 +
                         static_cast<size_t>(cap) * 8 + static_cast<size_t>(kMaxCand) * 2 + static_cast<size_t>(cap) * 2;
-    static size_t attr_smem = 0;  // the limit is 227 KiB minus the kernel's static shared memory: ask for what we use
+    static size_t attr_smem_dev[64] = {};  // per device; the limit is 227 KiB minus the static shared memory: ask for what we use
+    size_t& attr_smem = attr_smem_dev[current_device_or_zero()];
     if (smem > attr_smem) {
         cudaError_t e =
             cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -220,6 +220,12 @@ cudaError_t ResizeTables::launch(const uint8_t* d_raw, int raw_h, int raw_w, con
     }
     if ((err = cudaMemcpyAsync(d_img, h_img.data(), sizeof(ResizeImage) * B, cudaMemcpyHostToDevice, stream)) != cudaSuccess)
         return err;
+    int dev_now = 0;
+    cudaGetDevice(&dev_now);
+    if (dev_now != smem_device) {  // tables (and the opt-in) belong to the device they were created on
+        smem_configured = 0;
+        smem_device = dev_now;
+    }
     if (smem > 48 * 1024 && smem > smem_configured) {
         if ((err = cudaFuncSetAttribute(resize_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem))) != cudaSuccess)

@@ -48,6 +48,7 @@ class ResizeTables {
     ResizeImage* d_img = nullptr;
     int img_cap = 0;
     size_t smem_configured = 0;
+    int smem_device = -1;
 };
 
 }  // namespace dd3d

@@ -40,16 +40,21 @@ __global__ void preprocess_kernel(const T* __restrict__ src, const int* __restri
 }
 
 // ------------------------------------------------------------------------------------------ max-pool
-// element-wise maximum of 8 packed 16-bit values; through fp32, which is exact for bf16 and fp16 alike
+// element-wise maximum of 8 packed 16-bit values (paired HMNMX2 of the storage type; the flag is warp-uniform)
 __device__ __forceinline__ uint4 max8(uint4 a, uint4 b, int fp16) {
     uint4 r;
-    const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
-    const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
-    uint32_t* pr = reinterpret_cast<uint32_t*>(&r);
+    if (fp16) {
+        const __half2* pa = reinterpret_cast<const __half2*>(&a);
+        const __half2* pb = reinterpret_cast<const __half2*>(&b);
+        __half2* pr = reinterpret_cast<__half2*>(&r);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 x = unpack2_act(pa[i], fp16), y = unpack2_act(pb[i], fp16);
-        pr[i] = pack2_act(fmaxf(x.x, y.x), fmaxf(x.y, y.y), fp16);
+        for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+    } else {
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+        __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
     }
     return r;
 }

@@ -14,6 +14,7 @@
 #include <algorithm>
 
 #include "act16.cuh"
+#include "device_once.cuh"
 #include "ptx.cuh"
 #include "small_kernels.cuh"
 
@@ -184,11 +185,10 @@ cudaError_t launch_one(const __nv_bfloat16* in, const __nv_bfloat16* w, const fl
     const int Ho = (H + 2 * PAD - KS) / STRIDE + 1, Wo = (W + 2 * PAD - KS) / STRIDE + 1;
     const int tiles_x = (Wo + kTileW - 1) / kTileW, tiles_y = (Ho + kTileH - 1) / kTileH;
     const int smem = KB * 16384 + KB * COUT * 128 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static uint64_t attr_devices = 0;  // per template instantiation, per device
+    if (first_use_on_device(&attr_devices)) {
         cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<KS, STRIDE, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     const int ctas_per_sm = std::max(1, std::min(4, (200 * 1024) / smem));
     const int total = B * tiles_x * tiles_y;

@@ -66,6 +66,15 @@ SIGNATURES = {
     "dd3d_wait_host": (_I, [_P, _I]),
     "dd3d_overflow_flags": (_I, [_P, _P, C.POINTER(C.c_int32)]),
     "dd3d_set_option": (_I, [_P, C.c_char_p, _I]),
+    "dd3d_copy_flags": (_I, [_P, _P, _P]),
+    "dd3d_packed_bytes": (_I64, [_I, _I]),
+    "dd3d_comm_unique_id": (_I, [_P]),
+    "dd3d_comm_create": (_I, [_P, _I, _I, C.POINTER(_P)]),
+    "dd3d_comm_from_nccl": (_I, [_P, _I, _I, C.POINTER(_P)]),
+    "dd3d_comm_world": (_I, [_P]),
+    "dd3d_comm_destroy": (None, [_P]),
+    "dd3d_comm_last_error": (C.c_char_p, []),
+    "dd3d_allgather": (_I, [_P, _P, _P, _I64, _P]),
     "dd3d_launches_per_forward": (_I, [_P]),
     "dd3d_num_ops": (_I, [_P]),
     "dd3d_get_profile": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -55,9 +55,12 @@ class DD3DB200(nn.Module):
 
     def to(self, device=None, *args, **kwargs):  # noqa: D401 - mirrors nn.Module.to for the device move
         if device is not None and not isinstance(device, torch.dtype):
-            self._device = torch.device(device)
-            if self._device.type == "cuda" and self._device.index is None:
-                self._device = torch.device("cuda", torch.cuda.current_device())
+            new = torch.device(device)
+            if new.type == "cuda" and new.index is None:
+                new = torch.device("cuda", torch.cuda.current_device())
+            if new != self._device:
+                self._release()  # the engine (weights, workspace, TMA descriptors) is bound to the device it was created on
+            self._device = new
         return self
 
     def cuda(self, device=None):
@@ -138,6 +141,34 @@ class DD3DB200(nn.Module):
                 _lib.check(L.dd3d_plan(handle, B, Hs, Ws, None, 0), self._handle)
             self._plan_key = key
             self._host_bufs = None
+
+    def _sync_options(self, postprocess_in_forward):
+        """Pushes the attributes callers toggle at run time (postprocess_in_inference, do_nms: scripts/train.py:206-209,
+        core.py:134) to the engine.  Without NMS (or without a post-NMS top-k) up to 5 * PRE_NMS_TOPK detections per image
+        survive: an engine planned with the small NMS-sized output buffer is rebuilt with the large one instead of silently
+        truncating (the reference never truncates)."""
+        inf = self.cfg.DD3D.FCOS2D.INFERENCE
+        if self.do_bev_nms and not self.do_nms:
+            raise NotImplementedError("DO_BEV_NMS without DO_NMS: the BEV kernel expects the score-sorted output of the 2-D NMS")
+        need = 5 * inf.PRE_NMS_TOPK if (not self.do_nms or inf.POST_NMS_TOPK <= 0) else 0
+        if need > self._desc.out_cap:
+            self._release()
+            self._desc.out_cap = need
+        L = _lib.load()
+        h = self._engine()
+        _lib.check(L.dd3d_set_option(h, b"do_postprocess", int(postprocess_in_forward)), h)
+        _lib.check(L.dd3d_set_option(h, b"do_nms", int(self.do_nms)), h)
+
+    def _check_flags(self, flags):
+        """Overflow word of the last forward (folded into the counts D2H): any set bit means the output differs from the
+        reference's (which has no capacity limits) -- fail loudly instead of returning truncated detections."""
+        self.last_overflow_flags = int(flags)
+        if flags:
+            names = {1: "more candidates tied at the k-th pre-NMS score than the boundary buffer holds",
+                     2: "more detections than out_cap slots", 4: "more than 256 boxes entered the BEV NMS of one image",
+                     8: "sample aggregation capacity exceeded"}
+            raise RuntimeError("DD3DB200: detection capacity exceeded (" +
+                               "; ".join(v for k, v in names.items() if flags & k) + f"; flags={int(flags)})")
 
     # ------------------------------------------------------------------ forward
     def _gather_inputs(self, batched_inputs, device):
@@ -228,7 +259,9 @@ class DD3DB200(nn.Module):
         return self._finish(self._forward_device_raw(raw_inputs), raw_inputs)
 
     def _finish(self, r, batched_inputs):
-        return self._wrap(r["out"], r["counts"].cpu(), r["K"], r["sizes"], self._device)  # .cpu(): the only sync
+        host = r["counts"].cpu()  # the only sync: B counts + the overflow word
+        self._check_flags(int(host[-1]))
+        return self._wrap(r["out"], host[:-1], r["K"], r["sizes"], self._device)
 
     def _forward_device_raw(self, raw_inputs):
         device = self._device
@@ -258,21 +291,21 @@ class DD3DB200(nn.Module):
         K0 = torch.stack([torch.as_tensor(x["intrinsics"], dtype=torch.float32) for x in raw_inputs], 0).reshape(B, 9).contiguous()
         if torch.allclose(K0[0].reshape(3, 3), torch.eye(3)):  # image_list.py:57-62
             raise ValueError("Intrinsics is Identity.")
+        self._sync_options(self.postprocess_in_inference)
         self._plan(B, int(new_sizes[:, 0].max()), int(new_sizes[:, 1].max()))
         cap = self._desc.out_cap
         K = torch.empty((B, 9), dtype=torch.float32)
         with torch.cuda.device(device):
             d_raw = raw.to(device, non_blocking=True)
             out = torch.empty((B, cap, _lib.DET_WORDS), dtype=torch.float32, device=device)
-            counts = torch.empty((B, ), dtype=torch.int32, device=device)
+            counts = torch.zeros((B + 1, ), dtype=torch.int32, device=device)  # [B] counts + overflow word
             stream = torch.cuda.current_stream(device).cuda_stream
-            _lib.check(L.dd3d_set_option(self._handle, b"do_postprocess", int(self.postprocess_in_inference)), self._handle)
-            _lib.check(L.dd3d_set_option(self._handle, b"do_nms", int(self.do_nms)), self._handle)
             _lib.check(
                 L.dd3d_forward_raw(self._handle, C.c_void_p(d_raw.data_ptr()), raw_h, raw_w, C.c_void_p(raw_sizes.data_ptr()),
                                    C.c_void_p(K0.data_ptr()), min_size, max_size, C.c_void_p(out.data_ptr()),
                                    C.c_void_p(counts.data_ptr()), C.c_void_p(K.data_ptr()), None, C.c_void_p(stream)),
                 self._handle)
+            _lib.check(L.dd3d_copy_flags(self._handle, C.c_void_p(counts[B:].data_ptr()), C.c_void_p(stream)), self._handle)
             d_K = K.to(device, non_blocking=True)
         sizes = torch.cat([new_sizes, raw_sizes if self.postprocess_in_inference else new_sizes], 1)
         return dict(out=out, counts=counts, K=K, sizes=sizes, d_K=d_K, B=B, cap=cap, stream=stream)
@@ -280,6 +313,8 @@ class DD3DB200(nn.Module):
     def _forward_device(self, batched_inputs):
         device = self._device
         batch, K, sizes, shape, is_u8 = self._gather_inputs(batched_inputs, device)
+        # with BEV NMS the rescale/clip happens after it (core.py:137-160): the BEV kernel applies it then
+        self._sync_options(self.postprocess_in_inference and not self.do_bev_nms)
         self._plan(*shape)
         L = _lib.load()
         B = shape[0]
@@ -289,16 +324,13 @@ class DD3DB200(nn.Module):
             d_K = K.to(device, non_blocking=True)
             d_sizes = sizes.to(device, non_blocking=True)
             out = torch.empty((B, cap, _lib.DET_WORDS), dtype=torch.float32, device=device)
-            counts = torch.empty((B, ), dtype=torch.int32, device=device)
+            counts = torch.zeros((B + 1, ), dtype=torch.int32, device=device)  # [B] counts + overflow word
             stream = torch.cuda.current_stream(device).cuda_stream
-            # with BEV NMS the rescale/clip happens after it (core.py:137-160): the BEV kernel applies it then
-            post_in_fwd = self.postprocess_in_inference and not self.do_bev_nms
-            _lib.check(L.dd3d_set_option(self._handle, b"do_postprocess", int(post_in_fwd)), self._handle)
-            _lib.check(L.dd3d_set_option(self._handle, b"do_nms", int(self.do_nms)), self._handle)
             _lib.check(
                 L.dd3d_forward(self._handle, C.c_void_p(d_batch.data_ptr()), _lib.IMG_U8 if is_u8 else _lib.IMG_F32,
                                C.c_void_p(d_K.data_ptr()), C.c_void_p(d_sizes.data_ptr()), C.c_void_p(out.data_ptr()),
                                C.c_void_p(counts.data_ptr()), C.c_void_p(stream)), self._handle)
+            _lib.check(L.dd3d_copy_flags(self._handle, C.c_void_p(counts[B:].data_ptr()), C.c_void_p(stream)), self._handle)
             if self.do_bev_nms:
                 d_poses = self._gather_poses(batched_inputs).to(device, non_blocking=True)
                 self._bev_flags = torch.zeros(1, dtype=torch.int32, device=device)
@@ -307,6 +339,7 @@ class DD3DB200(nn.Module):
                                       C.c_void_p(d_poses.data_ptr()), C.c_void_p(d_sizes.data_ptr()),
                                       C.c_void_p(self._bev_flags.data_ptr()), B, cap, float(self.bev_nms_iou_thresh),
                                       int(self.postprocess_in_inference), C.c_void_p(stream)), self._handle)
+                counts[B:] |= self._bev_flags  # bit 2 rides in the same overflow word
         return dict(out=out, counts=counts, K=K, sizes=sizes, d_K=d_K, B=B, cap=cap, stream=stream)
 
     def __call__(self, batched_inputs):
@@ -315,7 +348,10 @@ class DD3DB200(nn.Module):
     @torch.no_grad()
     def forward_host(self, batched_inputs):
         """End-to-end path through HOST buffers: pinned staging -> dd3d_forward_host (H2D, kernels, D2H, sync)."""
+        if self.do_bev_nms:  # the BEV NMS runs on the device buffers: device forward, then the results to the host
+            return [{"instances": o["instances"].to("cpu")} for o in self.forward(batched_inputs)]
         batch, K, sizes, shape, is_u8 = self._gather_inputs(batched_inputs, self._device)
+        self._sync_options(self.postprocess_in_inference)
         self._plan(*shape)
         L = _lib.load()
         B = shape[0]
@@ -332,13 +368,12 @@ class DD3DB200(nn.Module):
         hb["sizes"].copy_(sizes)
         with torch.cuda.device(self._device):
             stream = torch.cuda.current_stream(self._device).cuda_stream
-            _lib.check(L.dd3d_set_option(self._handle, b"do_postprocess", int(self.postprocess_in_inference)),
-                       self._handle)
             _lib.check(
                 L.dd3d_forward_host(self._handle, C.c_void_p(hb["img"].data_ptr()),
                                     _lib.IMG_U8 if is_u8 else _lib.IMG_F32, C.c_void_p(hb["K"].data_ptr()),
                                     C.c_void_p(hb["sizes"].data_ptr()), C.c_void_p(hb["out"].data_ptr()),
                                     C.c_void_p(hb["counts"].data_ptr()), C.c_void_p(stream)), self._handle)
+        self._check_flags(self.overflow_flags())
         return self._wrap(hb["out"], hb["counts"], K, sizes, torch.device("cpu"))
 
     @torch.no_grad()
@@ -346,7 +381,11 @@ class DD3DB200(nn.Module):
         """Double-buffered host path (dd3d_submit_host): enqueues H2D -> kernels -> D2H for `slot` (0 / 1) and returns;
         ``wait_host(slot)`` returns the results.  Submitting the next batch to the other slot before waiting overlaps
         its H2D with the current batch's kernels.  All batches of a pipeline must share one plan shape."""
+        if self.do_bev_nms:
+            raise NotImplementedError("submit_host with DO_BEV_NMS: use forward() / forward_host() (the BEV NMS kernel runs on "
+                                      "the device buffers before the D2H)")
         batch, K, sizes, shape, is_u8 = self._gather_inputs(batched_inputs, self._device)
+        self._sync_options(self.postprocess_in_inference)
         self._plan(*shape)
         L = _lib.load()
         B, cap = shape[0], self._desc.out_cap
@@ -365,8 +404,6 @@ class DD3DB200(nn.Module):
         hb["ctx"] = (K, sizes)
         with torch.cuda.device(self._device):
             stream = torch.cuda.current_stream(self._device).cuda_stream
-            _lib.check(L.dd3d_set_option(self._handle, b"do_postprocess", int(self.postprocess_in_inference)),
-                       self._handle)
             _lib.check(
                 L.dd3d_submit_host(self._handle, int(slot), C.c_void_p(hb["img"].data_ptr()),
                                    _lib.IMG_U8 if is_u8 else _lib.IMG_F32, C.c_void_p(hb["K"].data_ptr()),
@@ -376,6 +413,7 @@ class DD3DB200(nn.Module):
     def wait_host(self, slot=0):
         hb = self._slots[slot]
         _lib.check(_lib.load().dd3d_wait_host(self._handle, int(slot)), self._handle)
+        self._check_flags(self.overflow_flags())
         K, sizes = hb["ctx"]
         return self._wrap(hb["out"].clone(), hb["counts"].clone(), K, sizes, torch.device("cpu"))
 
@@ -419,7 +457,10 @@ class DD3DB200(nn.Module):
         flags = C.c_int32(0)
         stream = torch.cuda.current_stream(self._device).cuda_stream
         _lib.check(_lib.load().dd3d_overflow_flags(self._handle, C.c_void_p(stream), C.byref(flags)), self._handle)
-        return flags.value
+        f = flags.value
+        if getattr(self, "_bev_flags", None) is not None:
+            f |= int(self._bev_flags.item())
+        return f
 
 
 def group_indices(sample_tokens, num_images_per_sample):
@@ -473,7 +514,10 @@ class NuscenesDD3DB200(DD3DB200):
                                                C.c_void_p(self._agg_flags.data_ptr()), B, cap,
                                                float(self.bev_nms_iou_thresh), int(self.max_num_dets_per_sample or 0),
                                                C.c_void_p(r["stream"])), self._handle)
-        return self._wrap(r["out"], r["counts"].cpu(), r["K"], r["sizes"], self._device, glob)
+            r["counts"][B:] |= self._agg_flags  # bit 3 rides in the same overflow word
+        host = r["counts"].cpu()
+        self._check_flags(int(host[-1]))
+        return self._wrap(r["out"], host[:-1], r["K"], r["sizes"], self._device, glob)
 
     def forward_host(self, batched_inputs):
         """Host-buffer path: the sample aggregation needs the detections of all cameras on the device, so this is the

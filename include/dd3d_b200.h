@@ -188,6 +188,27 @@ int dd3d_forward_resized(dd3d_handle h, const uint8_t* d_raw, int raw_h, int raw
                          const int32_t* h_new_sizes, const int32_t* h_flip, const float* h_intrinsics,
                          const int32_t* h_sizes, dd3d_det* d_out, int32_t* d_counts, dd3d_stream stream);
 
+/* ---- multi-GPU: ONE NCCL all-gather of the packed detections --------------------------------------
+ * Batches shard over the GPUs with replicated weights and no collective inside dd3d_forward; for whole-batch evaluation
+ * each rank contributes one fixed-stride buffer and receives everybody's -- the replacement of detectron2 comm.gather of
+ * pickled prediction lists (kitti_3d_evaluator.py:152-164).  Packed layout (dd3d_packed_bytes(B, out_cap) bytes, 256-byte
+ * padded):  dd3d_det[B][out_cap] | int32 counts[B] | int32 flags  -- allocate ONE device buffer, pass its two parts as
+ * d_out / d_counts of dd3d_forward, fill the flags word with dd3d_copy_flags, then gather the whole buffer.
+ * NCCL is resolved at run time (dlopen libnccl.so.2; env DD3D_NCCL_LIB overrides); without it these calls return
+ * DD3D_ERR_CUDA and dd3d_comm_last_error() says why.  One process per GPU. */
+typedef struct dd3d_comm_s* dd3d_comm;
+int64_t dd3d_packed_bytes(int B, int out_cap);
+/* device word of the overflow flags of the last forward (bits as dd3d_overflow_flags) -> d_dst, on `stream`, no sync */
+int dd3d_copy_flags(dd3d_handle h, int32_t* d_dst, dd3d_stream stream);
+int dd3d_comm_unique_id(uint8_t* h_id128);          /* rank 0: ncclGetUniqueId; ship the 128 bytes to the other ranks */
+int dd3d_comm_create(const uint8_t* h_id128, int rank, int world, dd3d_comm* out); /* ncclCommInitRank, current device */
+int dd3d_comm_from_nccl(void* nccl_comm, int rank, int world, dd3d_comm* out);     /* adopt an existing ncclComm_t */
+int dd3d_comm_world(dd3d_comm c);
+void dd3d_comm_destroy(dd3d_comm c);
+const char* dd3d_comm_last_error(void);
+/* ncclAllGather of bytes_per_rank bytes: d_recv receives world x bytes_per_rank, rank-major.  Enqueued on `stream`. */
+int dd3d_allgather(dd3d_comm c, const void* d_send, void* d_recv, int64_t bytes_per_rank, dd3d_stream stream);
+
 /* ---- introspection for stage-level parity tests ---------------------------------------------------------- */
 /* name: "p0".."p4" (FPN outputs, bf16 NHWC), "cls0".."cls4", "box0".."box4", "b3d0".."b3d4" (fp32 NHWC head maps),
  * "input" (bf16 [B][Hp][Wp][4]).  Returns the device pointer and fills dims = {B, H, W, C, pitch, elem_bytes}. */

@@ -6,6 +6,16 @@ import torch
 from dd3d_b200 import lib
 
 
+ACT = torch.bfloat16  # 16-bit storage type of the operator entry points (set_act_dtype)
+
+
+def set_act_dtype(name):
+    """"bf16" | "fp16": element type of the dd3d_op_* entry points (process-wide dd3d_set_conv_policy("op_fp16"))."""
+    global ACT
+    ACT = torch.float16 if name == "fp16" else torch.bfloat16
+    assert lib.load().dd3d_set_conv_policy(b"op_fp16", int(name == "fp16")) == 0
+
+
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -21,7 +31,7 @@ def pack_conv_weight(w):
     cin_pad = (cin + 63) // 64 * 64
     out = torch.zeros(cout_pad, k * k, cin_pad, dtype=torch.float32)
     out[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
-    return out.to(torch.bfloat16).contiguous()
+    return out.to(ACT).contiguous()
 
 
 def pad16(v, fill):
@@ -50,7 +60,7 @@ def conv2d(x_nhwc, w, scale, bias, stride=1, relu=False, residual=None, res_up2=
         out_ptr = out.data_ptr()
     else:
         op = out_pitch or cout
-        out = torch.full((B, Ho, Wo, op), 7.0, dtype=torch.bfloat16, device="cuda")
+        out = torch.full((B, Ho, Wo, op), 7.0, dtype=ACT, device="cuda")
         out_ptr = out.data_ptr() + 2 * out_offset
     in_ptr = x_nhwc.data_ptr() + 2 * c0
     res_ptr, res_pitch = None, 0
@@ -68,7 +78,7 @@ def conv2d_ref(x_nhwc, w, scale, bias, stride=1, relu=False, residual=None, res_
     import torch.nn.functional as F
     c0, cin = in_slice if in_slice is not None else (0, x_nhwc.shape[-1])
     x = x_nhwc[..., c0:c0 + cin].float().permute(0, 3, 1, 2)
-    wq = w.to(torch.bfloat16).float().to(x.device)
+    wq = w.to(ACT).float().to(x.device)
     k = w.shape[-1]
     y = F.conv2d(x, wq, None, stride, (k - 1) // 2)
     y = y * scale.to(x.device).view(1, -1, 1, 1) + bias.to(x.device).view(1, -1, 1, 1)

@@ -1,12 +1,15 @@
 """End-to-end parity (-m gpu): DD3DB200.forward (C ABI -> sm_100a kernels) vs the CPU oracle on identical inputs.
 
-Tolerances (see DESIGN.md "Numerics"): the engine stores activations in bf16, so it is compared
-  (a) tightly with the oracle run in bf16-storage emulation (same rounding points; differences come only from
-      fp32 accumulation order -> isolated 1-ulp bf16 flips): relative L2 error of every FPN / head map <= 1e-2 and
-      matched detections within 2e-2 (boxes relative to box size, scores absolute);
-  (b) loosely with the committed fp32 golden vectors of the REAL reference: >= 60 % of the reference detections
-      are reproduced (same level, location, class) with boxes within 10 % of the box size.
-The fp32 decode / NMS kernels themselves are held to <= 1e-4 in tests/test_kernels_gpu.py."""
+Tolerances (see DESIGN.md "Numerics"; thresholds = the measured values of profiles/parity_r02.json x ~2): the engine
+stores activations in bf16, so it is compared
+  (a) with the oracle run in bf16-storage emulation on ONE thread (same rounding points; differences come only from fp32
+      accumulation order -> isolated 1-ulp bf16 flips): relative L2 error of every FPN / head map <= 1e-2 / 1.5e-2 (measured
+      7e-3 .. 1.0e-2), >= 90 % of the detections matched (measured 95.5 % / 98.8 %), boxes within 1.3e-2 of the box size
+      (measured 6.5e-3), scores within 8e-3 (3.7e-3);
+  (b) with the committed fp32 golden vectors of the REAL reference: >= 90 % of the reference detections reproduced (same
+      level, location, class; measured 95.8 % / 100 %) with boxes within 1.6e-2 of the box size (measured 8e-3).
+The fp32 decode / NMS kernels themselves are held to <= 1e-4 in tests/test_kernels_gpu.py, and at the BASELINE shapes to
+exact sets / order in tests/test_parity_full_gpu.py (which also covers the fp16 storage type)."""
 import os
 
 import numpy as np
@@ -48,7 +51,7 @@ def test_forward_vs_emulating_oracle(arch):
     out = model(inputs)
     torch.cuda.synchronize()
     assert model.overflow_flags() == 0
-    ref, inter = DD3DOracle(cfg, sd, emulate_bf16=True).forward(inputs, return_intermediates=True)
+    ref, inter = DD3DOracle(cfg, sd, emulate="bf16", threads=1).forward(inputs, return_intermediates=True)
     C = cfg.DD3D.NUM_CLASSES
     # ---- stage level: preprocessed input (bit exact), FPN outputs, head maps
     x = model.get_tensor("input")[..., :3].float().cpu().permute(0, 3, 1, 2)
@@ -71,18 +74,18 @@ def test_forward_vs_emulating_oracle(arch):
         inst = o["instances"]
         kr = [det_key(l, p, c) for l, p, c in zip(r["level"], r["loc"], r["cls"])]
         ia, ib = match_by_key(_keys_inst(inst), kr)
-        assert len(ib) >= 0.8 * len(kr), f"image {b}: matched {len(ib)} of {len(kr)}"
+        assert len(ib) >= 0.9 * len(kr) - 1, f"image {b}: matched {len(ib)} of {len(kr)}"
         if len(ia) == 0:
             continue
         gb, rb = inst.pred_boxes.tensor.cpu()[ia], r["box2d"][ib]
         size = torch.stack([rb[:, 2] - rb[:, 0], rb[:, 3] - rb[:, 1]], 1).clamp(min=1.0).repeat(1, 2)
-        assert ((gb - rb).abs() / size).max() < 2e-2
-        assert (inst.scores_3d.cpu()[ia] - r["score3d"][ib]).abs().max() < 2e-2
-        assert (inst.scores.cpu()[ia] - r["score"][ib]).abs().max() < 2e-2
+        assert ((gb - rb).abs() / size).max() < 1.3e-2
+        assert (inst.scores_3d.cpu()[ia] - r["score3d"][ib]).abs().max() < 4e-3
+        assert (inst.scores.cpu()[ia] - r["score"][ib]).abs().max() < 8e-3
         b3 = inst.pred_boxes3d
-        assert quat_dist(b3.quat.cpu()[ia], r["quat"][ib]).max() < 3e-2
-        assert ((b3.size.cpu()[ia] - r["size"][ib]).abs() / r["size"][ib]).max() < 3e-2
-        assert ((b3.depth.cpu()[ia, 0] - r["depth"][ib]).abs() / r["depth"][ib]).max() < 3e-2
+        assert quat_dist(b3.quat.cpu()[ia], r["quat"][ib]).max() < 6e-2
+        assert ((b3.size.cpu()[ia] - r["size"][ib]).abs() / r["size"][ib]).max() < 2.6e-2
+        assert ((b3.depth.cpu()[ia, 0] - r["depth"][ib]).abs() / r["depth"][ib]).max() < 8e-3
         assert (b3.tvec.cpu()[ia] - r["tvec"][ib]).abs().max() < 0.05 * r["tvec"][ib].abs().max()
 
 
@@ -96,10 +99,10 @@ def test_forward_vs_reference_golden(arch):
         assert tuple(inst.image_size) == tuple(g[f"image_size{b}"].tolist())
         kg = [det_key(l, p, c) for l, p, c in zip(g[f"levels{b}"], g[f"locations{b}"], g[f"classes{b}"])]
         ia, ib = match_by_key(_keys_inst(inst), kg)
-        assert len(ib) >= 0.6 * len(kg), f"image {b}: matched {len(ib)} of {len(kg)}"
+        assert len(ib) >= 0.9 * len(kg) - 1, f"image {b}: matched {len(ib)} of {len(kg)}"
         gb, rb = inst.pred_boxes.tensor.cpu()[ia], torch.tensor(g[f"boxes{b}"])[ib]
         size = torch.stack([rb[:, 2] - rb[:, 0], rb[:, 3] - rb[:, 1]], 1).clamp(min=1.0).repeat(1, 2)
-        assert ((gb - rb).abs() / size).max() < 0.1
+        assert ((gb - rb).abs() / size).max() < 1.6e-2
 
 
 def test_host_path_equals_device_path_and_is_deterministic():

@@ -20,17 +20,28 @@ from util import quat_dist
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["bf16", "fp16"])
+def act(request):
+    """Runs the test once per 16-bit storage type of the engine (dd3d_model_desc.act_dtype)."""
+    gpu_ops.set_act_dtype(request.param)
+    yield request.param
+    gpu_ops.set_act_dtype("bf16")
+
+
 def _rand_act(B, H, W, C, seed, pitch=None):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, H, W, pitch or C, generator=g)
-    return x.to(torch.bfloat16).cuda()
+    return x.to(gpu_ops.ACT).cuda()
 
 
 def _check_bf16(out, ref, what):
+    """One rounding of an fp32-accumulated value to the storage type: 2^-8 (bf16) / 2^-11 (fp16) relative, doubled for
+    accumulation-order differences next to a rounding boundary, plus a small absolute term."""
+    fp16 = out.dtype == torch.float16
     out = out.float().cpu()
     ref = ref.cpu()
     err = (out - ref).abs()
-    tol = 2.0**-7 * ref.abs() + 2e-2
+    tol = (2.0**-10 * ref.abs() + 3e-3) if fp16 else (2.0**-7 * ref.abs() + 2e-2)
     bad = (err > tol)
     assert not bad.any(), f"{what}: {int(bad.sum())} / {bad.numel()} mismatches, max err {err.max():.4f}"
 
@@ -60,7 +71,7 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,H,W,B,relu,res", CONV_CASES)
-def test_conv_bf16(cin, cout, k, stride, H, W, B, relu, res):
+def test_conv_bf16(cin, cout, k, stride, H, W, B, relu, res, act):
     g = torch.Generator().manual_seed(cin * 131 + cout + k + H)
     x = _rand_act(B, H, W, cin, seed=cin + H)
     w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k)**0.5
@@ -77,7 +88,7 @@ def test_conv_bf16(cin, cout, k, stride, H, W, B, relu, res):
     _check_bf16(out, ref, f"conv {cin}->{cout} k{k} s{stride} {H}x{W}")
 
 
-def test_conv_concat_slices():
+def test_conv_concat_slices(act):
     """Input = channel slice of a wider buffer, output written into a slice of another (the free-concat trick)."""
     g = torch.Generator().manual_seed(3)
     x = _rand_act(1, 16, 24, 0, seed=11, pitch=448)
@@ -91,7 +102,7 @@ def test_conv_concat_slices():
 
 
 @pytest.mark.parametrize("cout", [15, 110, 55])
-def test_conv_f32_predictor(cout):
+def test_conv_f32_predictor(cout, act):
     g = torch.Generator().manual_seed(cout)
     x = _rand_act(2, 15, 25, 256, seed=cout)
     w = torch.randn(cout, 256, 3, 3, generator=g) / 48.0
@@ -119,7 +130,7 @@ def test_conv_linearity_large():
     _check_bf16(y1[:, 101:119, 201:231], ref[:, 1:-1, 1:-1], "crop of the large map")
 
 
-def test_stem_conv_and_preprocess():
+def test_stem_conv_and_preprocess(act):
     L = lib.load()
     g = torch.Generator().manual_seed(4)
     B, Hs, Ws, Hp, Wp = 2, 50, 70, 64, 128
@@ -127,7 +138,7 @@ def test_stem_conv_and_preprocess():
     sizes = torch.tensor([[50, 70], [41, 66]], dtype=torch.int32)
     mean = torch.tensor([103.53, 116.28, 123.675])
     std = torch.tensor([57.375, 57.12, 58.395])
-    out4 = torch.empty(B, Hp, Wp, 4, dtype=torch.bfloat16, device="cuda")
+    out4 = torch.empty(B, Hp, Wp, 4, dtype=gpu_ops.ACT, device="cuda")
     d_img, d_sizes = img.cuda(), sizes.cuda()  # keep the device tensors alive across the async launch
     st = L.dd3d_op_preprocess(gpu_ops._p(d_img), lib.IMG_U8, gpu_ops._p(d_sizes), gpu_ops._p(out4), B, Hs, Ws,
                               Hp, Wp, (C.c_float * 3)(*mean.tolist()), (C.c_float * 3)(*std.tolist()), gpu_ops._stream())
@@ -137,20 +148,20 @@ def test_stem_conv_and_preprocess():
     for b in range(B):
         h, w = sizes[b].tolist()
         ref[b, :, :h, :w] = (img[b, :, :h, :w].float() - mean.view(3, 1, 1)) / std.view(3, 1, 1)
-    ref = ref.to(torch.bfloat16)
+    ref = ref.to(gpu_ops.ACT)
     assert torch.equal(out4[..., :3].cpu(), ref.permute(0, 2, 3, 1))
     assert (out4[..., 3].float() == 0).all()
     for ksize, stride, cout in ((7, 1, 16), (3, 2, 64)):
         w = torch.randn(cout, 3, ksize, ksize, generator=g) / (3 * ksize * ksize)**0.5
-        wq = w.to(torch.bfloat16).float()
+        wq = w.to(gpu_ops.ACT).float()
         scale = 0.5 + torch.rand(cout, generator=g)
         bias = torch.randn(cout, generator=g) * 0.2
         kpad = (ksize * ksize * 4 + 63) // 64 * 64  # engine layout: bf16 [cout][kpad], k = (ky*ksize + kx)*4 + c
         wpk = torch.zeros(cout, kpad)
         wpk[:, :ksize * ksize * 4].view(cout, ksize * ksize, 4)[:, :, :3] = wq.permute(0, 2, 3, 1).reshape(cout, -1, 3)
-        wpk = wpk.to(torch.bfloat16).cuda()
+        wpk = wpk.to(gpu_ops.ACT).cuda()
         Ho, Wo = Hp // stride, Wp // stride
-        out = torch.empty(B, Ho, Wo, cout, dtype=torch.bfloat16, device="cuda")
+        out = torch.empty(B, Ho, Wo, cout, dtype=gpu_ops.ACT, device="cuda")
         d_scale, d_bias = scale.cuda(), bias.cuda()
         st = L.dd3d_op_stem_conv(gpu_ops._p(out4), gpu_ops._p(wpk), gpu_ops._p(d_scale), gpu_ops._p(d_bias),
                                  gpu_ops._p(out), B, Hp, Wp, ksize, stride, cout, cout, gpu_ops._stream())
@@ -162,12 +173,12 @@ def test_stem_conv_and_preprocess():
 
 
 @pytest.mark.parametrize("ksize,H,W", [(2, 24, 40), (3, 24, 40), (3, 15, 25)])
-def test_maxpool(ksize, H, W):
+def test_maxpool(ksize, H, W, act):
     L = lib.load()
     x = _rand_act(2, H, W, 0, seed=8, pitch=96)
     Cc = 64
     ref = F.max_pool2d(x[..., 16:16 + Cc].float().permute(0, 3, 1, 2), ksize, 2, ceil_mode=(ksize == 3)).permute(0, 2, 3, 1)
-    out = torch.zeros(2, ref.shape[1], ref.shape[2], 128, dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros(2, ref.shape[1], ref.shape[2], 128, dtype=gpu_ops.ACT, device="cuda")
     st = L.dd3d_op_maxpool(C.c_void_p(x.data_ptr() + 32), C.c_void_p(out.data_ptr() + 64), 2, H, W, Cc, 96, 128, ksize,
                            gpu_ops._stream())
     assert st == 0
@@ -177,7 +188,7 @@ def test_maxpool(ksize, H, W):
 
 
 @pytest.mark.parametrize("Cc,H,W,ident", [(256, 24, 40, False), (768, 15, 25, True), (1024, 8, 13, True)])
-def test_ese(Cc, H, W, ident):
+def test_ese(Cc, H, W, ident, act):
     L = lib.load()
     g = torch.Generator().manual_seed(Cc)
     B = 2
@@ -185,7 +196,7 @@ def test_ese(Cc, H, W, ident):
     idt = _rand_act(B, H, W, 0, seed=Cc + 1, pitch=Cc + 64) if ident else None
     fw = torch.randn(Cc, Cc, generator=g) / Cc**0.5
     fb = torch.randn(Cc, generator=g)
-    out = torch.zeros(B, H, W, Cc, dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros(B, H, W, Cc, dtype=gpu_ops.ACT, device="cuda")
     scratch = torch.empty(L.dd3d_op_ese_scratch_bytes(B, H * W, Cc) // 4, dtype=torch.float32, device="cuda")
     d_fw, d_fb = fw.cuda(), fb.cuda()
     st = L.dd3d_op_ese(gpu_ops._p(x), Cc, gpu_ops._p(d_fw), gpu_ops._p(d_fb), gpu_ops._p(idt), Cc + 64 if ident else 0,
