@@ -121,6 +121,10 @@ int dd3d_set_conv_policy(const char* name, int value) {
         conv_set_cta2(value);
         return DD3D_OK;
     }
+    if (!strcmp(name, "taps")) {
+        conv_set_taps(value);
+        return DD3D_OK;
+    }
     if (!strcmp(name, "op_fp16")) {
         g_op_fp16 = value ? 1 : 0;
         return DD3D_OK;
@@ -194,6 +198,8 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value) {
             e.desc.do_nms = value ? 1 : 0;
         } else if (n == "profile") {
             e.opt_profile = value ? 1 : 0;
+        } else if (n == "workspace_reuse") {  // applies to plans made afterwards
+            e.opt_workspace_reuse = value ? 1 : 0;
         } else if (n == "workspace_fill") {
             e.opt_workspace_fill = (value >= 0 && value <= 255) ? value : -1;
         } else {
@@ -341,12 +347,32 @@ int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch,
         g.res_H = res_up2 ? Ho / 2 : Ho;
         g.res_W = res_up2 ? Wo / 2 : Wo;
     }
+    p.taps_n = conv_taps_eligible(taps, stride, cout_pad, 1, &Ho, &Wo) ? 1 : 0;
+    if (!out_f32) g.out16 = d_out;
     conv_finalize_params(&p);
-    if (!make_weight_map(&p.w_map, d_w, taps * kchunks * kBlockK, cout_pad, p.cta2 ? block_n / 2 : block_n, g_op_fp16)) {
+    void* d_w_taps = nullptr;
+    if (p.taps_n) {
+        // repack [16][9][cin_pad] -> taps-in-N [9 * 16][cin_pad] on the device (operator entry point: not a hot path)
+        const int cin_pad = kchunks * kBlockK;
+        if (cudaMalloc(&d_w_taps, static_cast<size_t>(kTapsN) * cin_pad * 2) != cudaSuccess) return DD3D_ERR_CUDA;
+        for (int t = 0; t < 9; ++t)
+            cudaMemcpy2DAsync(static_cast<uint8_t*>(d_w_taps) + static_cast<size_t>(t) * 16 * cin_pad * 2, cin_pad * 2,
+                              static_cast<const uint8_t*>(d_w) + static_cast<size_t>(t) * cin_pad * 2, 9 * cin_pad * 2,
+                              cin_pad * 2, 16, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+        if (!make_weight_map_taps(&p.w_map, d_w_taps, cin_pad, g_op_fp16)) {
+            cudaFree(d_w_taps);
+            return DD3D_ERR_CUDA;
+        }
+    } else if (!make_weight_map(&p.w_map, d_w, taps * kchunks * kBlockK, cout_pad, p.cta2 ? block_n / 2 : block_n, g_op_fp16)) {
         fprintf(stderr, "dd3d_op_conv2d: %s\n", conv_last_error());
         return DD3D_ERR_CUDA;
     }
-    return cuda_status(launch_conv(p, device_sms(), static_cast<cudaStream_t>(stream)), nullptr);
+    const int st = cuda_status(launch_conv(p, device_sms(), static_cast<cudaStream_t>(stream)), nullptr);
+    if (d_w_taps) {
+        cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+        cudaFree(d_w_taps);
+    }
+    return st;
 }
 
 int dd3d_op_stem_conv(const void* d_in4, const void* d_w, const float* d_scale, const float* d_bias, void* d_out, int B,

@@ -555,15 +555,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             }
             // residual (BasicBlock identity / FPN top-down map) of this warp's FIRST step, fetched before the accumulator
             // wait; every later step's columns are fetched one step ahead (L2 / DRAM latency paid once per tile)
+            // NOTE: every branch that contains a warp-collective instruction (tcgen05.ld / tcgen05.wait::ld are .sync.aligned)
+            // must be WARP-UNIFORM.  `res_ptr` is per thread (null for pixels outside a ragged map), so the code below
+            // branches on `has_res` (per segment) and lets the out-of-image threads carry zeros.
+            const bool has_res = g.residual != nullptr;
             uint4 rpre[4];
             auto load_res = [&](int col) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    rpre[i] = (col + 8 * i < p.block_n) ? __ldg(reinterpret_cast<const uint4*>(res_ptr + col + 8 * i))
-                                                        : make_uint4(0u, 0u, 0u, 0u);
+                    rpre[i] = (res_ptr != nullptr && col + 8 * i < p.block_n)
+                                  ? __ldg(reinterpret_cast<const uint4*>(res_ptr + col + 8 * i))
+                                  : make_uint4(0u, 0u, 0u, 0u);
                 }
             };
-            if (res_ptr != nullptr && half * 32 < p.block_n) load_res(half * 32);
+            if (has_res && half * 32 < p.block_n) load_res(half * 32);
 
             ptx::mbar_wait(&tfull_bar[acc], acc_phase, 4);
             ptx::tc_fence_after();
@@ -593,7 +598,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         const uint32_t ssc = s_scale_u32 + (c0 + h) * 4, sbi = s_bias_u32 + (c0 + h) * 4;
                         const uint32_t stag_row = stag_u32 + row * 128;
                         const int mode = (p.relu ? 1 : 0) | (p.fp16 ? 2 : 0);  // warp-uniform: one branch per step
-                        if (res_ptr != nullptr) {
+                        if (has_res) {
                             switch (mode) {
                                 case 0: epi_fast_step<0, true>(v, ssc, sbi, rpre, stag_row, h >> 3, row & 7); break;
                                 case 1: epi_fast_step<1, true>(v, ssc, sbi, rpre, stag_row, h >> 3, row & 7); break;
@@ -624,7 +629,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                                 y[i + 3] = fmaf(__uint_as_float(v[i + 3]), sc.w, bi.w);
                             }
                         }
-                        if (res_ptr != nullptr) {
+                        if (has_res) {
 #pragma unroll
                             for (int i = 0; i < 32; i += 8) {
                                 if (i < cols) {
@@ -753,6 +758,241 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     }
 }
 
+// =========================================================================================== taps-in-N variant
+// 3x3 stride-1 convolutions with <= 16 output channels (FCOS predictors cls / [box2d_reg | centerness], DLA level0).
+// As nine N = 16 GEMMs per 64-channel block they sit at the UMMA instruction floor (~50-90 cycles for 128x16x16 instead of
+// 8) and reach 9 % tensor-pipe activity (profiles/r01d_conv_launches_v2_99.csv, launches 119/120).  Here the taps are GEMM
+// COLUMNS:  P[pixel of the (16+2)x(8+2) halo patch][tap * 16 + co] = sum_c in[pixel][c] * W[co][tap][c]  -- two
+// M128 x N144 x K16 UMMAs per K step over the SAME halo patch the halo variant stages -- and the output is the shifted sum
+//   out[y][x][co] = sum_{r,s} P[(y + r) * 10 + (x + s)][(3 r + s) * 16 + co]
+// taken from shared memory in a fixed order (deterministic).  9x fewer tensor cycles, no extra HBM traffic.
+constexpr int kTapsThreads = 192;                 // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kTapsStages = 2;
+constexpr int kTapsBBytes = kTapsN * 128;         // 18 KiB weight tile per 64-channel block
+constexpr int kTapsPStride = 148;                 // fp32 words per patch pixel in P (144 + 4: conflict-free 128-bit access)
+constexpr int kTapsPRows = kHaloPW * kHaloPH;     // 180
+constexpr int kTapsPBytes = (kTapsPRows * kTapsPStride * 4 + 1023) / 1024 * 1024;
+constexpr int kTapsSmem = kTapsStages * (kHaloABytes + kTapsBBytes) + kTapsPBytes + kBarBytes + 1024;
+constexpr int kTapsAcc1Col = 256;                 // TMEM column of the second accumulator (patch rows 128..255)
+
+__global__ void __launch_bounds__(kTapsThreads, 1) conv_taps_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // [A patches x stages | B tiles x stages | P | barriers].  The second UMMA of a K step reads patch rows 128..255; rows
+    // 180..255 lie past the patch (in the next slot / the B tiles): finite garbage that only reaches accumulator rows the
+    // epilogue never reads.
+    uint8_t* a_base = smem;
+    uint8_t* b_base = smem + kTapsStages * kHaloABytes;
+    const uint32_t p_u32 = ptx::smem_u32(b_base + kTapsStages * kTapsBBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + kTapsStages * kTapsBBytes + kTapsPBytes);
+    uint64_t* full_bar = bars;                   // [kTapsStages]
+    uint64_t* empty_bar = bars + kTapsStages;    // [kTapsStages]
+    uint64_t* tfull_bar = empty_bar + kTapsStages;
+    uint64_t* tempty_bar = tfull_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&p.w_map);
+        for (int s = 0; s < p.nseg; ++s) ptx::prefetch_tensormap(&p.seg[s].in_map[0]);
+        for (int i = 0; i < kTapsStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::mbar_init(tempty_bar, 4);  // one arrival per epilogue warp
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    const int w_first = static_cast<int>(blockIdx.x), w_step = static_cast<int>(gridDim.x), w_total = p.total_work;
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer: halo patch + weight tile per 64-ch block
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int work = w_first; work < w_total; work += w_step) {
+            const TileCoord t = decode_tile<false>(p, work, 0);
+            const ConvSeg& g = p.seg[t.seg];
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 11);
+                if (elect_one()) {
+                    ptx::mbar_expect_tx(&full_bar[stage], kHaloPW * kHaloPH * 128 + kTapsBBytes);
+                    ptx::tma_load_4d(a_base + stage * kHaloABytes, &g.in_map[0], &full_bar[stage], kc * kBlockK, t.x0 - 1,
+                                     t.y0 - 1, t.img);
+                    ptx::tma_load_2d(b_base + stage * kTapsBBytes, &p.w_map, &full_bar[stage], kc * kBlockK, 0);
+                }
+                __syncwarp();
+                if (++stage == kTapsStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ UMMA issuer
+        const uint32_t idesc = ptx::make_idesc_f16(kBlockM, kTapsN, p.fp16);
+        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, v1, SW128
+        const uint32_t a_lo0 = (ptx::smem_u32(a_base) >> 4) | (1u << 16);
+        const uint32_t b_lo0 = (ptx::smem_u32(b_base) >> 4) | (1u << 16);
+        int stage = 0;
+        uint32_t phase = 0, tphase = 0;
+        for (int work = w_first; work < w_total; work += w_step) {
+            ptx::mbar_wait(tempty_bar, tphase ^ 1, 12);  // the previous tile's accumulators have been dumped
+            ptx::tc_fence_after();
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                ptx::mbar_wait(&full_bar[stage], phase, 13);
+                ptx::tc_fence_after();
+                const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * (kHaloABytes >> 4);
+                const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(stage) * (kTapsBBytes >> 4);
+                const int ksteps = (kc == p.kchunks - 1) ? p.last_ksteps : kBlockK / 16;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        if (k < ksteps) {
+                            const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
+                            const uint64_t a0 = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + 2 * k);
+                            const uint64_t a1 = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + (16384 >> 4) + 2 * k);
+                            const uint32_t accumulate = (kc | k) != 0 ? 1u : 0u;
+                            ptx::umma_bf16(tmem_base, a0, bdesc, idesc, accumulate);                 // patch rows 0..127
+                            ptx::umma_bf16(tmem_base + kTapsAcc1Col, a1, bdesc, idesc, accumulate);  // patch rows 128..
+                        }
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                }
+                __syncwarp();
+                if (++stage == kTapsStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (elect_one()) ptx::umma_commit(tfull_bar);
+            __syncwarp();
+            tphase ^= 1;
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5): dump P, then shifted 9-tap sum
+        const int q = warp & 3;
+        const int m = q * 32 + lane;  // TMEM lane = patch row (first accumulator) and output pixel of the tile
+        uint32_t tphase = 0;
+        for (int work = w_first; work < w_total; work += w_step) {
+            const TileCoord t = decode_tile<false>(p, work, 0);
+            const ConvSeg& g = p.seg[t.seg];
+            ptx::mbar_wait(tfull_bar, tphase, 14);
+            ptx::tc_fence_after();
+            tphase ^= 1;
+            // ---- 1. TMEM -> P (fp32 [180][148]); patch rows 128..179 live in the second accumulator (warps of quarter 0 / 1)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int prow = a * 128 + m;
+                if (a == 1 && q >= 2) break;  // warp-uniform: rows 192.. do not exist
+                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * kTapsAcc1Col;
+                const uint32_t dst = p_u32 + prow * (kTapsPStride * 4);
+#pragma unroll
+                for (int c0 = 0; c0 < kTapsN; c0 += 32) {
+                    uint32_t v[32];
+                    if (c0 + 32 <= kTapsN) {
+                        ptx::tmem_ld32(t_addr + c0, v);
+                    } else {
+                        ptx::tmem_ld16(t_addr + c0, v);
+                    }
+                    ptx::tmem_ld_wait(v);
+                    if (prow < kTapsPRows) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            if (c0 + i < kTapsN) ptx::st_shared_v4(dst + (c0 + i) * 4, make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar);  // TMEM drained: the next tile's UMMAs may start
+            ptx::named_bar_sync(1, 128);                  // P complete
+            // ---- 2. out[y][x][:] = sum over the nine taps of the shifted partial sums (fixed order r, s)
+            const int ly = m >> 3, lx = m & 7;
+            const int oy = t.y0 + ly, ox = t.x0 + lx;
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int r = tap / 3, s = tap - 3 * r;
+                const uint32_t src = p_u32 + ((ly + r) * kHaloPW + lx + s) * (kTapsPStride * 4) + tap * 64;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 f = ptx::ld_shared_f4(src + 16 * i);
+                    acc[4 * i + 0] += f.x;
+                    acc[4 * i + 1] += f.y;
+                    acc[4 * i + 2] += f.z;
+                    acc[4 * i + 3] += f.w;
+                }
+            }
+            if (t.valid && oy < g.H && ox < g.W) {
+                float y[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(g.scale + i));
+                    const float4 bi = __ldg(reinterpret_cast<const float4*>(g.bias + i));
+                    y[i + 0] = fmaf(acc[i + 0], sc.x, bi.x);
+                    y[i + 1] = fmaf(acc[i + 1], sc.y, bi.y);
+                    y[i + 2] = fmaf(acc[i + 2], sc.z, bi.z);
+                    y[i + 3] = fmaf(acc[i + 3], sc.w, bi.w);
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+                }
+                const size_t pix = static_cast<size_t>(t.img * g.H + oy) * g.W + ox;
+                if (p.out_mode == 1) {
+                    float* dst = g.out_f32 + pix * g.out_pitch;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 o = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+                        if (g.lo != nullptr) {
+                            const float4 lo = __ldg(reinterpret_cast<const float4*>(g.lo + i));
+                            o.x = fmaxf(o.x, lo.x);
+                            o.y = fmaxf(o.y, lo.y);
+                            o.z = fmaxf(o.z, lo.z);
+                            o.w = fmaxf(o.w, lo.w);
+                        }
+                        *reinterpret_cast<float4*>(dst + i) = o;
+                    }
+                } else {
+                    uint4 o0, o1;
+                    o0.x = pack2_act(y[0], y[1], p.fp16);
+                    o0.y = pack2_act(y[2], y[3], p.fp16);
+                    o0.z = pack2_act(y[4], y[5], p.fp16);
+                    o0.w = pack2_act(y[6], y[7], p.fp16);
+                    o1.x = pack2_act(y[8], y[9], p.fp16);
+                    o1.y = pack2_act(y[10], y[11], p.fp16);
+                    o1.z = pack2_act(y[12], y[13], p.fp16);
+                    o1.w = pack2_act(y[14], y[15], p.fp16);
+                    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out16) + pix * g.out_pitch);
+                    dst[0] = o0;
+                    dst[1] = o1;
+                }
+            }
+            ptx::named_bar_sync(1, 128);  // every thread is done with P before the next tile's dump overwrites it
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 
 thread_local std::string g_conv_error;
@@ -817,6 +1057,27 @@ bool make_act_map_s2(CUtensorMap* map, const void* base, int wp, int B, int H, i
                              (cuuint64_t)H * W * pitch * 2};
     cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, 1, (cuuint32_t)th, 1};
     return encode(map, b, 5, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, fp16);
+}
+
+bool make_weight_map_taps(CUtensorMap* map, const void* base, int cin_pad, int fp16) {
+    cuuint64_t dims[2] = {(cuuint64_t)cin_pad, (cuuint64_t)kTapsN};
+    cuuint64_t strides[1] = {(cuuint64_t)cin_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kTapsN};
+    return encode(map, base, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, fp16);
+}
+
+// taps-in-N needs the fixed 16x8 halo tiling (same rule as the halo variant) and a 16-wide output
+static int g_taps_mode = -1;  // DD3D_CONV_TAPS=0 / dd3d_set_conv_policy("taps", 0) disables the variant (A/B, tests)
+
+void conv_set_taps(int mode) { g_taps_mode = (mode == 0 || mode == 1) ? mode : -1; }
+
+bool conv_taps_eligible(int taps, int stride, int cout_pad, int nseg, const int* Hs, const int* Ws) {
+    if (g_taps_mode < 0) {
+        const char* e = getenv("DD3D_CONV_TAPS");
+        g_taps_mode = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const int mode = g_taps_mode;
+    return mode && taps == 9 && stride == 1 && cout_pad == 16 && conv_prefer_halo(taps, stride, cout_pad, nseg, Hs, Ws);
 }
 
 int conv_halo_mode() { return 2; }  // one 128B-swizzled [18][10][64ch] box per 64-channel block
@@ -899,9 +1160,19 @@ void conv_finalize_params(ConvParams* p) {
             const char* e = getenv("DD3D_CONV_CTA2_MINN");
             min_n = e ? atoi(e) : 160;
         }
-        p->cta2 = (p->block_n >= min_n && tile >= 4 * 74) ? 1 : 0;
+        // ... or where the weight stream itself is the limiter: a deep-K layer re-reads its whole weight tensor from L2 for
+        // every 128-pixel tile (N x K x 2 B; 516 KB for the box3d predictor, N = 112, K = 2304 -> 16 GB per launch), a pair
+        // reads it once per 256 pixels.
+        static int deep_k = -1;
+        if (deep_k < 0) {
+            const char* e = getenv("DD3D_CONV_CTA2_DEEPK");
+            deep_k = e ? atoi(e) : 1;
+        }
+        const bool deep = deep_k && p->block_n >= 96 && p->taps * p->kchunks >= 36;
+        p->cta2 = ((p->block_n >= min_n || deep) && tile >= 4 * 74) ? 1 : 0;
     }
     if (p->cta2 && (tile < 2 || (p->block_n % 16) != 0)) p->cta2 = 0;
+    if (p->taps_n) p->cta2 = 0;
     p->pair_work = ((tile + 1) / 2) * p->n_blocks;
     const int stage_bytes = (p->halo ? 0 : kABytes) + (p->cta2 ? p->block_n / 2 : p->block_n) * 128;
     const int fixed = 2 * kStagingBytes + 1024 /*alignment slack*/ + kBarBytes + kSbBytes +
@@ -950,6 +1221,30 @@ cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
     }
     if (p.total_work <= 0) return cudaSuccess;
     if (p.total_work >= (1 << 24)) return cudaErrorInvalidValue;  // fast_div range of the tile decode
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char* e = getenv("DD3D_NO_PDL");
+        use_pdl = (e && atoi(e)) ? 0 : 1;
+    }
+    if (p.taps_n) {
+        static uint64_t taps_devices = 0;
+        if (first_use_on_device(&taps_devices)) {
+            cudaError_t e = cudaFuncSetAttribute(conv_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTapsSmem);
+            if (e != cudaSuccess) return e;
+        }
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(std::min(p.total_work, num_sms));
+        cfg.blockDim = dim3(kTapsThreads);
+        cfg.dynamicSmemBytes = kTapsSmem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = use_pdl ? 1 : 0;
+        return cudaLaunchKernelEx(&cfg, conv_taps_kernel, p);
+    }
     // CTA pairs: an even grid of 2-CTA clusters (one pair per TPC), each pair loops over pair-work items
     const int grid = p.cta2 ? 2 * std::min(p.pair_work, num_sms / 2) : std::min(p.total_work, num_sms);
     cudaLaunchConfig_t cfg;
@@ -960,11 +1255,6 @@ cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    static int use_pdl = -1;
-    if (use_pdl < 0) {
-        const char* e = getenv("DD3D_NO_PDL");
-        use_pdl = (e && atoi(e)) ? 0 : 1;
-    }
     if (use_pdl) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;

@@ -32,6 +32,7 @@ struct ConvSeg {
     int tile_begin;   // index of this segment's first M-tile
     int tw_shift;     // log2(tw)
     float inv_per_img, inv_tiles_x;  // reciprocals for the division-free tile decode (conv_finalize_params)
+    void* out16;          // taps-in-N variant, out_mode 0: NHWC 16-bit output written directly (pitch out_pitch)
     float* pool_partial;  // optional [B][tiles_per_image][4][pool_pitch] per-tile channel sums (eSE avg-pool), or nullptr
     int pool_pitch;
 };
@@ -60,6 +61,7 @@ struct ConvParams {
     int total_tiles;  // sum of M-tiles over the segments
     int pair_work;    // ceil(total_tiles / 2) * n_blocks
     float inv_n_blocks;
+    int taps_n;       // 1: taps-in-N variant for 3x3 stride-1 convs with <= 16 output channels (conv_taps_kernel)
     int fp16;         // 16-bit storage type of activations and weights: 0 bf16, 1 fp16 (act16.cuh)
 };
 static_assert(sizeof(ConvParams) <= 4096, "kernel parameter space");
@@ -84,6 +86,13 @@ bool make_act_map_halo(CUtensorMap* map, const void* base, int B, int H, int W, 
 // Policy: use the halo variant when its fixed 16x8 tiling costs at most 10 % more tiles than the best generic
 // tiling over all segments (env DD3D_CONV_MODE=generic|halo overrides, for tests).
 bool conv_prefer_halo(int taps, int stride, int block_n, int nseg, const int* Hs, const int* Ws);
+// Taps-in-N variant (3x3, stride 1, cout_pad == 16): the nine taps become GEMM columns -- ONE [180 patch pixels] x [9 x 16]
+// GEMM per 64-channel block instead of nine N = 16 GEMMs (the N = 16 UMMA costs ~50-90 cycles, the N = 144 one 72), then the
+// nine shifted partial sums are added from shared memory.  Weights: bf16 [9 * 16][cin_pad64] (row = tap * 16 + cout).
+constexpr int kTapsN = 144;
+bool make_weight_map_taps(CUtensorMap* map, const void* base, int cin_pad, int fp16 = 0);
+bool conv_taps_eligible(int taps, int stride, int cout_pad, int nseg, const int* Hs, const int* Ws);
+void conv_set_taps(int mode);  // 0 off, 1 on, -1 environment / default (on)
 // Fills num_stages / tmem_cols / total_work / tile bookkeeping from the already-set fields.
 void conv_finalize_params(ConvParams* p);
 cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream);

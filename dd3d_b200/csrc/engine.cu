@@ -139,6 +139,17 @@ const ConvLayer& Engine::conv_layer(const std::string& key, const std::vector<st
     cuda_check(cudaMemcpy(L.d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice), "upload conv weights");
     if (!make_weight_map(&L.w_map, L.d_w, L.ktot, L.cout_pad, L.block_n, fp16)) fail(DD3D_ERR_CUDA, conv_last_error());
     if (!make_weight_map(&L.w_map_half, L.d_w, L.ktot, L.cout_pad, L.block_n / 2, fp16)) fail(DD3D_ERR_CUDA, conv_last_error());
+    if (L.taps == 9 && L.cout_pad == 16) {
+        // taps-in-N copy (conv_taps_kernel): row = tap * 16 + cout, K = channels
+        std::vector<uint16_t> tp(static_cast<size_t>(kTapsN) * cin_pad, 0);
+        for (int co = 0; co < L.cout_pad; ++co)
+            for (int t = 0; t < 9; ++t)
+                for (int ci = 0; ci < cin_pad; ++ci)
+                    tp[(static_cast<size_t>(t) * 16 + co) * cin_pad + ci] = packed[(static_cast<size_t>(co) * L.taps + t) * cin_pad + ci];
+        L.d_w_taps = static_cast<__nv_bfloat16*>(dev_alloc(tp.size() * 2));
+        cuda_check(cudaMemcpy(L.d_w_taps, tp.data(), tp.size() * 2, cudaMemcpyHostToDevice), "upload taps-in-N weights");
+        if (!make_weight_map_taps(&L.w_map_taps, L.d_w_taps, cin_pad, fp16)) fail(DD3D_ERR_CUDA, conv_last_error());
+    }
     return convs.emplace(key, L).first->second;
 }
 
@@ -204,16 +215,36 @@ struct Builder {
     Plan* P;
     bool dry;       // true: only size the arena and create layers (no tensor maps, no ops)
     uint8_t* base;  // arena base (nullptr when dry)
-    size_t off = 0;
+    size_t off = 0;  // bump offset of the PERSISTENT region (input, fp32 maps, scratch); starts after the activation arena
     int B;
+    // Activation arena with liveness reuse: a first (dry, tracing) walk of the graph records for every bf16 activation
+    // buffer the first and last op that touches it; plan_arena() then packs buffers with disjoint lifetimes into the same
+    // memory (48 GB -> ~15 GB for V2-99 at B = 32), and the real walk hands out those offsets in the same order.
+    std::vector<ArenaBuf>* bufs = nullptr;
+    bool tracing = false;
+    int next_buf = 0, op_idx = 0;
 
     View alloc(int H, int W, int C) {
         View v;
         v.B = B; v.H = H; v.W = W; v.C = C; v.pitch = C;
-        const size_t bytes = static_cast<size_t>(B) * H * W * C * 2;
-        v.ptr = dry ? nullptr : reinterpret_cast<__nv_bfloat16*>(base + off);
-        off += round_up_sz(bytes, 1024);
+        const size_t bytes = round_up_sz(static_cast<size_t>(B) * H * W * C * 2, 1024);
+        v.buf = next_buf++;
+        if (tracing) {
+            ArenaBuf b;
+            b.bytes = bytes;
+            bufs->push_back(b);
+        }
+        v.ptr = dry ? nullptr : reinterpret_cast<__nv_bfloat16*>(base + (*bufs)[v.buf].offset);
         return v;
+    }
+    void touch(const View& v) {  // op `op_idx` reads or writes v
+        if (!tracing || v.buf < 0) return;
+        ArenaBuf& b = (*bufs)[v.buf];
+        b.first = std::min(b.first, op_idx);
+        b.last = std::max(b.last, op_idx);
+    }
+    void persist(const View& v) {
+        if (tracing && v.buf >= 0) (*bufs)[v.buf].persistent = true;
     }
     float* alloc_f32(size_t n) {
         float* p = dry ? nullptr : reinterpret_cast<float*>(base + off);
@@ -243,6 +274,12 @@ struct Builder {
     };
 
     void conv(const ConvLayer& L, int stride, bool relu, std::vector<SegSpec>& segs, bool f32_out) {
+        for (auto& sp : segs) {
+            touch(sp.in);
+            if (!f32_out) touch(sp.out);
+            if (sp.has_res) touch(sp.res);
+        }
+        ++op_idx;
         if (dry) return;
         Op op;
         op.type = Op::CONV;
@@ -267,6 +304,7 @@ struct Builder {
                 ws[s] = segs[s].in.W / stride;
             }
             p.halo = conv_prefer_halo(L.taps, stride, L.block_n, p.nseg, hs, ws) ? conv_halo_mode() : 0;
+            p.taps_n = (L.d_w_taps != nullptr && conv_taps_eligible(L.taps, stride, L.cout_pad, p.nseg, hs, ws)) ? 1 : 0;
         }
         for (int s = 0; s < p.nseg; ++s) {
             SegSpec& sp = segs[s];
@@ -306,6 +344,8 @@ struct Builder {
                     fail(DD3D_ERR_INVALID, "conv output view mismatch");
                 if (!make_act_map(&g.out_map, sp.out.ptr, B, Ho, Wo, sp.out.C, sp.out.pitch, g.th, g.tw, E->fp16))
                     fail(DD3D_ERR_CUDA, conv_last_error());
+                g.out16 = sp.out.ptr;
+                g.out_pitch = sp.out.pitch;
             }
             if (sp.has_res) {
                 g.residual = sp.res.ptr;
@@ -316,7 +356,7 @@ struct Builder {
             }
         }
         conv_finalize_params(&p);
-        p.w_map = p.cta2 ? L.w_map_half : L.w_map;
+        p.w_map = p.taps_n ? L.w_map_taps : (p.cta2 ? L.w_map_half : L.w_map);
         for (int s = 0; s < p.nseg; ++s)
             op.flops += 2.0 * B * p.seg[s].H * p.seg[s].W * static_cast<double>(L.cout) * L.cin * L.taps;
         if (!f32_out) {
@@ -344,6 +384,9 @@ struct Builder {
     }
 
     void maxpool(View in, View out, int ksize) {
+        touch(in);
+        touch(out);
+        ++op_idx;
         if (dry) return;
         Op op;
         op.type = Op::POOL;
@@ -355,6 +398,9 @@ struct Builder {
         P->ops.push_back(op);
     }
     void relu(View in, View out) {
+        touch(in);
+        touch(out);
+        ++op_idx;
         if (dry) return;
         Op op;
         op.type = Op::RELU;
@@ -429,6 +475,8 @@ struct Builder {
 
     void stem(const std::string& wname, const std::string& bn, View in4, View out, int ksize, int stride) {
         const StemLayer& S = E->stem_layer(wname, bn, ksize, stride);
+        touch(out);
+        ++op_idx;
         if (dry) return;
         Op op;
         op.type = Op::STEM;
@@ -512,6 +560,10 @@ struct Builder {
         float* tile_partial = alloc_f32(static_cast<size_t>(B) * T * xt.C);
         float* sums = alloc_f32(static_cast<size_t>(B) * xt.C);
         float* gate = alloc_f32(static_cast<size_t>(B) * xt.C);
+        touch(xt);
+        if (identity) touch(*identity);
+        touch(dst);
+        ++op_idx;
         if (dry) return;
         Op& cv = P->ops.back();
         if (cv.type != Op::CONV || cv.conv.nseg != 1 || cv.conv.halo || cv.conv.out_mode != 0 ||
@@ -554,17 +606,20 @@ struct Builder {
             }
             prev = lat;
             res[i] = alloc(c.H, c.W, 256);
+            persist(res[i]);
             conv1(p + ".fpn_output" + st, p + ".fpn_output" + st + ".norm", false, lat, res[i], 3, 1, false);
         }
         *outs = res;
         const View& p5 = res[n - 1];
         View p6 = alloc(p5.H / 2, p5.W / 2, 256);
+        persist(p6);
         conv1(p + ".top_block.p6", "", true, p5, p6, 3, 2, false);
         outs->push_back(p6);
         if (E->desc.arch == DD3D_ARCH_DLA34) {
             View r6 = alloc(p6.H, p6.W, 256);
             relu(p6, r6);
             View p7 = alloc(p6.H / 2, p6.W / 2, 256);
+            persist(p7);
             conv1(p + ".top_block.p7", "", true, r6, p7, 3, 2, false);
             outs->push_back(p7);
         }
@@ -599,10 +654,9 @@ struct Builder {
         const int cls_pitch = round_up(C + (nusc ? kNumAttributes + 1 : 0), 16), b3d_pitch = round_up(11 * C, 16);
         P->cls_pitch = cls_pitch;
         P->b3d_pitch = b3d_pitch;
+        // each tower is followed at once by its predictor, so that its ping-pong buffers die before the next tower starts
+        // (arena reuse); the launch order differs from fcos2d.py:130-156 / fcos3d.py:160-188, the arithmetic does not
         std::vector<View> cls_t, box_t, b3d_t;
-        tower("fcos2d_head.cls_tower", feats, &cls_t);
-        tower("fcos2d_head.box2d_tower", feats, &box_t);
-        tower("fcos3d_head.box3d_tower", feats, &b3d_t);
         for (int l = 0; l < L; ++l) {
             const size_t hw = static_cast<size_t>(B) * feats[l].H * feats[l].W;
             P->cls_map[l] = alloc_f32(hw * cls_pitch);
@@ -614,6 +668,7 @@ struct Builder {
         // cls_logits (fcos2d.py:96,142): bias only, shared across levels.  NuscenesDD3D adds attr_logits (3) and
         // relu(speed) (1) on the same tower output (nuscenes_dd3d.py:311-312,380-383): fused as extra GEMM columns
         // [cls C | attr 3 | speed 1] of the one predictor conv (still N = 16 for the 10 nuScenes classes).
+        tower("fcos2d_head.cls_tower", feats, &cls_t);
         {
             std::vector<std::string> names = {"fcos2d_head.cls_logits"};
             if (nusc) {
@@ -647,6 +702,7 @@ struct Builder {
             conv(Lc, 1, false, segs, true);
         }
         // [box2d_reg (4) | centerness (1)] on the box2d tower: relu(scale_l * (conv + b)) / conv + b (fcos2d.py:143-152)
+        tower("fcos2d_head.box2d_tower", feats, &box_t);
         {
             const ConvLayer& Lb = E->conv_layer("fcos2d_head.box2d_reg+centerness",
                                                 {"fcos2d_head.box2d_reg", "fcos2d_head.centerness"}, 256, 3);
@@ -677,6 +733,7 @@ struct Builder {
         }
         // [quat 4C | ctr 2C | depth C | size 3C | conf C] on the box3d tower with the per-level Scale/Offset folded
         // (fcos3d.py:166-180; PER_LEVEL_PREDICTORS False -> predictor index 0)
+        tower("fcos3d_head.box3d_tower", feats, &b3d_t);
         {
             const ConvLayer& L3 = E->conv_layer(
                 "fcos3d_head.box3d_all",
@@ -762,42 +819,102 @@ const EseLayer& Engine::ese_layer(const std::string& fc, int C) {
 
 int Engine::size_divisibility() const { return desc.arch == DD3D_ARCH_DLA34 ? 128 : 64; }
 
+// Offsets for the activation buffers: largest first, each at the lowest address where it does not collide (in address
+// AND lifetime) with an already placed one -- the greedy interval packing of static memory planners.  Without reuse
+// (opt_workspace_reuse = 0) buffers are simply laid out one after the other.  Returns the arena size.
+static size_t plan_arena(std::vector<ArenaBuf>& bufs, bool reuse) {
+    size_t total = 0;
+    if (!reuse) {
+        for (ArenaBuf& b : bufs) {
+            b.offset = total;
+            total += b.bytes;
+        }
+        return total;
+    }
+    const int last_op = 1 << 29;
+    for (ArenaBuf& b : bufs) {
+        if (b.last < 0) {  // never touched by an op (cannot happen for a well-formed graph): keep it alive throughout
+            b.first = 0;
+            b.last = last_op;
+        }
+        if (b.persistent) b.last = last_op;
+    }
+    std::vector<int> order(bufs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        return bufs[a].bytes != bufs[b].bytes ? bufs[a].bytes > bufs[b].bytes : a < b;
+    });
+    std::vector<int> placed;
+    for (int id : order) {
+        ArenaBuf& b = bufs[id];
+        std::vector<std::pair<size_t, size_t>> busy;  // address ranges of placed buffers alive at the same time
+        for (int o : placed) {
+            const ArenaBuf& q = bufs[o];
+            if (q.first <= b.last && b.first <= q.last) busy.emplace_back(q.offset, q.offset + q.bytes);
+        }
+        std::sort(busy.begin(), busy.end());
+        size_t at = 0;
+        for (auto& r : busy) {
+            if (at + b.bytes <= r.first) break;
+            at = std::max(at, r.second);
+        }
+        b.offset = at;
+        total = std::max(total, at + b.bytes);
+        placed.push_back(id);
+    }
+    return total;
+}
+
 size_t Engine::build(Plan* P, int B, int Hs, int Ws, void* workspace, bool dry) {
     const int d = size_divisibility();
     const int Hp = round_up(Hs, d), Wp = round_up(Ws, d);
-    P->B = B; P->Hs = Hs; P->Ws = Ws; P->Hp = Hp; P->Wp = Wp;
-    P->ops.clear();
-    Builder bld;
-    bld.E = this;
-    bld.P = P;
-    bld.dry = dry;
-    bld.base = static_cast<uint8_t*>(workspace);
-    bld.B = B;
-    View input;
-    input.B = B; input.H = Hp; input.W = Wp; input.C = 4; input.pitch = 4;
-    input.ptr = dry ? nullptr : reinterpret_cast<__nv_bfloat16*>(bld.base + bld.off);
-    bld.off += round_up_sz(static_cast<size_t>(B) * Hp * Wp * 4 * 2, 1024);
-    P->input = input;
-    std::vector<View> feats, fpn;
-    if (desc.arch == DD3D_ARCH_DLA34) {
-        bld.build_dla34(input, &feats);
-        bld.build_fpn(feats, 3, &fpn);
-    } else {
-        bld.build_v2_99(input, &feats);
-        bld.build_fpn(feats, 2, &fpn);
+    std::vector<ArenaBuf> bufs;
+    size_t arena_bytes = 0, total = 0;
+    // pass 0: trace (liveness of every activation buffer, layer creation); pass 1: the real walk with the planned offsets
+    for (int pass = 0; pass < (dry ? 1 : 2); ++pass) {
+        const bool tracing = pass == 0;
+        P->B = B; P->Hs = Hs; P->Ws = Ws; P->Hp = Hp; P->Wp = Wp;
+        P->ops.clear();
+        Builder bld;
+        bld.E = this;
+        bld.P = P;
+        bld.dry = tracing;
+        bld.tracing = tracing;
+        bld.bufs = &bufs;
+        bld.base = tracing ? nullptr : static_cast<uint8_t*>(workspace);
+        bld.B = B;
+        bld.off = arena_bytes;  // persistent region follows the activation arena (0 while tracing: sizes only)
+        View input;
+        input.B = B; input.H = Hp; input.W = Wp; input.C = 4; input.pitch = 4;
+        input.ptr = tracing ? nullptr : reinterpret_cast<__nv_bfloat16*>(bld.base + bld.off);
+        bld.off += round_up_sz(static_cast<size_t>(B) * Hp * Wp * 4 * 2, 1024);
+        P->input = input;
+        std::vector<View> feats, fpn;
+        if (desc.arch == DD3D_ARCH_DLA34) {
+            bld.build_dla34(input, &feats);
+            bld.build_fpn(feats, 3, &fpn);
+        } else {
+            bld.build_v2_99(input, &feats);
+            bld.build_fpn(feats, 2, &fpn);
+        }
+        if (static_cast<int>(fpn.size()) != kLevels) fail(DD3D_ERR_STATE, "internal: expected 5 FPN levels");
+        for (int l = 0; l < kLevels; ++l) P->fpn[l] = fpn[l];
+        bld.build_heads(fpn);
+        // detection scratch + staging for the host-facing path
+        P->detect_scratch = bld.alloc_bytes(decode_scratch_bytes(B, desc.pre_nms_topk));
+        P->d_K = static_cast<float*>(bld.alloc_bytes(static_cast<size_t>(B) * 9 * 4));
+        P->d_sizes = static_cast<int32_t*>(bld.alloc_bytes(static_cast<size_t>(B) * 4 * 4));
+        P->d_out = static_cast<Det*>(bld.alloc_bytes(static_cast<size_t>(B) * desc.out_cap * sizeof(Det)));
+        P->d_counts = static_cast<int32_t*>(bld.alloc_bytes(static_cast<size_t>(B) * 4));
+        P->d_images = bld.alloc_bytes(static_cast<size_t>(B) * 3 * Hs * Ws * 4);
+        P->d_canon = nullptr;
+        if (tracing) {
+            arena_bytes = plan_arena(bufs, opt_workspace_reuse != 0);
+            total = arena_bytes + bld.off;
+        }
     }
-    if (static_cast<int>(fpn.size()) != kLevels) fail(DD3D_ERR_STATE, "internal: expected 5 FPN levels");
-    for (int l = 0; l < kLevels; ++l) P->fpn[l] = fpn[l];
-    bld.build_heads(fpn);
-    // detection scratch + staging for the host-facing path
-    P->detect_scratch = bld.alloc_bytes(decode_scratch_bytes(B, desc.pre_nms_topk));
-    P->d_K = static_cast<float*>(bld.alloc_bytes(static_cast<size_t>(B) * 9 * 4));
-    P->d_sizes = static_cast<int32_t*>(bld.alloc_bytes(static_cast<size_t>(B) * 4 * 4));
-    P->d_out = static_cast<Det*>(bld.alloc_bytes(static_cast<size_t>(B) * desc.out_cap * sizeof(Det)));
-    P->d_counts = static_cast<int32_t*>(bld.alloc_bytes(static_cast<size_t>(B) * 4));
-    P->d_images = bld.alloc_bytes(static_cast<size_t>(B) * 3 * Hs * Ws * 4);
-    P->d_canon = nullptr;
-    return bld.off;
+    P->arena_bytes = arena_bytes;
+    return total;
 }
 
 void Engine::finalize() {

@@ -30,6 +30,16 @@ struct HostTensor {
 struct View {
     __nv_bfloat16* ptr = nullptr;
     int B = 0, H = 0, W = 0, C = 0, pitch = 0;
+    int buf = -1;  // arena buffer this view (or channel slice) lives in: index into the plan's liveness table
+};
+
+// One activation buffer of the workspace arena: its size, the first / last engine op that touches it (liveness interval,
+// inclusive) and the offset the planner gave it.  Buffers whose intervals do not intersect share memory.
+struct ArenaBuf {
+    size_t bytes = 0;
+    int first = 1 << 30, last = -1;
+    bool persistent = false;  // FPN outputs: kept for dd3d_get_tensor after the forward
+    size_t offset = 0;
 };
 
 struct ConvLayer {
@@ -37,6 +47,8 @@ struct ConvLayer {
     __nv_bfloat16* d_w;
     CUtensorMap w_map;
     CUtensorMap w_map_half;  // box of block_n / 2 rows: each CTA of a pair loads half of the weight tile
+    __nv_bfloat16* d_w_taps = nullptr;  // taps-in-N layout [9 * 16][cin_pad64] (3x3 layers with cout_pad == 16 only)
+    CUtensorMap w_map_taps;
 };
 struct Epilogue {
     float* d_scale;
@@ -76,6 +88,7 @@ struct Plan {
     int B = 0, Hs = 0, Ws = 0, Hp = 0, Wp = 0;
     void* owned_workspace = nullptr;
     size_t owned_bytes = 0;
+    size_t arena_bytes = 0;  // part of the workspace that holds the liveness-packed bf16 activations
     void* slot1 = nullptr;  // second set of host-path staging buffers (dd3d_submit_host slot 1), allocated on first use
     void* s1_images = nullptr;
     float* s1_K = nullptr;
@@ -155,6 +168,7 @@ class Engine {
     bool finalized = false;
     int opt_do_postprocess = 1;
     int opt_profile = 0;
+    int opt_workspace_reuse = 1;  // 0: bump allocation, every op output keeps its own memory (stage-level tests / debugging)
     int opt_workspace_fill = -1;  // >= 0: byte the whole arena is filled with at dd3d_plan (poison test)
     std::vector<cudaEvent_t> prof_ev;
     std::vector<int> prof_cat;

@@ -16,27 +16,72 @@ namespace dd3d {
 namespace {
 
 // ------------------------------------------------------------------------------------------ preprocess
+// One thread = 4 consecutive pixels of a row: three 4-byte (uint8 planes) or 16-byte (fp32 planes) loads and one 32-byte
+// store.  (One pixel per thread -- 3 single-byte loads, one 8-byte store -- ran at 20 % of the HBM roof, BENCH_r01.)
 template <typename T>
-__global__ void preprocess_kernel(const T* __restrict__ src, const int* __restrict__ sizes, __nv_bfloat16* __restrict__ dst,
-                                  int B, int Hs, int Ws, int Hp, int Wp, int size_stride, float m0, float m1, float m2,
-                                  float s0, float s1, float s2, int fp16) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) preprocess_kernel(const T* __restrict__ src, const int* __restrict__ sizes,
+                                                         __nv_bfloat16* __restrict__ dst, int B, int Hs, int Ws, int Hp, int Wp,
+                                                         int size_stride, float m0, float m1, float m2, float s0, float s1,
+                                                         float s2, int fp16, int vec_ok) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
     const int b = blockIdx.z;
-    if (x >= Wp) return;
+    if (x0 >= Wp) return;
     const int h = sizes[size_stride * b], w = sizes[size_stride * b + 1];
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    if (y < h && x < w) {
+    float v[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[c][j] = 0.f;
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+    if (y < h && x0 < w) {
         const size_t plane = static_cast<size_t>(Hs) * Ws;
-        const T* p = src + static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(y) * Ws + x;
-        v0 = (static_cast<float>(p[0]) - m0) / s0;
-        v1 = (static_cast<float>(p[plane]) - m1) / s1;
-        v2 = (static_cast<float>(p[2 * plane]) - m2) / s2;
+        const T* p = src + static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(y) * Ws + x0;
+        if (vec_ok && x0 + 3 < w) {  // Ws % 4 == 0 and an aligned base: one vector load per plane
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (sizeof(T) == 1) {
+                    const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(p + c * plane));
+                    v[c][0] = q.x; v[c][1] = q.y; v[c][2] = q.z; v[c][3] = q.w;
+                } else {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(p + c * plane));
+                    v[c][0] = q.x; v[c][1] = q.y; v[c][2] = q.z; v[c][3] = q.w;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[c][j] = (v[c][j] - mean[c]) / stdv[c];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (x0 + j < w) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[c][j] = (static_cast<float>(p[c * plane + j]) - mean[c]) / stdv[c];
+                }
+            }
+        }
     }
-    uint2 o;
-    o.x = pack2_act(v0, v1, fp16);
-    o.y = pack2_act(v2, 0.f, fp16);
-    *reinterpret_cast<uint2*>(dst + (static_cast<size_t>(b * Hp + y) * Wp + x) * 4) = o;
+    __nv_bfloat16* d = dst + (static_cast<size_t>(b * Hp + y) * Wp + x0) * 4;
+    if (x0 + 3 < Wp) {
+        uint4 o0, o1;
+        o0.x = pack2_act(v[0][0], v[1][0], fp16); o0.y = pack2_act(v[2][0], 0.f, fp16);
+        o0.z = pack2_act(v[0][1], v[1][1], fp16); o0.w = pack2_act(v[2][1], 0.f, fp16);
+        o1.x = pack2_act(v[0][2], v[1][2], fp16); o1.y = pack2_act(v[2][2], 0.f, fp16);
+        o1.z = pack2_act(v[0][3], v[1][3], fp16); o1.w = pack2_act(v[2][3], 0.f, fp16);
+        reinterpret_cast<uint4*>(d)[0] = o0;
+        reinterpret_cast<uint4*>(d)[1] = o1;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (x0 + j < Wp) {
+                uint2 o;
+                o.x = pack2_act(v[0][j], v[1][j], fp16);
+                o.y = pack2_act(v[2][j], 0.f, fp16);
+                reinterpret_cast<uint2*>(d)[j] = o;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ max-pool
@@ -168,37 +213,54 @@ __global__ void ese_fc_kernel(const float* __restrict__ partial, const float* __
     }
 }
 
-// out = bf16(x * gate[b][c] (+ identity))
-__global__ void ese_scale_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gate,
-                                 const __nv_bfloat16* __restrict__ identity, __nv_bfloat16* __restrict__ out, int B, int HW,
-                                 int C, int x_pitch, int id_pitch, int out_pitch, int fp16) {
+// out = 16-bit(x * gate[b][c] (+ identity)).  Pure streaming (2-3 tensor passes): every thread keeps kEseUnroll
+// independent 16-byte loads of x (and of the identity) in flight per iteration -- one load per thread left the kernel at
+// 66 % of the HBM roof (BENCH_r01).
+constexpr int kEseUnroll = 4;
+__global__ void __launch_bounds__(256) ese_scale_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gate,
+                                                        const __nv_bfloat16* __restrict__ identity,
+                                                        __nv_bfloat16* __restrict__ out, int B, int HW, int C, int x_pitch,
+                                                        int id_pitch, int out_pitch, int fp16) {
     const int vc = C >> 3;
     const size_t total = static_cast<size_t>(B) * HW * vc;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int v = static_cast<int>(i % vc);
-        const size_t pix = i / vc;
-        const int b = static_cast<int>(pix / HW);
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pix * x_pitch + v * 8));
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * C + v * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * C + v * 8 + 4));
-        float f[8];
-        float2 t;
-        t = unpack2_act(u.x, fp16); f[0] = t.x * g0.x; f[1] = t.y * g0.y;
-        t = unpack2_act(u.y, fp16); f[2] = t.x * g0.z; f[3] = t.y * g0.w;
-        t = unpack2_act(u.z, fp16); f[4] = t.x * g1.x; f[5] = t.y * g1.y;
-        t = unpack2_act(u.w, fp16); f[6] = t.x * g1.z; f[7] = t.y * g1.w;
-        if (identity != nullptr) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(identity + pix * id_pitch + v * 8));
-            t = unpack2_act(q.x, fp16); f[0] += t.x; f[1] += t.y;
-            t = unpack2_act(q.y, fp16); f[2] += t.x; f[3] += t.y;
-            t = unpack2_act(q.z, fp16); f[4] += t.x; f[5] += t.y;
-            t = unpack2_act(q.w, fp16); f[6] += t.x; f[7] += t.y;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i0 < total; i0 += stride * kEseUnroll) {
+        uint4 u[kEseUnroll], q[kEseUnroll];
+        size_t pix[kEseUnroll];
+        int v[kEseUnroll];
+#pragma unroll
+        for (int k = 0; k < kEseUnroll; ++k) {
+            const size_t i = i0 + k * stride;
+            v[k] = static_cast<int>(i % vc);
+            pix[k] = i / vc;
+            if (i < total) {
+                u[k] = __ldg(reinterpret_cast<const uint4*>(x + pix[k] * x_pitch + v[k] * 8));
+                if (identity != nullptr) q[k] = __ldg(reinterpret_cast<const uint4*>(identity + pix[k] * id_pitch + v[k] * 8));
+            }
         }
-        uint4 o;
-        o.x = pack2_act(f[0], f[1], fp16); o.y = pack2_act(f[2], f[3], fp16); o.z = pack2_act(f[4], f[5], fp16);
-        o.w = pack2_act(f[6], f[7], fp16);
-        *reinterpret_cast<uint4*>(out + pix * out_pitch + v * 8) = o;
+#pragma unroll
+        for (int k = 0; k < kEseUnroll; ++k) {
+            if (i0 + k * stride >= total) break;
+            const int b = static_cast<int>(pix[k] / HW);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * C + v[k] * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * C + v[k] * 8 + 4));
+            float f[8];
+            float2 t;
+            t = unpack2_act(u[k].x, fp16); f[0] = t.x * g0.x; f[1] = t.y * g0.y;
+            t = unpack2_act(u[k].y, fp16); f[2] = t.x * g0.z; f[3] = t.y * g0.w;
+            t = unpack2_act(u[k].z, fp16); f[4] = t.x * g1.x; f[5] = t.y * g1.y;
+            t = unpack2_act(u[k].w, fp16); f[6] = t.x * g1.z; f[7] = t.y * g1.w;
+            if (identity != nullptr) {
+                t = unpack2_act(q[k].x, fp16); f[0] += t.x; f[1] += t.y;
+                t = unpack2_act(q[k].y, fp16); f[2] += t.x; f[3] += t.y;
+                t = unpack2_act(q[k].z, fp16); f[4] += t.x; f[5] += t.y;
+                t = unpack2_act(q[k].w, fp16); f[6] += t.x; f[7] += t.y;
+            }
+            uint4 o;
+            o.x = pack2_act(f[0], f[1], fp16); o.y = pack2_act(f[2], f[3], fp16); o.z = pack2_act(f[4], f[5], fp16);
+            o.w = pack2_act(f[6], f[7], fp16);
+            *reinterpret_cast<uint4*>(out + pix[k] * out_pitch + v[k] * 8) = o;
+        }
     }
 }
 
@@ -228,15 +290,18 @@ inline int grid_for(size_t total, int block, int num_sms) {
 cudaError_t launch_preprocess(const void* src, int src_is_u8, const int* d_sizes, int size_stride, __nv_bfloat16* dst,
                               int B, int Hs, int Ws, int Hp, int Wp, const float mean[3], const float std[3],
                               cudaStream_t stream, int fp16) {
-    dim3 block(256), grid((Wp + 255) / 256, Hp, B);
+    dim3 block(256), grid((Wp + 1023) / 1024, Hp, B);
+    const int esz = src_is_u8 ? 1 : 4;
+    const int vec_ok = (Ws % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % (4 * esz) == 0) &&
+                       ((static_cast<size_t>(Hs) * Ws) % 4 == 0);
     if (src_is_u8) {
-        preprocess_kernel<uint8_t><<<grid, block, 0, stream>>>(static_cast<const uint8_t*>(src), d_sizes, dst, B, Hs,
-                                                               Ws, Hp, Wp, size_stride, mean[0], mean[1], mean[2], std[0],
-                                                               std[1], std[2], fp16);
+        preprocess_kernel<uint8_t><<<grid, block, 0, stream>>>(static_cast<const uint8_t*>(src), d_sizes, dst, B, Hs, Ws, Hp, Wp,
+                                                               size_stride, mean[0], mean[1], mean[2], std[0], std[1], std[2],
+                                                               fp16, vec_ok);
     } else {
-        preprocess_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(src), d_sizes, dst, B, Hs, Ws,
-                                                             Hp, Wp, size_stride, mean[0], mean[1], mean[2], std[0], std[1],
-                                                             std[2], fp16);
+        preprocess_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(src), d_sizes, dst, B, Hs, Ws, Hp, Wp,
+                                                             size_stride, mean[0], mean[1], mean[2], std[0], std[1], std[2], fp16,
+                                                             vec_ok);
     }
     return cudaGetLastError();
 }
@@ -272,7 +337,7 @@ cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, c
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t total = static_cast<size_t>(B) * HW * vc;
-    ese_scale_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
+    ese_scale_kernel<<<grid_for((total + kEseUnroll - 1) / kEseUnroll, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
                                                                       id_pitch, out_pitch, fp16);
     return cudaGetLastError();
 }
@@ -290,7 +355,7 @@ cudaError_t launch_ese_fused(const __nv_bfloat16* x, int x_pitch, const float* t
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t total = static_cast<size_t>(B) * HW * (C / 8);
-    ese_scale_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
+    ese_scale_kernel<<<grid_for((total + kEseUnroll - 1) / kEseUnroll, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
                                                                       id_pitch, out_pitch, fp16);
     return cudaGetLastError();
 }

@@ -145,13 +145,16 @@ int dd3d_wait_host(dd3d_handle h, int slot);
 int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags);
 /* Runtime switches the reference's callers toggle on the meta-arch: "do_postprocess" (postprocess_in_inference,
  * scripts/train.py:206-209, test_time_augmentation.py:107), "do_nms" (core.py:134), "profile" (see
- * dd3d_get_profile), and "workspace_fill" (0..255: dd3d_plan fills the whole workspace with that byte first, -1 = off;
+ * dd3d_get_profile), "workspace_reuse" (default 1: activation buffers with disjoint lifetimes share workspace memory --
+ * after a forward only "input", "p0".."p4" and the head maps of dd3d_get_tensor are intact; 0: every op output keeps its own
+ * memory, for stage-level tests; applies to plans made afterwards), and "workspace_fill" (0..255: dd3d_plan fills the whole workspace with that byte first, -1 = off;
  * the poison test of tests/test_determinism_gpu.py: results must not depend on what the arena held). */
 int dd3d_set_option(dd3d_handle h, const char* name, int value);
 /* Process-wide kernel-selection policy for plans / operator calls made afterwards (tests, A/B measurements):
  * "cta2" = 0 single-CTA conv kernel everywhere, 1 CTA pairs (tcgen05.mma.cta_group::2) wherever legal, 2 auto (default:
  * pairs for block_n >= 160 and >= 296 tiles), -1 back to the DD3D_CONV_CTA2 environment setting.
- * "op_fp16" = 1: the dd3d_op_* entry points below treat their 16-bit buffers as fp16 (default 0: bf16). */
+ * "op_fp16" = 1: the dd3d_op_* entry points below treat their 16-bit buffers as fp16 (default 0: bf16).
+ * "taps" = 0: 3x3 convs with <= 16 output channels use the per-tap kernels instead of the taps-in-N kernel (default 1). */
 int dd3d_set_conv_policy(const char* name, int value);
 /* Number of kernel launches one dd3d_forward enqueues (for the bench's gpu_launches claim). */
 int dd3d_launches_per_forward(dd3d_handle h);

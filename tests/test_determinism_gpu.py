@@ -29,13 +29,14 @@ def _bits(t):
     return t.view(torch.int16) if t.element_size() == 2 else t.view(torch.int32)
 
 
-def _run(case, dtype, fill):
+def _run(case, dtype, fill, reuse=1):
     cfg = case_cfg(case, act_dtype=dtype)
     model = DD3DB200(cfg).to("cuda")
     model.load_state_dict(make_state_dict(cfg))
     L = lib.load()
     h = model._engine()
     lib.check(L.dd3d_set_option(h, b"workspace_fill", fill), h)
+    lib.check(L.dd3d_set_option(h, b"workspace_reuse", reuse), h)
     out = model(case_inputs(case))
     torch.cuda.synchronize()
     assert model.overflow_flags() == 0
@@ -66,6 +67,28 @@ def test_poisoned_workspace_changes_nothing(case, dtype):
     for k in a:
         assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), f"{case} {dtype}: {k} depends on the arena contents"
     assert sum(a[k].shape[0] for k in a if k.startswith("dets")) > 0
+
+
+@pytest.mark.parametrize("case,dtype", [("dla34", "bf16"), ("v2_99", "bf16")])
+def test_workspace_liveness_reuse_changes_nothing_but_the_footprint(case, dtype):
+    """Activation buffers with disjoint lifetimes share arena memory (default); with reuse off every op output has its own.
+    Persistent tensors (input, FPN outputs, head maps) and the detections must be bit-identical; the arena must shrink."""
+    a = _run(case, dtype, 0xFF, reuse=1)
+    b = _run(case, dtype, 0xFF, reuse=0)
+    keep = [k for k in a if not k.startswith("op")]
+    assert len(keep) >= 1 + 15 + 1
+    for k in keep:
+        assert torch.equal(a[k], b[k]), f"{case}: {k} differs between reuse on / off"
+    cfg = case_cfg(case, act_dtype=dtype)
+    model = DD3DB200(cfg).to("cuda")
+    model.load_state_dict(make_state_dict(cfg))
+    L = lib.load()
+    h = model._engine()
+    sizes = {}
+    for reuse in (1, 0):
+        lib.check(L.dd3d_set_option(h, b"workspace_reuse", reuse), h)
+        sizes[reuse] = L.dd3d_workspace_bytes(h, 8, 384, 1280)
+    assert 0 < sizes[1] < 0.6 * sizes[0], sizes
 
 
 def _probe(env_extra):

@@ -346,6 +346,37 @@ def _decode_case(arch, rate, seed, flags):
             np.testing.assert_allclose(got[:, 5], ref["score3d"], rtol=1e-5)
 
 
+@pytest.mark.parametrize("cin,cout,H,W,B,f32", [(256, 14, 30, 50, 2, True), (256, 5, 15, 25, 3, True), (256, 16, 48, 160, 1, True),
+                                                  (16, 16, 64, 96, 2, False), (64, 16, 33, 70, 1, False), (160, 11, 9, 9, 2, True)])
+def test_conv_taps_in_n_matches_per_tap_kernel(cin, cout, H, W, B, f32, act):
+    """The taps-in-N kernel (nine taps as GEMM columns + shifted sum from shared memory) against the per-tap implicit GEMM
+    on the same operands: same fp32 products, different summation order -> equal within fp32 rounding of the accumulation
+    (relative to the output scale), ragged maps / partial tiles / K tails / zero padding included; and against torch."""
+    L = lib.load()
+    g = torch.Generator().manual_seed(cin + cout + H)
+    x = _rand_act(B, H, W, cin, seed=cin + W)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9)**0.5
+    scale = 0.5 + torch.rand(cout, generator=g)
+    bias = torch.randn(cout, generator=g) * 0.5
+    outs = []
+    try:
+        for mode in (1, 0):
+            assert L.dd3d_set_conv_policy(b"taps", mode) == 0
+            outs.append(gpu_ops.conv2d(x, w, scale, bias, 1, not f32, None, False, out_f32=f32))
+    finally:
+        L.dd3d_set_conv_policy(b"taps", -1)
+    a, b = outs[0].float().cpu(), outs[1].float().cpu()
+    ref = gpu_ops.conv2d_ref(x.cpu(), w, scale, bias, 1, not f32)
+    if f32:
+        tol = 2e-5 * max(1.0, ref.abs().max().item())
+        assert (a[..., :cout] - b[..., :cout]).abs().max().item() < tol
+        assert (a[..., :cout] - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+        assert torch.isfinite(a).all()
+    else:
+        _check_bf16(outs[0], ref, "taps-in-N 16-bit output")
+        assert (a != b).float().mean().item() < 2e-3  # isolated 1-ulp storage flips only
+
+
 @pytest.mark.parametrize("cin,cout,k,stride,H,W,B,relu,res", CONV_CASES)
 def test_conv_cta_pair_bitwise_equals_single_cta(cin, cout, k, stride, H, W, B, relu, res):
     """The CTA-pair kernel (tcgen05.mma.cta_group::2, M = 256, half weight tile per CTA) accumulates every output in the
