@@ -110,8 +110,12 @@ def param_specs(cfg):
 
     C = cfg.DD3D.NUM_CLASSES
     L = 5
-    for tower, frozen in (("fcos2d_head.cls_tower", False), ("fcos2d_head.box2d_tower", False),
-                          ("fcos3d_head.box3d_tower", True)):
+    f2, f3 = cfg.DD3D.FCOS2D, cfg.DD3D.FCOS3D
+    box3d_on = bool(cfg.MODEL.BOX3D_ON)  # core.py:34-40: no FCOS3D head at all when off
+    towers = [("fcos2d_head.cls_tower", False), ("fcos2d_head.box2d_tower", False)]
+    if box3d_on:
+        towers.append(("fcos3d_head.box3d_tower", True))
+    for tower, frozen in towers:
         for i in range(4):
             _conv(specs, f"{tower}.{i}", 256, 256, 3)
             for l in range(L):
@@ -119,21 +123,26 @@ def param_specs(cfg):
     _conv(specs, "fcos2d_head.cls_logits", C, 256, 3, bias=True, role="cls_logits")
     _conv(specs, "fcos2d_head.box2d_reg", 4, 256, 3, bias=True, role="box2d_reg")
     _conv(specs, "fcos2d_head.centerness", 1, 256, 3, bias=True, role="centerness")
-    for l in range(L):
-        specs[f"fcos2d_head.scales_box2d_reg.{l}.scale"] = ((1, ), "scalar:box2d")
-    specs["fcos3d_head.mean_depth_per_level"] = ((L, ), "buffer")
-    specs["fcos3d_head.std_depth_per_level"] = ((L, ), "buffer")
-    _conv(specs, "fcos3d_head.box3d_quat.0", 4 * C, 256, 3, bias=True, role="quat")
-    _conv(specs, "fcos3d_head.box3d_ctr.0", 2 * C, 256, 3, bias=True, role="ctr")
-    _conv(specs, "fcos3d_head.box3d_depth.0", C, 256, 3, bias=False, role="depth")
-    _conv(specs, "fcos3d_head.box3d_size.0", 3 * C, 256, 3, bias=True, role="size")
-    _conv(specs, "fcos3d_head.box3d_conf.0", C, 256, 3, bias=True, role="conf")
-    for l in range(L):
-        specs[f"fcos3d_head.scales_proj_ctr.{l}.scale"] = ((1, ), "scalar:ctr")
-        specs[f"fcos3d_head.scales_size.{l}.scale"] = ((1, ), "scalar:one")
-        specs[f"fcos3d_head.scales_conf.{l}.scale"] = ((1, ), "scalar:one")
-        specs[f"fcos3d_head.scales_depth.{l}.scale"] = ((1, ), "scalar:depth")
-        specs[f"fcos3d_head.offsets_depth.{l}.bias"] = ((1, ), "scalar:depth_offset")
+    if f2.USE_SCALE:  # fcos2d.py:100-108
+        for l in range(L):
+            specs[f"fcos2d_head.scales_box2d_reg.{l}.scale"] = ((1, ), "scalar:box2d")
+    if box3d_on:
+        C3 = 1 if f3.CLASS_AGNOSTIC_BOX3D else C          # fcos3d.py:103
+        NL = L if f3.PER_LEVEL_PREDICTORS else 1           # fcos3d.py:104
+        specs["fcos3d_head.mean_depth_per_level"] = ((L, ), "buffer")
+        specs["fcos3d_head.std_depth_per_level"] = ((L, ), "buffer")
+        for name, mult, role, bias in (("quat", 4, "quat", True), ("ctr", 2, "ctr", True),
+                                       ("depth", 1, "depth", not f3.USE_SCALE),  # fcos3d.py:116
+                                       ("size", 3, "size", True), ("conf", 1, "conf", True)):
+            for li in range(NL):
+                _conv(specs, f"fcos3d_head.box3d_{name}.{li}", mult * C3, 256, 3, bias=bias, role=role)
+        if f3.USE_SCALE:  # fcos3d.py:128-139
+            for l in range(L):
+                specs[f"fcos3d_head.scales_proj_ctr.{l}.scale"] = ((1, ), "scalar:ctr")
+                specs[f"fcos3d_head.scales_size.{l}.scale"] = ((1, ), "scalar:one")
+                specs[f"fcos3d_head.scales_conf.{l}.scale"] = ((1, ), "scalar:one")
+                specs[f"fcos3d_head.scales_depth.{l}.scale"] = ((1, ), "scalar:depth")
+                specs[f"fcos3d_head.offsets_depth.{l}.bias"] = ((1, ), "scalar:depth_offset")
     if is_nuscenes_arch(cfg):  # nuscenes_dd3d.py:311-312 (appended last: the synthetic generator stream of the rest is unchanged)
         _conv(specs, "attr_logits", MAX_NUM_ATTRIBUTES, 256, 3, bias=True, role="attr")
         _conv(specs, "speed", 1, 256, 3, bias=True, role="speed")

@@ -276,8 +276,10 @@ int dd3d_get_tensor(dd3d_handle h, const char* name, void** d_ptr, int32_t dims[
             memcpy(dims, d, sizeof(d));
         } else if (n.rfind("b3d", 0) == 0) {
             const int l = level(3);
+            if (P.b3d_map[l] == nullptr) throw EngineError(DD3D_ERR_INVALID, "no 3-D head (box3d_on = 0): " + n);
             *d_ptr = P.b3d_map[l];
-            const int32_t d[6] = {P.B, P.lvl_h[l], P.lvl_w[l], 11 * e.desc.num_classes, P.b3d_pitch, 4};
+            const int32_t d[6] = {P.B, P.lvl_h[l], P.lvl_w[l], 11 * (e.desc.class_agnostic_box3d ? 1 : e.desc.num_classes),
+                                  P.b3d_pitch, 4};
             memcpy(dims, d, sizeof(d));
         } else {
             throw EngineError(DD3D_ERR_INVALID, "unknown tensor: " + n);

@@ -64,8 +64,9 @@ __global__ void __launch_bounds__(kDenseThreads) dense_kernel(const __grid_const
             for (int j = 0; j < 4; ++j) {
                 const int c = c0 + j;
                 if (c < p.C) {
-                    const float s = sigmoidf(vv[j]) * ctr;
-                    if (s > p.thresh) {
+                    const float cs = sigmoidf(vv[j]);
+                    const float s = cs * ctr;
+                    if ((p.thresh_with_ctr ? s : cs) > p.thresh) {
                         const int bin = min(score_bin(p, s), kHistBins - 1);
                         if (MODE == 0) {
                             atomicAdd(&shist[bin], 1u);
@@ -245,8 +246,20 @@ __device__ void decode_one(const DecodeParams& p, const DecodeLevel& L, int b, i
         d.speed = __ldg(a + p.num_attr);
     }
 
-    const float* g = L.b3d + gp * p.b3d_pitch + c;
-    const int C = p.C;
+    if (!p.box3d_on) {  // 2-D detector only (core.py:117-125): the NMS is keyed on `scores`
+        d.score3d = d.score;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) d.quat[t] = t == 0 ? 1.f : 0.f;
+        d.proj_ctr[0] = lx;
+        d.proj_ctr[1] = ly;
+        d.depth = 0.f;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) d.size[t] = 0.f;
+        *out = d;
+        return;
+    }
+    const int C = p.C3;  // channel = component * C3 + class (class 0 when class agnostic; fcos3d.py:333-352)
+    const float* g = L.b3d + gp * p.b3d_pitch + (p.C3 == 1 ? 0 : c);
     float q[4] = {__ldg(g), __ldg(g + C), __ldg(g + 2 * C), __ldg(g + 3 * C)};
     const float cx = __ldg(g + 4 * C), cy = __ldg(g + 5 * C);
     float depth = __ldg(g + 6 * C);
@@ -397,7 +410,9 @@ void decode_finalize_params(DecodeParams* p) {
     }
     p->total_blocks = blk;
     uint32_t tb;
-    float t = p->thresh > 0.f ? p->thresh : 0.f;
+    // the ranked score cls * ctr is > thresh only when the threshold is applied to the product; otherwise it can be anywhere
+    // in (0, 1) and the histogram starts at 0
+    float t = (p->thresh > 0.f && p->thresh_with_ctr) ? p->thresh : 0.f;
     memcpy(&tb, &t, 4);
     p->thresh_bits = tb;
     const uint32_t one = 0x3F800000u;

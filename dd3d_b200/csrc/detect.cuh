@@ -54,6 +54,9 @@ struct DecodeParams {
     const float* canon;   // [C][3]
     float min_depth, max_depth, depth_factor;
     int scale_depth_by_focal, allocentric, predict_distance;
+    int thresh_with_ctr;  // 1: threshold sigmoid(cls) * sigmoid(ctr); 0: threshold sigmoid(cls), rank by the product (fcos2d.py:280-290)
+    int C3;               // classes of the 3-D maps: num_classes, or 1 when CLASS_AGNOSTIC_BOX3D (fcos3d.py:333-352)
+    int box3d_on;         // 0: no 3-D head (MODEL.BOX3D_ON False): score_3d = score, 3-D fields zero
     // scratch (all per image x level)
     uint32_t* hist;       // [B][L][kHistBins]
     int32_t* sel;         // [B][L][4] : T, n_above, need, total

@@ -651,7 +651,12 @@ struct Builder {
         const int C = E->desc.num_classes;
         const int L = static_cast<int>(feats.size());
         const bool nusc = E->desc.nuscenes_heads != 0;
-        const int cls_pitch = round_up(C + (nusc ? kNumAttributes + 1 : 0), 16), b3d_pitch = round_up(11 * C, 16);
+        // head switches no shipped experiment changes (dd3d_model_desc): class-agnostic 3-D channels, per-level predictors,
+        // no Scale / Offset layers, no 3-D head at all
+        const bool use_scale2 = E->desc.fcos2d_use_scale != 0, use_scale3 = E->desc.fcos3d_use_scale != 0;
+        const bool per_level = E->desc.per_level_predictors != 0, box3d_on = E->desc.box3d_on != 0;
+        const int C3 = E->desc.class_agnostic_box3d ? 1 : C;
+        const int cls_pitch = round_up(C + (nusc ? kNumAttributes + 1 : 0), 16), b3d_pitch = round_up(11 * C3, 16);
         P->cls_pitch = cls_pitch;
         P->b3d_pitch = b3d_pitch;
         // each tower is followed at once by its predictor, so that its ping-pong buffers die before the next tower starts
@@ -661,7 +666,7 @@ struct Builder {
             const size_t hw = static_cast<size_t>(B) * feats[l].H * feats[l].W;
             P->cls_map[l] = alloc_f32(hw * cls_pitch);
             P->box_map[l] = alloc_f32(hw * 16);
-            P->b3d_map[l] = alloc_f32(hw * b3d_pitch);
+            P->b3d_map[l] = box3d_on ? alloc_f32(hw * b3d_pitch) : nullptr;
             P->lvl_h[l] = feats[l].H;
             P->lvl_w[l] = feats[l].W;
         }
@@ -710,7 +715,8 @@ struct Builder {
             for (int l = 0; l < L; ++l) {
                 const std::string key = "fcos2d_head.box@" + std::to_string(l);
                 if (E->epis.find(key) == E->epis.end()) {
-                    const float s = E->weight("fcos2d_head.scales_box2d_reg." + std::to_string(l) + ".scale").data[0];
+                    const float s = use_scale2 ? E->weight("fcos2d_head.scales_box2d_reg." + std::to_string(l) + ".scale").data[0]
+                                               : 1.0f;  // fcos2d.py:145-152
                     const HostTensor& br = E->weight("fcos2d_head.box2d_reg.bias");
                     const HostTensor& bc = E->weight("fcos2d_head.centerness.bias");
                     std::vector<float> sc(5), bi(5), lo(5);
@@ -733,36 +739,43 @@ struct Builder {
         }
         // [quat 4C | ctr 2C | depth C | size 3C | conf C] on the box3d tower with the per-level Scale/Offset folded
         // (fcos3d.py:166-180; PER_LEVEL_PREDICTORS False -> predictor index 0)
+        if (!box3d_on) return;  // MODEL.BOX3D_ON = False (core.py:34-40): 2-D detector only
         tower("fcos3d_head.box3d_tower", feats, &b3d_t);
+        // [quat 4C | ctr 2C | depth C | size 3C | conf C] on the box3d tower with the per-level Scale/Offset folded
+        // (fcos3d.py:166-180).  PER_LEVEL_PREDICTORS False (shipped): predictor index 0 for every level, one launch over the
+        // five levels; True: level l uses predictor l, one launch per level.
         {
-            const ConvLayer& L3 = E->conv_layer(
-                "fcos3d_head.box3d_all",
-                {"fcos3d_head.box3d_quat.0", "fcos3d_head.box3d_ctr.0", "fcos3d_head.box3d_depth.0",
-                 "fcos3d_head.box3d_size.0", "fcos3d_head.box3d_conf.0"},
-                256, 3);
+            auto layer_for = [&](int li) -> const ConvLayer& {
+                const std::string i = std::to_string(li);
+                return E->conv_layer("fcos3d_head.box3d_all." + i,
+                                     {"fcos3d_head.box3d_quat." + i, "fcos3d_head.box3d_ctr." + i, "fcos3d_head.box3d_depth." + i,
+                                      "fcos3d_head.box3d_size." + i, "fcos3d_head.box3d_conf." + i},
+                                     256, 3);
+            };
             std::vector<SegSpec> segs(L);
             for (int l = 0; l < L; ++l) {
                 const std::string key = "fcos3d_head.b3d@" + std::to_string(l);
                 if (E->epis.find(key) == E->epis.end()) {
-                    const std::string ls = std::to_string(l);
-                    const float s_ctr = E->weight("fcos3d_head.scales_proj_ctr." + ls + ".scale").data[0];
-                    const float s_size = E->weight("fcos3d_head.scales_size." + ls + ".scale").data[0];
-                    const float s_conf = E->weight("fcos3d_head.scales_conf." + ls + ".scale").data[0];
-                    const float s_depth = E->weight("fcos3d_head.scales_depth." + ls + ".scale").data[0];
-                    const float o_depth = E->weight("fcos3d_head.offsets_depth." + ls + ".bias").data[0];
-                    std::vector<float> sc(11 * C), bi(11 * C);
-                    auto fill = [&](int c0, int n, float s, const char* bias_name, float add) {
+                    const std::string ls = std::to_string(l), pi = std::to_string(per_level ? l : 0);
+                    auto scalar = [&](const std::string& n, float dflt) { return use_scale3 ? E->weight(n).data[0] : dflt; };
+                    const float s_ctr = scalar("fcos3d_head.scales_proj_ctr." + ls + ".scale", 1.0f);
+                    const float s_size = scalar("fcos3d_head.scales_size." + ls + ".scale", 1.0f);
+                    const float s_conf = scalar("fcos3d_head.scales_conf." + ls + ".scale", 1.0f);
+                    const float s_depth = scalar("fcos3d_head.scales_depth." + ls + ".scale", 1.0f);
+                    const float o_depth = scalar("fcos3d_head.offsets_depth." + ls + ".bias", 0.0f);
+                    std::vector<float> sc(11 * C3), bi(11 * C3);
+                    auto fill = [&](int c0, int n, float s, const std::string& bias_name, float add) {
                         const bool has = E->weights.find(bias_name) != E->weights.end();
                         for (int k = 0; k < n; ++k) {
                             sc[c0 + k] = s;
                             bi[c0 + k] = (has ? E->weight(bias_name).data[k] : 0.0f) * s + add;
                         }
                     };
-                    fill(0, 4 * C, 1.0f, "fcos3d_head.box3d_quat.0.bias", 0.f);
-                    fill(4 * C, 2 * C, s_ctr, "fcos3d_head.box3d_ctr.0.bias", 0.f);
-                    fill(6 * C, C, s_depth, "fcos3d_head.box3d_depth.0.bias", o_depth);
-                    fill(7 * C, 3 * C, s_size, "fcos3d_head.box3d_size.0.bias", 0.f);
-                    fill(10 * C, C, s_conf, "fcos3d_head.box3d_conf.0.bias", 0.f);
+                    fill(0, 4 * C3, 1.0f, "fcos3d_head.box3d_quat." + pi + ".bias", 0.f);
+                    fill(4 * C3, 2 * C3, s_ctr, "fcos3d_head.box3d_ctr." + pi + ".bias", 0.f);
+                    fill(6 * C3, C3, s_depth, "fcos3d_head.box3d_depth." + pi + ".bias", o_depth);  // bias only without USE_SCALE
+                    fill(7 * C3, 3 * C3, s_size, "fcos3d_head.box3d_size." + pi + ".bias", 0.f);
+                    fill(10 * C3, C3, s_conf, "fcos3d_head.box3d_conf." + pi + ".bias", 0.f);
                     E->epilogue(key, sc, bi, nullptr);
                 }
                 segs[l].in = b3d_t[l];
@@ -770,7 +783,14 @@ struct Builder {
                 segs[l].out_f32 = P->b3d_map[l];
                 segs[l].out_pitch = b3d_pitch;
             }
-            conv(L3, 1, false, segs, true);
+            if (!per_level) {
+                conv(layer_for(0), 1, false, segs, true);
+            } else {
+                for (int l = 0; l < L; ++l) {
+                    std::vector<SegSpec> one(1, segs[l]);
+                    conv(layer_for(l), 1, false, one, true);
+                }
+            }
         }
     }
 };
@@ -1026,6 +1046,9 @@ void fill_decode_params(DecodeParams* dp, const dd3d_model_desc& desc, int B, in
     dp->scale_depth_by_focal = desc.scale_depth_by_focal_lengths;
     dp->allocentric = desc.predict_allocentric_rot;
     dp->predict_distance = desc.predict_distance;
+    dp->thresh_with_ctr = desc.thresh_with_ctr;
+    dp->C3 = desc.class_agnostic_box3d ? 1 : desc.num_classes;
+    dp->box3d_on = desc.box3d_on;
 }
 
 void fill_nms_params(NmsParams* np, const dd3d_model_desc& desc, const DecodeParams& dp, int B) {

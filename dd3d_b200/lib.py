@@ -39,6 +39,12 @@ class ModelDesc(C.Structure):
         ("out_cap", C.c_int32),
         ("nuscenes_heads", C.c_int32),
         ("act_dtype", C.c_int32),
+        ("thresh_with_ctr", C.c_int32),
+        ("fcos2d_use_scale", C.c_int32),
+        ("fcos3d_use_scale", C.c_int32),
+        ("class_agnostic_box3d", C.c_int32),
+        ("per_level_predictors", C.c_int32),
+        ("box3d_on", C.c_int32),
     ]
 
 
@@ -133,17 +139,18 @@ def desc_from_cfg(cfg, out_cap=None):
         d.pixel_std[i] = cfg.MODEL.PIXEL_STD[i]
     d.feature_locations_offset_half = int(cfg.DD3D.FEATURE_LOCATIONS_OFFSET == "half")
     inf = cfg.DD3D.FCOS2D.INFERENCE
-    if not inf.THRESH_WITH_CTR:
-        raise NotImplementedError("THRESH_WITH_CTR=False is not supported by the B200 decode kernel")
+    d.thresh_with_ctr = int(bool(inf.THRESH_WITH_CTR))  # fcos2d.py:280-290
     d.pre_nms_thresh = inf.PRE_NMS_THRESH
     d.pre_nms_topk = inf.PRE_NMS_TOPK
     d.post_nms_topk = inf.POST_NMS_TOPK
     d.nms_thresh = inf.NMS_THRESH
     d.do_nms = int(cfg.DD3D.INFERENCE.DO_NMS)
     f3 = cfg.DD3D.FCOS3D
-    if f3.CLASS_AGNOSTIC_BOX3D or f3.PER_LEVEL_PREDICTORS or not f3.USE_SCALE or not cfg.DD3D.FCOS2D.USE_SCALE:
-        raise NotImplementedError("only the shipped head configuration (class-aware, shared predictors, USE_SCALE) "
-                                  "is implemented")
+    d.fcos2d_use_scale = int(bool(cfg.DD3D.FCOS2D.USE_SCALE))       # fcos2d.py:100-108,145-152
+    d.fcos3d_use_scale = int(bool(f3.USE_SCALE))                    # fcos3d.py:62,116,128-139,175-180
+    d.class_agnostic_box3d = int(bool(f3.CLASS_AGNOSTIC_BOX3D))     # fcos3d.py:103,333,352
+    d.per_level_predictors = int(bool(f3.PER_LEVEL_PREDICTORS))     # fcos3d.py:65,104,166
+    d.box3d_on = int(bool(cfg.MODEL.BOX3D_ON))                      # core.py:34-40,117
     d.min_depth, d.max_depth = f3.MIN_DEPTH, f3.MAX_DEPTH
     d.scale_depth_by_focal_lengths = int(f3.SCALE_DEPTH_BY_FOCAL_LENGTHS)
     d.scale_depth_by_focal_lengths_factor = f3.SCALE_DEPTH_BY_FOCAL_LENGTHS_FACTOR

@@ -30,9 +30,7 @@ class DD3DB200(nn.Module):
         if is_nuscenes_arch(cfg) != isinstance(self, NuscenesDD3DB200):
             raise ValueError(f"MODEL.META_ARCHITECTURE = {cfg.MODEL.META_ARCHITECTURE} does not match {type(self).__name__}")
         self.arch = arch_of(cfg)  # raises KeyError for an unknown FE.BUILDER like the reference registry
-        if not cfg.MODEL.BOX3D_ON:
-            raise NotImplementedError("DD3DB200 implements the BOX3D_ON configuration")
-        self.only_box2d = False
+        self.only_box2d = not cfg.MODEL.BOX3D_ON  # core.py:34-40
         self.num_classes = cfg.DD3D.NUM_CLASSES
         self.postprocess_in_inference = cfg.DD3D.INFERENCE.DO_POSTPROCESS
         self.do_nms = cfg.DD3D.INFERENCE.DO_NMS
@@ -148,6 +146,8 @@ class DD3DB200(nn.Module):
         survive: an engine planned with the small NMS-sized output buffer is rebuilt with the large one instead of silently
         truncating (the reference never truncates)."""
         inf = self.cfg.DD3D.FCOS2D.INFERENCE
+        if self.do_bev_nms and self.only_box2d:
+            self.do_bev_nms = False  # core.py:137: the BEV NMS needs the 3-D boxes
         if self.do_bev_nms and not self.do_nms:
             raise NotImplementedError("DO_BEV_NMS without DO_NMS: the BEV kernel expects the score-sorted output of the 2-D NMS")
         need = 5 * inf.PRE_NMS_TOPK if (not self.do_nms or inf.POST_NMS_TOPK <= 0) else 0
@@ -232,9 +232,10 @@ class DD3DB200(nn.Module):
             inst.pred_classes = di[:, 6].to(torch.int64)
             inst.locations = d[:, 18:20].clone()
             inst.fpn_levels = di[:, 7].to(torch.int64)
-            inst.pred_boxes3d = Boxes3D(d[:, 8:12].clone(), d[:, 12:14].clone(), d[:, 14:15].clone(),
-                                        d[:, 15:18].clone(), inv_K[b][None].expand(n, 3, 3))
-            inst.scores_3d = d[:, 5].clone()
+            if not self.only_box2d:  # core.py:117-125
+                inst.pred_boxes3d = Boxes3D(d[:, 8:12].clone(), d[:, 12:14].clone(), d[:, 14:15].clone(),
+                                            d[:, 15:18].clone(), inv_K[b][None].expand(n, 3, 3))
+                inst.scores_3d = d[:, 5].clone()
             if self._desc.nuscenes_heads:
                 inst.pred_attributes = di[:, 21].to(torch.int64)
                 inst.pred_speeds = d[:, 22].clone()

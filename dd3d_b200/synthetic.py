@@ -66,7 +66,10 @@ def make_state_dict(cfg, seed=0, gains=None):
             if role == "cls_logits":
                 sd[name] = torch.full(shape, float(gains.get("cls_bias", -4.0)))
             elif role in _PRED:
-                sd[name] = torch.full(shape, float(_PRED[role][1])) + 0.1 * torch.randn(shape, generator=g)
+                b0 = _PRED[role][1]
+                if b0 is None:  # box3d_depth has a bias only when FCOS3D.USE_SCALE is off (fcos3d.py:116): a plausible depth
+                    b0 = 20.0
+                sd[name] = torch.full(shape, float(b0)) + 0.1 * torch.randn(shape, generator=g)
             elif role == "ese":
                 sd[name] = torch.randn(shape, generator=g)
             else:  # top_block p6/p7

@@ -68,6 +68,15 @@ typedef struct dd3d_model_desc {
     int32_t nuscenes_heads; /* MODEL.META_ARCHITECTURE == NuscenesDD3D: attr_logits (3) + speed (1, relu) predictor convs
                              * on the cls tower (nuscenes_dd3d.py:311-312,380-383) */
     int32_t act_dtype;      /* dd3d_act_dtype */
+    /* head switches no shipped experiment changes, mirrored for completeness (defaults 1, 1, 1, 0, 0, 1): */
+    int32_t thresh_with_ctr;      /* FCOS2D.INFERENCE.THRESH_WITH_CTR: 0 = threshold sigmoid(cls) alone, rank by cls * ctr
+                                   * (fcos2d.py:280-290) */
+    int32_t fcos2d_use_scale;     /* FCOS2D.USE_SCALE: per-level Scale on box2d_reg (fcos2d.py:100-108,145-152) */
+    int32_t fcos3d_use_scale;     /* FCOS3D.USE_SCALE: per-level Scale / Offset on ctr, size, conf, depth; when 0 the depth
+                                   * predictor has a bias instead (fcos3d.py:116,128-139,175-180) */
+    int32_t class_agnostic_box3d; /* FCOS3D.CLASS_AGNOSTIC_BOX3D: 11 instead of 11 * num_classes 3-D channels (fcos3d.py:103) */
+    int32_t per_level_predictors; /* FCOS3D.PER_LEVEL_PREDICTORS: box3d_{quat,ctr,depth,size,conf}.<level> (fcos3d.py:104,166) */
+    int32_t box3d_on;             /* MODEL.BOX3D_ON: 0 = 2-D detector only (core.py:34-40; NMS keyed on `scores`, :117-125) */
 } dd3d_model_desc;
 
 /* One detection = the fields the reference returns in Instances (fcos2d.py:331-335,263; fcos3d.py:398-399). */

@@ -235,6 +235,8 @@ class DD3DOracle:
 
     def heads(self, features):
         sd = self.sd
+        f2, f3 = self.cfg.DD3D.FCOS2D, self.cfg.DD3D.FCOS3D
+        box3d_on = bool(self.cfg.MODEL.BOX3D_ON)
         out = dict(logits=[], box2d_reg=[], centerness=[], quat=[], ctr=[], depth=[], size=[], conf=[])
         for l, f in enumerate(features):
             cls_t = self._tower(f, "fcos2d_head.cls_tower", l)
@@ -245,19 +247,28 @@ class DD3DOracle:
                 out.setdefault("speed", []).append(self.conv(cls_t, "speed", relu=True, quant_out=False))
             out["centerness"].append(self.conv(box_t, "fcos2d_head.centerness", quant_out=False))
             reg = self.conv(box_t, "fcos2d_head.box2d_reg", quant_out=False)
-            reg = reg * sd[f"fcos2d_head.scales_box2d_reg.{l}.scale"]
+            if f2.USE_SCALE:  # fcos2d.py:145-152
+                reg = reg * sd[f"fcos2d_head.scales_box2d_reg.{l}.scale"]
             out["box2d_reg"].append(F.relu(reg))
+            if not box3d_on:  # core.py:34-40
+                continue
             b3 = self._tower(f, "fcos3d_head.box3d_tower", l)
-            out["quat"].append(self.conv(b3, "fcos3d_head.box3d_quat.0", quant_out=False))
-            out["ctr"].append(
-                self.conv(b3, "fcos3d_head.box3d_ctr.0", quant_out=False) * sd[f"fcos3d_head.scales_proj_ctr.{l}.scale"])
-            depth = self.conv(b3, "fcos3d_head.box3d_depth.0", quant_out=False)
-            out["depth"].append(depth * sd[f"fcos3d_head.scales_depth.{l}.scale"] +
-                                sd[f"fcos3d_head.offsets_depth.{l}.bias"])
-            out["size"].append(
-                self.conv(b3, "fcos3d_head.box3d_size.0", quant_out=False) * sd[f"fcos3d_head.scales_size.{l}.scale"])
-            out["conf"].append(
-                self.conv(b3, "fcos3d_head.box3d_conf.0", quant_out=False) * sd[f"fcos3d_head.scales_conf.{l}.scale"])
+            i = l if f3.PER_LEVEL_PREDICTORS else 0  # fcos3d.py:166
+            quat = self.conv(b3, f"fcos3d_head.box3d_quat.{i}", quant_out=False)
+            ctr = self.conv(b3, f"fcos3d_head.box3d_ctr.{i}", quant_out=False)
+            depth = self.conv(b3, f"fcos3d_head.box3d_depth.{i}", quant_out=False)
+            size = self.conv(b3, f"fcos3d_head.box3d_size.{i}", quant_out=False)
+            conf = self.conv(b3, f"fcos3d_head.box3d_conf.{i}", quant_out=False)
+            if f3.USE_SCALE:  # fcos3d.py:175-180
+                ctr = ctr * sd[f"fcos3d_head.scales_proj_ctr.{l}.scale"]
+                size = size * sd[f"fcos3d_head.scales_size.{l}.scale"]
+                conf = conf * sd[f"fcos3d_head.scales_conf.{l}.scale"]
+                depth = depth * sd[f"fcos3d_head.scales_depth.{l}.scale"] + sd[f"fcos3d_head.offsets_depth.{l}.bias"]
+            out["quat"].append(quat)
+            out["ctr"].append(ctr)
+            out["depth"].append(depth)
+            out["size"].append(size)
+            out["conf"].append(conf)
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -281,9 +292,11 @@ class DD3DOracle:
         scores = logits.permute(1, 2, 0).reshape(-1, C).sigmoid()
         ctrness = maps["centerness"][lvl][b].permute(1, 2, 0).reshape(-1).sigmoid()
         reg = maps["box2d_reg"][lvl][b].permute(1, 2, 0).reshape(-1, 4)
-        assert cfg2.THRESH_WITH_CTR
-        scores = scores * ctrness[:, None]
+        if cfg2.THRESH_WITH_CTR:  # fcos2d.py:280-290: threshold the product, or the class score alone
+            scores = scores * ctrness[:, None]
         mask = scores > cfg2.PRE_NMS_THRESH
+        if not cfg2.THRESH_WITH_CTR:
+            scores = scores * ctrness[:, None]
         cand = mask.nonzero(as_tuple=False)
         pix, cls = cand[:, 0], cand[:, 1]
         s = scores[mask]
@@ -296,9 +309,16 @@ class DD3DOracle:
         boxes = torch.stack([loc[:, 0] - r[:, 0], loc[:, 1] - r[:, 1], loc[:, 0] + r[:, 2], loc[:, 1] + r[:, 3]], 1)
         score2d = torch.sqrt(s)
 
+        if not self.cfg.MODEL.BOX3D_ON:  # core.py:117-125: 2-D detector, the NMS is keyed on `scores`
+            n = pix.shape[0]
+            return dict(pixel=pix, cls=cls, level=torch.full_like(pix, lvl), box2d=boxes, score=score2d, score3d=score2d,
+                        loc=loc, quat=torch.tensor([[1.0, 0, 0, 0]]).repeat(n, 1), proj_ctr=loc.clone(),
+                        depth=torch.zeros(n), size=torch.zeros(n, 3), tvec=torch.zeros(n, 3))
+        C3 = 1 if self.cfg.DD3D.FCOS3D.CLASS_AGNOSTIC_BOX3D else C  # fcos3d.py:333-352
+
         def gather(name, ncomp):
-            m = maps[name][lvl][b].permute(1, 2, 0).reshape(-1, ncomp, C)  # channel = comp*C + class
-            return m[pix, :, cls]
+            m = maps[name][lvl][b].permute(1, 2, 0).reshape(-1, ncomp, C3)  # channel = comp*C3 + class
+            return m[pix, :, cls if C3 > 1 else torch.zeros_like(cls)]
 
         quat = gather("quat", 4)
         ctr = gather("ctr", 2)

@@ -171,6 +171,69 @@ def test_oracle_decode_flags_vs_live_reference(flags, have_reference):
     assert (ref.pred_boxes3d.tvec - out["tvec"]).abs().max() < 1e-3
 
 
+HEAD_CASES = [  # head configurations no shipped experiment uses (VERDICT r1 missing #2)
+    dict(THRESH_WITH_CTR=False),
+    dict(FCOS3D_USE_SCALE=False),
+    dict(FCOS2D_USE_SCALE=False),
+    dict(CLASS_AGNOSTIC_BOX3D=True),
+    dict(PER_LEVEL_PREDICTORS=True),
+    dict(BOX3D_ON=False),
+    dict(THRESH_WITH_CTR=False, FCOS3D_USE_SCALE=False, FCOS2D_USE_SCALE=False, CLASS_AGNOSTIC_BOX3D=True,
+         PER_LEVEL_PREDICTORS=True),
+]
+
+
+def apply_head_flags(cfg, flags):
+    for k, v in flags.items():
+        if k == "THRESH_WITH_CTR":
+            cfg.DD3D.FCOS2D.INFERENCE.THRESH_WITH_CTR = v
+        elif k == "FCOS3D_USE_SCALE":
+            cfg.DD3D.FCOS3D.USE_SCALE = v
+        elif k == "FCOS2D_USE_SCALE":
+            cfg.DD3D.FCOS2D.USE_SCALE = v
+        elif k == "BOX3D_ON":
+            cfg.MODEL.BOX3D_ON = v
+        else:
+            cfg.DD3D.FCOS3D[k] = v
+    return cfg
+
+
+@pytest.mark.parametrize("flags", HEAD_CASES, ids=lambda f: "+".join(f))
+def test_oracle_head_configs_vs_live_reference(flags, have_reference):
+    """THRESH_WITH_CTR False (fcos2d.py:280-290), USE_SCALE False (fcos2d.py:100-108,145-152; fcos3d.py:116,128-139,175-180),
+    CLASS_AGNOSTIC_BOX3D (fcos3d.py:103,333-352), PER_LEVEL_PREDICTORS (fcos3d.py:104,166), BOX3D_ON False (core.py:34-40,
+    117-125): the parameter inventory equals the reference's state_dict and the oracle equals the reference's forward."""
+    if not have_reference:
+        pytest.skip("/root/reference not present (GPU box)")
+    from oracle import ref_standin
+    cfg = apply_head_flags(get_cfg("dla34", "kitti_3d"), flags)
+    cfg.DD3D.FCOS2D.INFERENCE.PRE_NMS_THRESH = 0.03
+    model = ref_standin.build_reference_model(cfg).eval()
+    specs = param_specs(cfg)
+    ref_sd = model.state_dict()
+    assert set(ref_sd.keys()) == set(specs.keys()), set(ref_sd.keys()) ^ set(specs.keys())
+    for k, (shape, _) in specs.items():
+        assert tuple(ref_sd[k].shape) == tuple(shape), k
+    sd = make_state_dict(cfg)
+    model.load_state_dict(sd)
+    inputs = make_inputs(1, 128, 256, 721.5, seed_base=7)
+    with torch.no_grad():
+        ref = model(inputs)[0]["instances"]
+    out = DD3DOracle(cfg, sd).forward(inputs)[0]
+    assert len(ref) == out["box2d"].shape[0] > 5
+    assert (ref.pred_boxes.tensor - out["box2d"]).abs().max() < 1e-3
+    assert (ref.scores - out["score"]).abs().max() < 1e-5
+    assert torch.equal(ref.pred_classes, out["cls"]) and torch.equal(ref.fpn_levels, out["level"])
+    if cfg.MODEL.BOX3D_ON:
+        assert (ref.scores_3d - out["score3d"]).abs().max() < 1e-5
+        assert quat_dist(ref.pred_boxes3d.quat, out["quat"]).max() < 1e-4
+        assert (ref.pred_boxes3d.depth.reshape(-1) - out["depth"]).abs().max() < 1e-3
+        assert ((ref.pred_boxes3d.size - out["size"]).abs() / out["size"].abs().clamp(min=1e-3)).max() < 1e-4
+        assert (ref.pred_boxes3d.tvec - out["tvec"]).abs().max() < 1e-3
+    else:
+        assert not ref.has("pred_boxes3d") and not ref.has("scores_3d")
+
+
 # ------------------------------------------------------------------------------------------------ host logic / ABI
 def test_identity_intrinsics_raises():
     cfg = get_cfg("dla34", "kitti_3d")
@@ -232,7 +295,7 @@ def test_cabi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name)
     import ctypes
-    assert ctypes.sizeof(lib.ModelDesc) == 4 * (2 + 3 + 3 + 1 + 1 + 3 + 1 + 2 + 1 + 1 + 1 + 1 + 48 + 1 + 1 + 1)  # + act_dtype
+    assert ctypes.sizeof(lib.ModelDesc) == 4 * (2 + 3 + 3 + 1 + 1 + 3 + 1 + 2 + 1 + 1 + 1 + 1 + 48 + 1 + 1 + 1 + 6)  # + act_dtype + 6 head switches
     assert ctypes.sizeof(lib.TtaView) == 4 * (1 + 1 + 2 + 2 + 9 + 9)  # dd3d_tta_view
     assert lib.DET_WORDS * 4 == 96  # dd3d_det
 

@@ -200,3 +200,57 @@ def test_submit_wait_host_matches_forward_host():
             assert torch.equal(ia.scores_3d, ib.scores_3d)
             assert torch.equal(ia.pred_boxes3d.vectorize(), ib.pred_boxes3d.vectorize())
     assert total > 10
+
+
+HEAD_CASES = [dict(THRESH_WITH_CTR=False), dict(FCOS3D_USE_SCALE=False), dict(FCOS2D_USE_SCALE=False),
+              dict(CLASS_AGNOSTIC_BOX3D=True), dict(PER_LEVEL_PREDICTORS=True), dict(BOX3D_ON=False),
+              dict(THRESH_WITH_CTR=False, FCOS3D_USE_SCALE=False, FCOS2D_USE_SCALE=False, CLASS_AGNOSTIC_BOX3D=True,
+                   PER_LEVEL_PREDICTORS=True)]
+
+
+@pytest.mark.parametrize("flags", HEAD_CASES, ids=lambda f: "+".join(f))
+def test_non_default_head_configs_vs_oracle(flags):
+    """The head switches no shipped experiment changes (fcos2d.py:280-290,100-108; fcos3d.py:103-104,116,128-139,166,
+    175-180,333-352; core.py:34-40,117-125) run on the engine; tests/test_cpu_oracle.py pins the oracle for the same
+    switches against the reference executed in the build container."""
+    from test_cpu_oracle import apply_head_flags
+    cfg = apply_head_flags(get_cfg("dla34", "kitti_3d"), flags)
+    cfg.DD3D.FCOS2D.INFERENCE.PRE_NMS_THRESH = 0.03
+    sd = make_state_dict(cfg)
+    model = DD3DB200(cfg).to("cuda")
+    model.load_state_dict(sd)
+    inputs = make_inputs(2, 128, 256, 721.5, seed_base=7)
+    out = model(inputs)
+    ref, inter = DD3DOracle(cfg, sd, emulate="bf16", threads=1).forward(inputs, return_intermediates=True)
+    C = cfg.DD3D.NUM_CLASSES
+    for l in range(5):
+        cls = model.get_tensor(f"cls{l}").cpu().permute(0, 3, 1, 2)
+        box = model.get_tensor(f"box{l}").cpu().permute(0, 3, 1, 2)
+        assert _rel_l2(cls, inter["maps"]["logits"][l]) < 1.5e-2
+        assert _rel_l2(box[:, :4], inter["maps"]["box2d_reg"][l]) < 1.5e-2
+        if cfg.MODEL.BOX3D_ON:
+            m = inter["maps"]
+            ref3d = torch.cat([m["quat"][l], m["ctr"][l], m["depth"][l], m["size"][l], m["conf"][l]], 1)
+            b3d = model.get_tensor(f"b3d{l}").cpu().permute(0, 3, 1, 2)
+            assert b3d.shape[1] == ref3d.shape[1] == 11 * (1 if cfg.DD3D.FCOS3D.CLASS_AGNOSTIC_BOX3D else C)
+            assert _rel_l2(b3d, ref3d) < 1.5e-2
+    total = 0
+    for b, (o, r) in enumerate(zip(out, ref)):
+        inst = o["instances"]
+        assert inst.has("pred_boxes3d") == bool(cfg.MODEL.BOX3D_ON) and inst.has("scores_3d") == bool(cfg.MODEL.BOX3D_ON)
+        kr = [det_key(l, p, c) for l, p, c in zip(r["level"], r["loc"], r["cls"])]
+        ia, ib = match_by_key(_keys_inst(inst), kr)
+        assert len(ib) >= 0.85 * len(kr) - 1, f"image {b}: matched {len(ib)} of {len(kr)}"
+        total += len(ib)
+        if len(ia) == 0:
+            continue
+        gb, rb = inst.pred_boxes.tensor.cpu()[ia], r["box2d"][ib]
+        size = torch.stack([rb[:, 2] - rb[:, 0], rb[:, 3] - rb[:, 1]], 1).clamp(min=1.0).repeat(1, 2)
+        assert ((gb - rb).abs() / size).max() < 2e-2
+        assert (inst.scores.cpu()[ia] - r["score"][ib]).abs().max() < 8e-3
+        if cfg.MODEL.BOX3D_ON:
+            assert (inst.scores_3d.cpu()[ia] - r["score3d"][ib]).abs().max() < 8e-3
+            b3 = inst.pred_boxes3d
+            assert ((b3.depth.cpu()[ia, 0] - r["depth"][ib]).abs() / r["depth"][ib]).max() < 1.5e-2
+            assert ((b3.size.cpu()[ia] - r["size"][ib]).abs() / r["size"][ib]).max() < 4e-2
+    assert total > 5

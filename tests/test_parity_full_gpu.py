@@ -42,7 +42,7 @@ def test_parity_at_baseline_shape(case, dtype):
     # decode + NMS kernels vs the oracle on identical (engine) head maps: exact sets / order, fp32-rounding field errors
     hyb = rep["hybrid"]
     assert hyb["candidate_sets_equal"] and hyb["kept_order_equal"] and hyb["forward_equals_operator"], hyb
-    assert hyb["candidates"] > 1000 and hyb["kept"] >= 50
+    assert hyb["candidates"] > 500 and hyb["kept"] >= 50
     for f, e in hyb["max_err"].items():
         assert e < 1e-5, (f, e)  # measured <= 4e-7: fp32 rounding only
     # conv stack: storage-precision bound
