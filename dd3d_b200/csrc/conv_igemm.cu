@@ -1169,7 +1169,12 @@ void conv_finalize_params(ConvParams* p) {
             deep_k = e ? atoi(e) : 1;
         }
         const bool deep = deep_k && p->block_n >= 96 && p->taps * p->kchunks >= 36;
-        p->cta2 = ((p->block_n >= min_n || deep) && tile >= 4 * 74) ? 1 : 0;
+        // ... or a 3x3 stride-1 layer with N = 128: per UMMA the tensor core reads A (4 KB) + B (4 KB) from shared memory in
+        // the 64 cycles the MMA takes -- the whole smem bandwidth before TMA refills it (59.6 % tensor pipe); in a pair each
+        // CTA reads half of B.  Same box, alternating: OSA2 3x3 0.82 -> 0.71 ms; the stride-2 generic N = 128 layer
+        // (stem_3) loses 47 % to pairing and stays single (profiles/r02_ab.md).
+        const bool n128_halo = p->halo && p->block_n >= 128;
+        p->cta2 = ((p->block_n >= min_n || deep || n128_halo) && tile >= 4 * 74) ? 1 : 0;
     }
     if (p->cta2 && (tile < 2 || (p->block_n % 16) != 0)) p->cta2 = 0;
     if (p->taps_n) p->cta2 = 0;
