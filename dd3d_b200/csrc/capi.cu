@@ -121,6 +121,10 @@ int dd3d_set_conv_policy(const char* name, int value) {
         conv_set_cta2(value);
         return DD3D_OK;
     }
+    if (!strcmp(name, "nms_class_parallel")) {
+        nms_set_class_parallel(value);
+        return DD3D_OK;
+    }
     if (!strcmp(name, "taps")) {
         conv_set_taps(value);
         return DD3D_OK;
@@ -486,7 +490,8 @@ int dd3d_op_sample_aggregate(dd3d_det* d_dets, int32_t* d_counts, const float* d
 }
 
 int64_t dd3d_op_detect_scratch_bytes(int B, int pre_nms_topk) {
-    return static_cast<int64_t>(decode_scratch_bytes(B, pre_nms_topk)) + DD3D_MAX_CLASSES * 3 * 4 + 256;
+    return static_cast<int64_t>(decode_scratch_bytes(B, pre_nms_topk)) + DD3D_MAX_CLASSES * 3 * 4 + 512 +
+           static_cast<int64_t>(nms_scratch_bytes(B, pre_nms_topk));
 }
 
 int dd3d_op_detect(const dd3d_model_desc* desc, int B, const int32_t* h_level_hw, const int32_t* h_strides,
@@ -527,6 +532,7 @@ int dd3d_op_detect(const dd3d_model_desc* desc, int B, const int32_t* h_level_hw
     }
     NmsParams np;
     fill_nms_params(&np, *desc, dp, B);
+    np.scratch = reinterpret_cast<uint8_t*>(d_canon) + 256;  // behind the canonical sizes (192 B) at the tail of d_scratch
     np.sizes = d_sizes;
     np.out = reinterpret_cast<Det*>(d_out);
     np.out_count = d_counts;

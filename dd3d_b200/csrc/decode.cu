@@ -205,8 +205,9 @@ __device__ __forceinline__ void mat_to_quat(const float* m, float* q) {
     for (int t = 0; t < 4; ++t) q[t] = c[t] / den;
 }
 
+// g3d: the candidate pixel's box3d predictor outputs (dense map pixel or sparse row), channel = component * C3 + class
 __device__ void decode_one(const DecodeParams& p, const DecodeLevel& L, int b, int l, uint32_t score_bits, int index,
-                           Det* out) {
+                           const float* g3d, Det* out) {
     const int hw = L.H * L.W;
     const int pix = index / p.C;
     const int c = index - pix * p.C;
@@ -259,7 +260,7 @@ __device__ void decode_one(const DecodeParams& p, const DecodeLevel& L, int b, i
         return;
     }
     const int C = p.C3;  // channel = component * C3 + class (class 0 when class agnostic; fcos3d.py:333-352)
-    const float* g = L.b3d + gp * p.b3d_pitch + (p.C3 == 1 ? 0 : c);
+    const float* g = g3d + (p.C3 == 1 ? 0 : c);
     float q[4] = {__ldg(g), __ldg(g + C), __ldg(g + 2 * C), __ldg(g + 3 * C)};
     const float cx = __ldg(g + 4 * C), cy = __ldg(g + 5 * C);
     float depth = __ldg(g + 6 * C);
@@ -326,8 +327,9 @@ __device__ void decode_one(const DecodeParams& p, const DecodeLevel& L, int b, i
     *out = d;
 }
 
-// One block per (level, image).
-__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ DecodeParams p) {
+// One block per (level, image): the final candidate list.  Candidates in histogram bins above the k-th score's bin are in
+// ("sure"); inside that bin the exact rank (score desc, index asc) decides.  fin[slot] = (score bits, index).
+__global__ void __launch_bounds__(256) select_final_kernel(const __grid_constant__ DecodeParams p) {
     const int l = blockIdx.x, b = blockIdx.y;
     const int bl = b * kLevels + l;
     const int* sel = p.sel + bl * 4;
@@ -339,11 +341,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ D
         if (nb_raw > kBoundaryCap) atomicOr(p.flags, 1);
         p.cand_count[bl] = n_sure + need;
     }
-    const DecodeLevel& L = p.lvl[l];
     const uint2* sure = p.sure + static_cast<size_t>(bl) * p.topk;
     const uint2* bnd = p.boundary + static_cast<size_t>(bl) * kBoundaryCap;
-    Det* out = p.cand + (static_cast<size_t>(b) * kLevels + l) * p.topk;
-    for (int i = threadIdx.x; i < n_sure; i += blockDim.x) decode_one(p, L, b, l, sure[i].x, sure[i].y, out + i);
+    uint2* fin = p.fin + static_cast<size_t>(bl) * p.topk;
+    for (int i = threadIdx.x; i < n_sure; i += blockDim.x) fin[i] = sure[i];
     if (need > 0) {
         for (int i = threadIdx.x; i < nb; i += blockDim.x) {
             const uint2 me = bnd[i];
@@ -352,8 +353,28 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ D
                 const uint2 o = bnd[j];
                 rank += (o.x > me.x) || (o.x == me.x && o.y < me.y);
             }
-            if (rank < need) decode_one(p, L, b, l, me.x, me.y, out + n_sure + rank);
+            if (rank < need) fin[n_sure + rank] = me;
         }
+    }
+}
+
+// One thread per final candidate: 2-D box + 3-D box decode.
+__global__ void __launch_bounds__(256) decode_final_kernel(const __grid_constant__ DecodeParams p) {
+    const int l = blockIdx.x, b = blockIdx.y;
+    const int bl = b * kLevels + l;
+    const int n = p.cand_count[bl];
+    const DecodeLevel& L = p.lvl[l];
+    const uint2* fin = p.fin + static_cast<size_t>(bl) * p.topk;
+    Det* out = p.cand + (static_cast<size_t>(b) * kLevels + l) * p.topk;
+    const size_t hw = static_cast<size_t>(L.H) * L.W;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint2 me = fin[i];
+        const float* g3d = nullptr;
+        if (p.box3d_on) {
+            g3d = p.b3d_rows != nullptr ? p.b3d_rows + (static_cast<size_t>(bl) * p.topk + i) * p.b3d_pitch
+                                        : L.b3d + (static_cast<size_t>(b) * hw + me.y / p.C) * p.b3d_pitch;
+        }
+        decode_one(p, L, b, l, me.x, static_cast<int>(me.y), g3d, out + i);
     }
 }
 
@@ -379,6 +400,7 @@ size_t decode_scratch_bytes(int B, int topk) {
     n += align_up(bl * kBoundaryCap * 8, 256);
     n += align_up(bl * topk * sizeof(Det), 256);
     n += align_up(bl * 4, 256);
+    n += align_up(bl * topk * 8, 256);  // fin
     return n;
 }
 
@@ -400,6 +422,8 @@ void decode_bind_scratch(DecodeParams* p, void* scratch) {
     p->cand = reinterpret_cast<Det*>(s);
     s += align_up(bl * p->topk * sizeof(Det), 256);
     p->cand_count = reinterpret_cast<int32_t*>(s);
+    s += align_up(bl * 4, 256);
+    p->fin = reinterpret_cast<uint2*>(s);
 }
 
 void decode_finalize_params(DecodeParams* p) {
@@ -421,7 +445,7 @@ void decode_finalize_params(DecodeParams* p) {
     p->hist_shift = shift;
 }
 
-cudaError_t launch_decode(const DecodeParams& p, cudaStream_t stream) {
+cudaError_t launch_decode_select(const DecodeParams& p, cudaStream_t stream) {
     const size_t bl = static_cast<size_t>(p.B) * kLevels;
     const size_t clear_words = (align_up(bl * kHistBins * 4, 256) + align_up(bl * 2 * 4, 256) + 256) / 4;
     clear_kernel<<<148, 256, 0, stream>>>(p.hist, clear_words);
@@ -429,8 +453,19 @@ cudaError_t launch_decode(const DecodeParams& p, cudaStream_t stream) {
     dense_kernel<0><<<dgrid, kDenseThreads, 0, stream>>>(p);
     select_kernel<<<dim3(kLevels, p.B), 256, 0, stream>>>(p);
     dense_kernel<1><<<dgrid, kDenseThreads, 0, stream>>>(p);
-    finalize_kernel<<<dim3(kLevels, p.B), 256, 0, stream>>>(p);
+    select_final_kernel<<<dim3(kLevels, p.B), 256, 0, stream>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t launch_decode_final(const DecodeParams& p, cudaStream_t stream) {
+    decode_final_kernel<<<dim3(kLevels, p.B), 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode(const DecodeParams& p, cudaStream_t stream) {
+    cudaError_t e = launch_decode_select(p, stream);
+    if (e != cudaSuccess) return e;
+    return launch_decode_final(p, stream);
 }
 
 }  // namespace dd3d

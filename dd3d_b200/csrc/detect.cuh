@@ -66,6 +66,10 @@ struct DecodeParams {
     Det* cand;            // [B][L*topk]           decoded candidates
     int32_t* cand_count;  // [B][L]
     int32_t* flags;       // [1] bit0: boundary overflow
+    uint2* fin;           // [B][L][topk] final candidates (score bits, index): slot order of `cand`
+    // sparse 3-D head: the box3d predictor is evaluated only at the final candidates (b3d_sparse.cu); row of candidate `slot`
+    // of (image b, level l) = b3d_rows + ((b * L + l) * topk + slot) * b3d_pitch, same channel layout as a dense map pixel
+    const float* b3d_rows;  // nullptr: dense maps (lvl[].b3d)
 };
 
 struct NmsParams {
@@ -78,13 +82,21 @@ struct NmsParams {
     int B, topk, out_cap;
     int do_nms, post_topk, do_postprocess;
     float nms_thresh;
+    void* scratch;    // nms_scratch_bytes(B, topk) bytes, or nullptr: single-CTA kernel (one CTA per image)
+    int num_classes;  // with scratch: one greedy scan per (class, image) CTA
 };
 
 size_t decode_scratch_bytes(int B, int topk);
 void decode_bind_scratch(DecodeParams* p, void* scratch);
 void decode_finalize_params(DecodeParams* p);
-cudaError_t launch_decode(const DecodeParams& p, cudaStream_t stream);
+cudaError_t launch_decode(const DecodeParams& p, cudaStream_t stream);  // = select + final
+// the two halves: threshold / top-k / final candidate list (fin, cand_count), then the per-candidate 2-D + 3-D decode;
+// the sparse box3d predictor runs between them
+cudaError_t launch_decode_select(const DecodeParams& p, cudaStream_t stream);
+cudaError_t launch_decode_final(const DecodeParams& p, cudaStream_t stream);
 cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream);
+size_t nms_scratch_bytes(int B, int topk);
+void nms_set_class_parallel(int mode);  // 0 single-CTA kernel, 1 per-(class, image) CTAs, -1 environment / default (1)
 // BEV rotated NMS on the (already 2-D-NMSed, score-sorted) detections, in place; poses: [B][7] (w,x,y,z, tx,ty,tz).
 cudaError_t launch_bev_nms(Det* dets, int32_t* counts, const float* K, const float* poses, const int32_t* sizes,
                            int32_t* flags, int B, int cap, float thr, int do_postprocess, cudaStream_t stream);

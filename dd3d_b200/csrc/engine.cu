@@ -922,6 +922,7 @@ size_t Engine::build(Plan* P, int B, int Hs, int Ws, void* workspace, bool dry) 
         bld.build_heads(fpn);
         // detection scratch + staging for the host-facing path
         P->detect_scratch = bld.alloc_bytes(decode_scratch_bytes(B, desc.pre_nms_topk));
+        P->nms_scratch = bld.alloc_bytes(nms_scratch_bytes(B, desc.pre_nms_topk));
         P->d_K = static_cast<float*>(bld.alloc_bytes(static_cast<size_t>(B) * 9 * 4));
         P->d_sizes = static_cast<int32_t*>(bld.alloc_bytes(static_cast<size_t>(B) * 4 * 4));
         P->d_out = static_cast<Det*>(bld.alloc_bytes(static_cast<size_t>(B) * desc.out_cap * sizeof(Det)));
@@ -1026,6 +1027,7 @@ void Engine::make_plan(int B, int Hs, int Ws, void* workspace, size_t bytes) {
     decode_bind_scratch(&dp, plan.detect_scratch);
     decode_finalize_params(&dp);
     fill_nms_params(&plan.nms, desc, dp, B);
+    plan.nms.scratch = plan.nms_scratch;
 }
 
 void fill_decode_params(DecodeParams* dp, const dd3d_model_desc& desc, int B, int cls_pitch, int b3d_pitch,
@@ -1063,10 +1065,11 @@ void fill_nms_params(NmsParams* np, const dd3d_model_desc& desc, const DecodePar
     np->post_topk = desc.post_nms_topk;
     np->do_postprocess = 1;
     np->nms_thresh = desc.nms_thresh;
+    np->num_classes = desc.num_classes;
 }
 
 int Engine::launches_per_forward() const {
-    int n = 1 /*preprocess*/ + 5 /*decode*/ + 1 /*nms*/;
+    int n = 1 /*preprocess*/ + 5 /*decode*/ + ((desc.do_nms && desc.nms_thresh > 0.f) ? 3 : 1) /*nms: sort, per class, finish*/;
     for (const Op& op : plan.ops) n += (op.type == Op::ESE) ? 3 : 1;
     return n;
 }
@@ -1251,7 +1254,7 @@ void Engine::get_profile(double* ms, double* flops, double* bytes, int32_t* laun
         }
     }
     launches[6] = 5;
-    launches[7] = 1;
+    launches[7] = (desc.do_nms && desc.nms_thresh > 0.f) ? 3 : 1;
     for (int l = 0; l < kLevels; ++l)  // two dense passes over the fp32 logits + centerness
         bytes[6] += 2.0 * P.B * P.lvl_h[l] * P.lvl_w[l] * (C + 1) * 4;
 }

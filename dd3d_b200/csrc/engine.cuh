@@ -104,6 +104,7 @@ struct Plan {
     int cls_pitch = 0, b3d_pitch = 0;
     std::vector<Op> ops;
     void* detect_scratch = nullptr;
+    void* nms_scratch = nullptr;
     float* d_K = nullptr;
     int32_t* d_sizes = nullptr;
     Det* d_out = nullptr;

@@ -12,6 +12,8 @@
 #include "detect.cuh"
 #include "device_once.cuh"
 
+#include <stdlib.h>
+
 namespace dd3d {
 
 namespace {
@@ -85,25 +87,33 @@ __device__ int compact_indices(const uint8_t* flag, int n, int* dst, int* s_warp
     return *s_base;
 }
 
-__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_constant__ NmsParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    const int b = blockIdx.x;
-    const int cap = kLevels * p.topk;
-    // smem carve-up
-    uint64_t* key = reinterpret_cast<uint64_t*>(smem_raw);                  // [kMaxCand]
-    float4* boxes = reinterpret_cast<float4*>(key + kMaxCand);              // [cap]
-    int* list = reinterpret_cast<int*>(boxes + cap);                        // [cap]
-    int* list2 = list + cap;                                                // [cap]
-    uint16_t* val = reinterpret_cast<uint16_t*>(list2 + cap);               // [kMaxCand]
-    uint8_t* cls = reinterpret_cast<uint8_t*>(val + kMaxCand);              // [cap]
-    uint8_t* flag = cls + cap;                                              // [cap]  (removed / keep flags)
-    __shared__ int s_warp_sums[33];
-    __shared__ int s_base;
-    __shared__ int s_lvl_off[kLevels + 1];
-    __shared__ unsigned long long s_kept_mask;
-    __shared__ unsigned long long s_diag[64];
+// ---------------------------------------------------------------------------------------------- building blocks
+// Shared-memory working set of one image (cap = L * topk candidates).
+struct NmsSmem {
+    uint64_t* key;   // [kMaxCand]
+    float4* boxes;   // [cap]
+    int* list;       // [cap]
+    int* list2;      // [cap]
+    uint16_t* val;   // [kMaxCand]  sorted position -> candidate slot
+    uint8_t* cls;    // [cap]
+    uint8_t* flag;   // [cap]
+};
 
-    const Det* cand = p.cand + static_cast<size_t>(b) * cap;
+__device__ __forceinline__ NmsSmem carve(uint8_t* raw, int cap) {
+    NmsSmem m;
+    m.key = reinterpret_cast<uint64_t*>(raw);
+    m.boxes = reinterpret_cast<float4*>(m.key + kMaxCand);
+    m.list = reinterpret_cast<int*>(m.boxes + cap);
+    m.list2 = m.list + cap;
+    m.val = reinterpret_cast<uint16_t*>(m.list2 + cap);
+    m.cls = reinterpret_cast<uint8_t*>(m.val + kMaxCand);
+    m.flag = m.cls + cap;
+    return m;
+}
+
+// 1. keys (score3d desc, level asc, index asc) -> bitonic sort (when do_nms) -> val[i] = candidate slot of sorted position i.
+//    Returns n.  s_lvl_off: [kLevels + 1] shared ints.
+__device__ int sort_candidates(const NmsParams& p, int b, const Det* cand, NmsSmem m, int* s_lvl_off) {
     if (threadIdx.x == 0) {
         int off = 0;
         for (int l = 0; l < kLevels; ++l) {
@@ -116,8 +126,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     const int n = s_lvl_off[kLevels];
     int n2 = 1;
     while (n2 < n) n2 <<= 1;
-
-    // ---- 1. keys: (score3d desc, level asc, index asc); payload = slot in the candidate array
     for (int i = threadIdx.x; i < n2; i += blockDim.x) {
         uint64_t k = ~0ull;
         uint16_t v = 0;
@@ -132,142 +140,137 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             k = (static_cast<uint64_t>(sb) << 32) | (static_cast<uint64_t>(l) << 28) | static_cast<uint32_t>(d.index);
             v = static_cast<uint16_t>(slot);
         }
-        key[i] = k;
-        val[i] = v;
+        m.key[i] = k;
+        m.val[i] = v;
     }
     __syncthreads();
-    if (p.do_nms) bitonic_sort(key, val, n2);
+    if (p.do_nms) bitonic_sort(m.key, m.val, n2);
+    return n;
+}
 
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const Det& d = cand[val[i]];
-        boxes[i] = make_float4(d.box[0], d.box[1], d.box[2], d.box[3]);
-        cls[i] = static_cast<uint8_t>(d.cls);
-        flag[i] = 0;  // removed flag
-    }
-    __syncthreads();
-
-    int nkeep = n;
-    if (p.do_nms && p.nms_thresh > 0.f) {
-        // ---- 2. greedy NMS, 64 sorted boxes per step
-        for (int c0 = 0; c0 < n; c0 += 64) {
-            const int cn = min(64, n - c0);
-            // (A) diagonal block: 16 threads per row, 4 columns each; OR-reduce the 4-bit pieces with shuffles
-            {
-                const int i = threadIdx.x >> 4, part = threadIdx.x & 15;
-                unsigned long long m = 0ull;
-                if (i < cn) {
-                    const float4 bi = boxes[c0 + i];
-                    const uint8_t ci = cls[c0 + i];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = part * 4 + u;
-                        if (j > i && j < cn && cls[c0 + j] == ci && iou_tv(bi, boxes[c0 + j]) > p.nms_thresh) m |= 1ull << j;
-                    }
+// 2. greedy NMS over n boxes already in score order, 64 boxes per step: resolve the 64x64 diagonal block serially (warp 0),
+//    then let all threads test the remaining boxes against the step's survivors.  cls == nullptr: single class.
+//    flag[i] = 1 where removed (must be 0 on entry).  blockDim.x must be a multiple of 64 and >= 64.
+__device__ void greedy_nms(const float4* boxes, const uint8_t* cls, uint8_t* flag, int n, float thr,
+                           unsigned long long* s_diag, unsigned long long* s_kept_mask) {
+    const int tpr = blockDim.x >> 6;  // threads per row of the diagonal block
+    const int cpt = 64 / tpr;         // columns per thread
+    for (int c0 = 0; c0 < n; c0 += 64) {
+        const int cn = min(64, n - c0);
+        {
+            const int i = threadIdx.x / tpr, part = threadIdx.x - i * tpr;
+            unsigned long long m = 0ull;
+            if (i < cn) {
+                const float4 bi = boxes[c0 + i];
+                const int ci = cls ? cls[c0 + i] : 0;
+                for (int u = 0; u < cpt; ++u) {
+                    const int j = part * cpt + u;
+                    if (j > i && j < cn && (cls == nullptr || cls[c0 + j] == ci) && iou_tv(bi, boxes[c0 + j]) > thr) m |= 1ull << j;
                 }
-#pragma unroll
-                for (int o = 1; o < 16; o <<= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
-                if (part == 0) s_diag[i] = m;
             }
-            __syncthreads();
-            // (B) warp 0 resolves the 64 boxes serially in registers (diag rows via shuffles)
-            if (threadIdx.x < 32) {
-                const int l = threadIdx.x;
-                const unsigned long long d_lo = s_diag[l], d_hi = s_diag[l + 32];
-                const unsigned r_lo = __ballot_sync(0xffffffffu, l < cn && flag[c0 + l]);
-                const unsigned r_hi = __ballot_sync(0xffffffffu, l + 32 < cn && flag[c0 + l + 32]);
-                unsigned long long removed = (static_cast<unsigned long long>(r_hi) << 32) | r_lo;
-                if (cn < 64) removed |= ~0ull << cn;
-                unsigned long long kept = 0ull;
-#pragma unroll 8
-                for (int i = 0; i < 64; ++i) {
-                    const unsigned long long di = __shfl_sync(0xffffffffu, i < 32 ? d_lo : d_hi, i & 31);
-                    if (!((removed >> i) & 1ull)) {
-                        kept |= 1ull << i;
-                        removed |= di;
-                    }
-                }
-                if (l == 0) s_kept_mask = kept;
-                if (l < cn) flag[c0 + l] = ((kept >> l) & 1ull) ? 0 : 1;
-                if (l + 32 < cn) flag[c0 + l + 32] = ((kept >> (l + 32)) & 1ull) ? 0 : 1;
-            }
-            __syncthreads();
-            // (C) every later box is tested against the step's survivors
-            const unsigned long long kept = s_kept_mask;
-            for (int k = c0 + cn + threadIdx.x; k < n; k += blockDim.x) {
-                if (flag[k]) continue;
-                const float4 bk = boxes[k];
-                const uint8_t ck = cls[k];
-                unsigned long long m = kept;
-                bool rem = false;
-                while (m) {
-                    const int i = __ffsll(static_cast<long long>(m)) - 1;
-                    m &= m - 1;
-                    if (cls[c0 + i] == ck && iou_tv(boxes[c0 + i], bk) > p.nms_thresh) {
-                        rem = true;
-                        break;
-                    }
-                }
-                if (rem) flag[k] = 1;
-            }
-            __syncthreads();
+            for (int o = 1; o < tpr; o <<= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);  // tpr is a power of two <= 32
+            if (part == 0) s_diag[i] = m;
         }
-        // keep flags = !removed
-        for (int i = threadIdx.x; i < n; i += blockDim.x) flag[i] = flag[i] ? 0 : 1;
         __syncthreads();
-        nkeep = compact_indices(flag, n, list, s_warp_sums, &s_base);
-    } else {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) list[i] = i;
+        if (threadIdx.x < 32) {
+            const int l = threadIdx.x;
+            const unsigned long long d_lo = s_diag[l], d_hi = s_diag[l + 32];
+            const unsigned r_lo = __ballot_sync(0xffffffffu, l < cn && flag[c0 + l]);
+            const unsigned r_hi = __ballot_sync(0xffffffffu, l + 32 < cn && flag[c0 + l + 32]);
+            unsigned long long removed = (static_cast<unsigned long long>(r_hi) << 32) | r_lo;
+            if (cn < 64) removed |= ~0ull << cn;
+            unsigned long long kept = 0ull;
+#pragma unroll 8
+            for (int i = 0; i < 64; ++i) {
+                const unsigned long long di = __shfl_sync(0xffffffffu, i < 32 ? d_lo : d_hi, i & 31);
+                if (!((removed >> i) & 1ull)) {
+                    kept |= 1ull << i;
+                    removed |= di;
+                }
+            }
+            if (l == 0) *s_kept_mask = kept;
+            if (l < cn) flag[c0 + l] = ((kept >> l) & 1ull) ? 0 : 1;
+            if (l + 32 < cn) flag[c0 + l + 32] = ((kept >> (l + 32)) & 1ull) ? 0 : 1;
+        }
+        __syncthreads();
+        const unsigned long long kept = *s_kept_mask;
+        for (int k = c0 + cn + threadIdx.x; k < n; k += blockDim.x) {
+            if (flag[k]) continue;
+            const float4 bk = boxes[k];
+            const int ck = cls ? cls[k] : 0;
+            unsigned long long m = kept;
+            bool rem = false;
+            while (m) {
+                const int i = __ffsll(static_cast<long long>(m)) - 1;
+                m &= m - 1;
+                if ((cls == nullptr || cls[c0 + i] == ck) && iou_tv(boxes[c0 + i], bk) > thr) {
+                    rem = true;
+                    break;
+                }
+            }
+            if (rem) flag[k] = 1;
+        }
         __syncthreads();
     }
+}
 
-    // ---- 3. post-NMS top-k on the 2-D score (>= k-th value keeps ties)
+// 3. + 4. survivors (flag[i] = 1 where KEPT, sorted order) -> post-NMS top-k on the 2-D score -> detector_postprocess -> out
+__device__ void finish_image(const NmsParams& p, int b, const Det* cand, NmsSmem m, int n, bool have_keep_flags,
+                             int* s_warp_sums, int* s_base) {
+    int nkeep = n;
+    if (have_keep_flags) {
+        nkeep = compact_indices(m.flag, n, m.list, s_warp_sums, s_base);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) m.list[i] = i;
+        __syncthreads();
+    }
+    // ---- post-NMS top-k on the 2-D score (>= k-th value keeps ties)
     if (p.do_nms && p.post_topk > 0 && nkeep > p.post_topk) {
         int m2 = 1;
         while (m2 < nkeep) m2 <<= 1;
-        uint16_t* dummy = reinterpret_cast<uint16_t*>(list2);  // payload not needed; reuse list2 as scratch
+        uint16_t* dummy = reinterpret_cast<uint16_t*>(m.list2);  // payload not needed; reuse list2 as scratch
         for (int i = threadIdx.x; i < m2; i += blockDim.x) {
             uint64_t k = ~0ull;
-            if (i < nkeep) k = static_cast<uint64_t>(~__float_as_uint(cand[val[list[i]]].score));
-            key[i] = k;
+            if (i < nkeep) k = static_cast<uint64_t>(~__float_as_uint(cand[m.val[m.list[i]]].score));
+            m.key[i] = k;
             dummy[i] = 0;
         }
         __syncthreads();
         // NOTE: sorting `key` destroys the sort keys of step 1 (no longer needed); val[] must stay intact,
         // so the payload array handed to the sort is the scratch one.
-        bitonic_sort(key, dummy, m2);
-        const uint32_t thr_bits = ~static_cast<uint32_t>(key[p.post_topk - 1]);
+        bitonic_sort(m.key, dummy, m2);
+        const uint32_t thr_bits = ~static_cast<uint32_t>(m.key[p.post_topk - 1]);
         const float thr = __uint_as_float(thr_bits);
-        for (int i = threadIdx.x; i < nkeep; i += blockDim.x) flag[i] = (cand[val[list[i]]].score >= thr) ? 1 : 0;
+        for (int i = threadIdx.x; i < nkeep; i += blockDim.x) m.flag[i] = (cand[m.val[m.list[i]]].score >= thr) ? 1 : 0;
         __syncthreads();
-        const int m = compact_indices(flag, nkeep, list2, s_warp_sums, &s_base);
-        for (int i = threadIdx.x; i < m; i += blockDim.x) list2[i] = list[list2[i]];
+        const int k2 = compact_indices(m.flag, nkeep, m.list2, s_warp_sums, s_base);
+        for (int i = threadIdx.x; i < k2; i += blockDim.x) m.list2[i] = m.list[m.list2[i]];
         __syncthreads();
-        for (int i = threadIdx.x; i < m; i += blockDim.x) list[i] = list2[i];
+        for (int i = threadIdx.x; i < k2; i += blockDim.x) m.list[i] = m.list2[i];
         __syncthreads();
-        nkeep = m;
+        nkeep = k2;
     }
-
-    // ---- 4. detector_postprocess: scale, clip, drop empty
+    // ---- detector_postprocess: scale, clip, drop empty
     const int img_h = p.sizes[b * 4 + 0], img_w = p.sizes[b * 4 + 1];
     const int out_h = p.sizes[b * 4 + 2], out_w = p.sizes[b * 4 + 3];
     const float sx = static_cast<float>(out_w) / static_cast<float>(img_w);
     const float sy = static_cast<float>(out_h) / static_cast<float>(img_h);
     if (p.do_postprocess) {
         for (int i = threadIdx.x; i < nkeep; i += blockDim.x) {
-            float4 bx = boxes[list[i]];
+            float4 bx = m.boxes[m.list[i]];
             bx.x = fminf(fmaxf(bx.x * sx, 0.f), static_cast<float>(out_w));
             bx.z = fminf(fmaxf(bx.z * sx, 0.f), static_cast<float>(out_w));
             bx.y = fminf(fmaxf(bx.y * sy, 0.f), static_cast<float>(out_h));
             bx.w = fminf(fmaxf(bx.w * sy, 0.f), static_cast<float>(out_h));
-            flag[i] = ((bx.z - bx.x) > 0.f && (bx.w - bx.y) > 0.f) ? 1 : 0;
+            m.flag[i] = ((bx.z - bx.x) > 0.f && (bx.w - bx.y) > 0.f) ? 1 : 0;
         }
         __syncthreads();
-        const int m = compact_indices(flag, nkeep, list2, s_warp_sums, &s_base);
-        for (int i = threadIdx.x; i < m; i += blockDim.x) list2[i] = list[list2[i]];
+        const int k2 = compact_indices(m.flag, nkeep, m.list2, s_warp_sums, s_base);
+        for (int i = threadIdx.x; i < k2; i += blockDim.x) m.list2[i] = m.list[m.list2[i]];
         __syncthreads();
-        for (int i = threadIdx.x; i < m; i += blockDim.x) list[i] = list2[i];
+        for (int i = threadIdx.x; i < k2; i += blockDim.x) m.list[i] = m.list2[i];
         __syncthreads();
-        nkeep = m;
+        nkeep = k2;
     }
     if (threadIdx.x == 0) {
         if (nkeep > p.out_cap) atomicOr(p.flags, 2);
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     const int nout = min(nkeep, p.out_cap);
     Det* out = p.out + static_cast<size_t>(b) * p.out_cap;
     for (int i = threadIdx.x; i < nout; i += blockDim.x) {
-        Det d = cand[val[list[i]]];
+        Det d = cand[m.val[m.list[i]]];
         if (p.do_postprocess) {
             d.box[0] = fminf(fmaxf(d.box[0] * sx, 0.f), static_cast<float>(out_w));
             d.box[2] = fminf(fmaxf(d.box[2] * sx, 0.f), static_cast<float>(out_w));
@@ -287,23 +290,200 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------------------- single-CTA kernel
+// One CTA per image does everything (used when no scratch is given -- the TTA merge -- and when NMS is off).
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_constant__ NmsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int b = blockIdx.x;
+    const int cap = kLevels * p.topk;
+    NmsSmem m = carve(smem_raw, cap);
+    __shared__ int s_warp_sums[33];
+    __shared__ int s_base;
+    __shared__ int s_lvl_off[kLevels + 1];
+    __shared__ unsigned long long s_kept_mask;
+    __shared__ unsigned long long s_diag[64];
+    const Det* cand = p.cand + static_cast<size_t>(b) * cap;
+    const int n = sort_candidates(p, b, cand, m, s_lvl_off);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const Det& d = cand[m.val[i]];
+        m.boxes[i] = make_float4(d.box[0], d.box[1], d.box[2], d.box[3]);
+        m.cls[i] = static_cast<uint8_t>(d.cls);
+        m.flag[i] = 0;  // removed flag
+    }
+    __syncthreads();
+    const bool suppress = p.do_nms && p.nms_thresh > 0.f;
+    if (suppress) {
+        greedy_nms(m.boxes, m.cls, m.flag, n, p.nms_thresh, s_diag, &s_kept_mask);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) m.flag[i] = m.flag[i] ? 0 : 1;  // keep flags = !removed
+        __syncthreads();
+    }
+    finish_image(p, b, cand, m, n, suppress, s_warp_sums, &s_base);
+}
+
+// ---------------------------------------------------------------------------------------------- class-parallel path
+// batched_nms never lets boxes of different classes suppress each other (detectron2 batched_nms -> torchvision: per-class
+// coordinate offsets), so the greedy scan is independent per (image, class): with one CTA per image the 32 CTAs of a V2-99
+// batch leave 116 SMs idle for ~0.9 ms (8 CTAs for the DLA-34 batch: 8 % of its step).  Three launches:
+//   nms_sort_kernel  (B CTAs)      : sort the image's candidates by score_3d, publish order / class
+//   nms_class_kernel (C x B CTAs)  : ordered sub-list of one class -> greedy NMS -> removed flags by sorted position
+//   nms_finish_kernel(B CTAs)      : survivors in sorted order -> post-NMS top-k -> postprocess -> output
+// Same kept set and order as the single-CTA kernel (tests/test_kernels_gpu.py compares both with the oracle).
+struct NmsScratch {
+    uint16_t* order;   // [B][cap] sorted position -> candidate slot
+    uint8_t* cls;      // [B][cap]
+    uint8_t* removed;  // [B][cap]
+    int32_t* n;        // [B]
+};
+
+__device__ __forceinline__ NmsScratch bind_nms_scratch(void* scratch, int B, int cap) {
+    NmsScratch s;
+    uint8_t* q = static_cast<uint8_t*>(scratch);
+    s.order = reinterpret_cast<uint16_t*>(q);
+    q += (static_cast<size_t>(B) * cap * 2 + 255) / 256 * 256;
+    s.cls = q;
+    q += (static_cast<size_t>(B) * cap + 255) / 256 * 256;
+    s.removed = q;
+    q += (static_cast<size_t>(B) * cap + 255) / 256 * 256;
+    s.n = reinterpret_cast<int32_t*>(q);
+    return s;
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_sort_kernel(const __grid_constant__ NmsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int b = blockIdx.x;
+    const int cap = kLevels * p.topk;
+    NmsSmem m = carve(smem_raw, cap);
+    __shared__ int s_lvl_off[kLevels + 1];
+    const Det* cand = p.cand + static_cast<size_t>(b) * cap;
+    const int n = sort_candidates(p, b, cand, m, s_lvl_off);
+    const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int slot = m.val[i];
+        sc.order[static_cast<size_t>(b) * cap + i] = static_cast<uint16_t>(slot);
+        sc.cls[static_cast<size_t>(b) * cap + i] = static_cast<uint8_t>(cand[slot].cls);
+        sc.removed[static_cast<size_t>(b) * cap + i] = 0;
+    }
+    if (threadIdx.x == 0) sc.n[b] = n;
+}
+
+constexpr int kClassThreads = 512;
+
+__global__ void __launch_bounds__(kClassThreads, 1) nms_class_kernel(const __grid_constant__ NmsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int c = blockIdx.x, b = blockIdx.y;
+    const int cap = kLevels * p.topk;
+    float4* boxes = reinterpret_cast<float4*>(smem_raw);            // [cap]
+    uint16_t* pos = reinterpret_cast<uint16_t*>(boxes + cap);       // [cap] sorted position of the class's k-th box
+    uint8_t* flag = reinterpret_cast<uint8_t*>(pos + cap);          // [cap]
+    __shared__ int s_warp_sums[kClassThreads / 32];
+    __shared__ int s_base;
+    __shared__ unsigned long long s_kept_mask;
+    __shared__ unsigned long long s_diag[64];
+    const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap);
+    const int n = sc.n[b];
+    const uint8_t* cls = sc.cls + static_cast<size_t>(b) * cap;
+    const uint16_t* order = sc.order + static_cast<size_t>(b) * cap;
+    const Det* cand = p.cand + static_cast<size_t>(b) * cap;
+    // order-preserving compaction of the sorted positions that hold class c
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int start = 0; start < n; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        const int f = (i < n && cls[i] == c) ? 1 : 0;
+        const unsigned mk = __ballot_sync(0xffffffffu, f);
+        const int prefix = __popc(mk & ((1u << lane) - 1));
+        if (lane == 0) s_warp_sums[warp] = __popc(mk);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += s_warp_sums[w];
+        const int base = s_base;
+        if (f) {
+            const int k = base + before + prefix;
+            pos[k] = static_cast<uint16_t>(i);
+            const Det& d = cand[order[i]];
+            boxes[k] = make_float4(d.box[0], d.box[1], d.box[2], d.box[3]);
+            flag[k] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < kClassThreads / 32; ++w) tot += s_warp_sums[w];
+            s_base = base + tot;
+        }
+        __syncthreads();
+    }
+    const int nc = s_base;
+    if (nc <= 1) return;  // nothing to suppress (block-uniform)
+    greedy_nms(boxes, nullptr, flag, nc, p.nms_thresh, s_diag, &s_kept_mask);
+    uint8_t* removed = sc.removed + static_cast<size_t>(b) * cap;
+    for (int k = threadIdx.x; k < nc; k += blockDim.x)
+        if (flag[k]) removed[pos[k]] = 1;
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_finish_kernel(const __grid_constant__ NmsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int b = blockIdx.x;
+    const int cap = kLevels * p.topk;
+    NmsSmem m = carve(smem_raw, cap);
+    __shared__ int s_warp_sums[33];
+    __shared__ int s_base;
+    const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap);
+    const Det* cand = p.cand + static_cast<size_t>(b) * cap;
+    const int n = sc.n[b];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int slot = sc.order[static_cast<size_t>(b) * cap + i];
+        m.val[i] = static_cast<uint16_t>(slot);
+        const Det& d = cand[slot];
+        m.boxes[i] = make_float4(d.box[0], d.box[1], d.box[2], d.box[3]);
+        m.flag[i] = sc.removed[static_cast<size_t>(b) * cap + i] ? 0 : 1;  // keep flags
+    }
+    __syncthreads();
+    finish_image(p, b, cand, m, n, true, s_warp_sums, &s_base);
+}
+
 }  // namespace
+
+static int g_class_parallel = -1;
+void nms_set_class_parallel(int mode) { g_class_parallel = (mode == 0 || mode == 1) ? mode : -1; }
+
+size_t nms_scratch_bytes(int B, int topk) {
+    const size_t cap = static_cast<size_t>(kLevels) * topk;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    return up(B * cap * 2) + 2 * up(B * cap) + up(static_cast<size_t>(B) * 4);
+}
 
 cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream) {
     const int cap = kLevels * p.topk;
     if (cap > kMaxCand || p.B <= 0) return cudaErrorInvalidValue;
     const size_t smem = static_cast<size_t>(kMaxCand) * 8 + static_cast<size_t>(cap) * 16 +
                         static_cast<size_t>(cap) * 8 + static_cast<size_t>(kMaxCand) * 2 + static_cast<size_t>(cap) * 2;
+    const size_t smem_cls = static_cast<size_t>(cap) * (16 + 2 + 1);
     static size_t attr_smem_dev[64] = {};  // per device; the limit is 227 KiB minus the static shared memory: ask for what we use
     size_t& attr_smem = attr_smem_dev[current_device_or_zero()];
     if (smem > attr_smem) {
-        cudaError_t e =
-            cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(nms_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cls));
         if (e != cudaSuccess) {
             cudaGetLastError();
             return e;
         }
         attr_smem = smem;
+    }
+    if (g_class_parallel < 0) {  // DD3D_NMS_CLASS_PARALLEL=0 / dd3d_set_conv_policy("nms_class_parallel", 0): single-CTA kernel
+        const char* e = getenv("DD3D_NMS_CLASS_PARALLEL");
+        g_class_parallel = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (g_class_parallel && p.scratch != nullptr && p.do_nms && p.nms_thresh > 0.f && p.num_classes >= 1 && p.num_classes <= 255) {
+        nms_sort_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);
+        nms_class_kernel<<<dim3(p.num_classes, p.B), kClassThreads, smem_cls, stream>>>(p);
+        nms_finish_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);
+        return cudaGetLastError();
     }
     nms_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);
     return cudaGetLastError();

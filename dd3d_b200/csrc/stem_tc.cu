@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(160) stem_tc_kernel(const __nv_bfloat16* __res
     uint8_t* sB = smem + KB * 16384;        // [KB][COUT rows][128 B]
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_scale[COUT];  // folded BN, read as broadcast LDS.128 in the epilogue (128 scalar LDG
+    __shared__ __align__(16) float s_bias[COUT];   // per thread and tile before)
+    const uint32_t sA_u32 = ptx::smem_u32(sA);     // explicit STS: the integer-aligned pointer would compile to generic ST.E
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
@@ -70,7 +73,11 @@ __global__ void __launch_bounds__(160) stem_tc_kernel(const __nv_bfloat16* __res
     }
     if (tid < 128) {  // zero the K padding of the operand rows once (chunks >= CHUNKS never change)
         for (int q = CHUNKS; q < KB * 8; ++q)
-            *reinterpret_cast<uint4*>(sA + (q >> 3) * 16384 + tid * 128 + (((q & 7) ^ (tid & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+            ptx::st_shared_v4(sA_u32 + (q >> 3) * 16384 + tid * 128 + (((q & 7) ^ (tid & 7)) << 4), make_uint4(0, 0, 0, 0));
+    }
+    for (int i = tid; i < COUT; i += blockDim.x) {
+        s_scale[i] = __ldg(scale + i);
+        s_bias[i] = __ldg(bias + i);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -112,8 +119,8 @@ __global__ void __launch_bounds__(160) stem_tc_kernel(const __nv_bfloat16* __res
             v[KS * KS] = make_uint2(0u, 0u);
 #pragma unroll
             for (int q = 0; q < CHUNKS; ++q)
-                *reinterpret_cast<uint4*>(sA + (q >> 3) * 16384 + tid * 128 + (((q & 7) ^ (tid & 7)) << 4)) =
-                    make_uint4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+                ptx::st_shared_v4(sA_u32 + (q >> 3) * 16384 + tid * 128 + (((q & 7) ^ (tid & 7)) << 4),
+                                  make_uint4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y));
             ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         }
         __syncthreads();
@@ -152,11 +159,16 @@ __global__ void __launch_bounds__(160) stem_tc_kernel(const __nv_bfloat16* __res
                     for (int i = 0; i < cols; i += 8) {
                         uint32_t o[4];
 #pragma unroll
+                        const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + c0 + i);
+                        const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + c0 + i + 4);
+                        const float4 bi0 = *reinterpret_cast<const float4*>(s_bias + c0 + i);
+                        const float4 bi1 = *reinterpret_cast<const float4*>(s_bias + c0 + i + 4);
+                        const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                        const float biv[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+#pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int n = c0 + i + 2 * j;
-                            const float y0 = fmaxf(fmaf(__uint_as_float(v[i + 2 * j]), __ldg(scale + n), __ldg(bias + n)), 0.f);
-                            const float y1 =
-                                fmaxf(fmaf(__uint_as_float(v[i + 2 * j + 1]), __ldg(scale + n + 1), __ldg(bias + n + 1)), 0.f);
+                            const float y0 = fmaxf(fmaf(__uint_as_float(v[i + 2 * j]), scv[2 * j], biv[2 * j]), 0.f);
+                            const float y1 = fmaxf(fmaf(__uint_as_float(v[i + 2 * j + 1]), scv[2 * j + 1], biv[2 * j + 1]), 0.f);
                             o[j] = pack2_act(y0, y1, fp16);
                         }
                         *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(o[0], o[1], o[2], o[3]);

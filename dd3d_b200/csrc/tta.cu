@@ -13,6 +13,8 @@
 // descending scores_3d order (merged_instances[keep]).
 #include "detect.cuh"
 
+#include <string.h>
+
 namespace dd3d {
 
 namespace {
@@ -140,6 +142,7 @@ cudaError_t launch_tta_merge(const Det* dets, const int32_t* counts, const TtaVi
     // one class-aware NMS over the merged set (all candidates sit in "level 0" of the NMS kernel's layout); no top-k,
     // no rescale: test_time_augmentation.py:163-171
     NmsParams np;
+    memset(&np, 0, sizeof(np));  // scratch = nullptr: single-CTA kernel (one merged set)
     np.cand = p.cand;
     np.cand_count = p.cand_count;
     np.sizes = p.cand_count;  // read but unused without do_postprocess

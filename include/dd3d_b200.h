@@ -163,6 +163,7 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value);
  * "cta2" = 0 single-CTA conv kernel everywhere, 1 CTA pairs (tcgen05.mma.cta_group::2) wherever legal, 2 auto (default:
  * pairs for block_n >= 160 and >= 296 tiles), -1 back to the DD3D_CONV_CTA2 environment setting.
  * "op_fp16" = 1: the dd3d_op_* entry points below treat their 16-bit buffers as fp16 (default 0: bf16).
+ * "nms_class_parallel" = 0: one CTA per image does the whole NMS instead of one CTA per (class, image) (default 1).
  * "taps" = 0: 3x3 convs with <= 16 output channels use the per-tap kernels instead of the taps-in-N kernel (default 1). */
 int dd3d_set_conv_policy(const char* name, int value);
 /* Number of kernel launches one dd3d_forward enqueues (for the bench's gpu_launches claim). */

@@ -260,6 +260,18 @@ def test_decode_and_nms_vs_oracle(arch, rate, seed):
     _decode_case(arch, rate, seed, {})
 
 
+@pytest.mark.parametrize("arch,rate,seed", [("v2_99", -0.5, 1), ("dla34", -2.0, 2)])
+def test_decode_and_nms_single_cta_path_vs_oracle(arch, rate, seed):
+    """The same decode + NMS cases through the one-CTA-per-image NMS kernel (the path the TTA merge uses; the default
+    engine path runs one CTA per (class, image))."""
+    L = lib.load()
+    try:
+        assert L.dd3d_set_conv_policy(b"nms_class_parallel", 0) == 0
+        _decode_case(arch, rate, seed, {})
+    finally:
+        L.dd3d_set_conv_policy(b"nms_class_parallel", -1)
+
+
 @pytest.mark.parametrize("flags", [
     dict(FEATURE_LOCATIONS_OFFSET="half"), dict(PREDICT_DISTANCE=True), dict(PREDICT_ALLOCENTRIC_ROT=False),
     dict(SCALE_DEPTH_BY_FOCAL_LENGTHS=False),
