@@ -129,6 +129,10 @@ int dd3d_set_conv_policy(const char* name, int value) {
         conv_set_taps(value);
         return DD3D_OK;
     }
+    if (!strcmp(name, "n_split")) {
+        conv_set_n_split(value);
+        return DD3D_OK;
+    }
     if (!strcmp(name, "op_fp16")) {
         g_op_fp16 = value ? 1 : 0;
         return DD3D_OK;
@@ -204,6 +208,9 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value) {
             e.opt_profile = value ? 1 : 0;
         } else if (n == "workspace_reuse") {  // applies to plans made afterwards
             e.opt_workspace_reuse = value ? 1 : 0;
+        } else if (n == "dla_front") {  // 1 (default): fused DLA-34 front end (dla_front.cu); 0: layer by layer
+            if (e.opt_dla_front != (value ? 1 : 0)) e.drop_plans();
+            e.opt_dla_front = value ? 1 : 0;
         } else if (n == "workspace_fill") {
             e.opt_workspace_fill = (value >= 0 && value <= 255) ? value : -1;
         } else {
@@ -389,6 +396,17 @@ int dd3d_op_stem_conv(const void* d_in4, const void* d_w, const float* d_scale, 
                        nullptr);
 }
 
+int dd3d_op_dla_front(const void* d_in4, const void* d_w0, const void* d_w1, const void* d_w2, const float* d_sb0,
+                      const float* d_sb1, const float* d_sb2, void* d_out, int out_pitch, void* d_pool, int pool_pitch,
+                      int B, int H, int W, dd3d_stream stream) {
+    using bf = __nv_bfloat16;
+    return cuda_status(launch_dla_front(static_cast<const bf*>(d_in4), static_cast<const bf*>(d_w0), static_cast<const bf*>(d_w1),
+                                        static_cast<const bf*>(d_w2), d_sb0, d_sb1, d_sb2, static_cast<bf*>(d_out), out_pitch,
+                                        static_cast<bf*>(d_pool), pool_pitch, B, H, W, device_sms(),
+                                        static_cast<cudaStream_t>(stream), g_op_fp16),
+                       nullptr);
+}
+
 int dd3d_op_preprocess(const void* d_images, int img_dtype, const int32_t* d_sizes2, void* d_out4, int B, int Hs, int Ws,
                        int Hp, int Wp, const float* h_mean, const float* h_std, dd3d_stream stream) {
     return cuda_status(launch_preprocess(d_images, img_dtype == DD3D_IMG_U8, d_sizes2, 2, static_cast<__nv_bfloat16*>(d_out4),
@@ -491,7 +509,7 @@ int dd3d_op_sample_aggregate(dd3d_det* d_dets, int32_t* d_counts, const float* d
 
 int64_t dd3d_op_detect_scratch_bytes(int B, int pre_nms_topk) {
     return static_cast<int64_t>(decode_scratch_bytes(B, pre_nms_topk)) + DD3D_MAX_CLASSES * 3 * 4 + 512 +
-           static_cast<int64_t>(nms_scratch_bytes(B, pre_nms_topk));
+           static_cast<int64_t>(nms_scratch_bytes(B, pre_nms_topk, DD3D_MAX_CLASSES));
 }
 
 int dd3d_op_detect(const dd3d_model_desc* desc, int B, const int32_t* h_level_hw, const int32_t* h_strides,

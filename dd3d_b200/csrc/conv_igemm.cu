@@ -1197,6 +1197,16 @@ void conv_finalize_params(ConvParams* p) {
 }
 
 static int g_cta2_mode = -1;
+static int g_n_split = -1;
+
+bool conv_n_split_enabled() {
+    if (g_n_split < 0) {
+        const char* e = getenv("DD3D_CONV_NSPLIT");
+        g_n_split = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return g_n_split != 0;
+}
+void conv_set_n_split(int mode) { g_n_split = (mode == 0 || mode == 1) ? mode : -1; }
 
 int conv_use_cta2() {  // 0 never, 1 always (where legal), 2 auto (per-layer rule in conv_finalize_params)
     if (g_cta2_mode < 0) {

@@ -92,7 +92,10 @@ bool conv_prefer_halo(int taps, int stride, int block_n, int nseg, const int* Hs
 constexpr int kTapsN = 144;
 bool make_weight_map_taps(CUtensorMap* map, const void* base, int cin_pad, int fp16 = 0);
 bool conv_taps_eligible(int taps, int stride, int cout_pad, int nseg, const int* Hs, const int* Ws);
-void conv_set_taps(int mode);  // 0 off, 1 on, -1 environment / default (on)
+void conv_set_taps(int mode);
+// N-split of under-filled launches (engine.cu Builder::conv): 1 on (default; DD3D_CONV_NSPLIT=0 turns it off), -1 = environment
+bool conv_n_split_enabled();
+void conv_set_n_split(int mode);  // 0 off, 1 on, -1 environment / default (on)
 // Fills num_stages / tmem_cols / total_work / tile bookkeeping from the already-set fields.
 void conv_finalize_params(ConvParams* p);
 cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream);

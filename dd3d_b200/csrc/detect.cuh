@@ -82,8 +82,8 @@ struct NmsParams {
     int B, topk, out_cap;
     int do_nms, post_topk, do_postprocess;
     float nms_thresh;
-    void* scratch;    // nms_scratch_bytes(B, topk) bytes, or nullptr: single-CTA kernel (one CTA per image)
-    int num_classes;  // with scratch: one greedy scan per (class, image) CTA
+    void* scratch;    // nms_scratch_bytes(B, topk, num_classes) bytes, or nullptr: single-CTA kernel (one CTA per image)
+    int num_classes;  // with scratch: IoU bit matrix on all SMs + one scan CTA per (class, image)
 };
 
 size_t decode_scratch_bytes(int B, int topk);
@@ -95,8 +95,8 @@ cudaError_t launch_decode(const DecodeParams& p, cudaStream_t stream);  // = sel
 cudaError_t launch_decode_select(const DecodeParams& p, cudaStream_t stream);
 cudaError_t launch_decode_final(const DecodeParams& p, cudaStream_t stream);
 cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream);
-size_t nms_scratch_bytes(int B, int topk);
-void nms_set_class_parallel(int mode);  // 0 single-CTA kernel, 1 per-(class, image) CTAs, -1 environment / default (1)
+size_t nms_scratch_bytes(int B, int topk, int num_classes);
+void nms_set_class_parallel(int mode);  // 0 single-CTA kernel, 1 multi-CTA path (sort / IoU bit matrix / scan / finish), -1 environment / default (1)
 // BEV rotated NMS on the (already 2-D-NMSed, score-sorted) detections, in place; poses: [B][7] (w,x,y,z, tx,ty,tz).
 cudaError_t launch_bev_nms(Det* dets, int32_t* counts, const float* K, const float* poses, const int32_t* sizes,
                            int32_t* flags, int B, int cap, float thr, int do_postprocess, cudaStream_t stream);

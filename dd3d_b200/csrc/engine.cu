@@ -12,6 +12,7 @@
 #include "act16.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -49,6 +50,7 @@ Engine::Engine(const dd3d_model_desc& d) : desc(d) {
                                 std::to_string(prop.major) + std::to_string(prop.minor));
     }
     num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("DD3D_DLA_FRONT")) opt_dla_front = atoi(e) ? 1 : 0;  // A/B runs of bench.py; default 1
 }
 
 Engine::~Engine() {
@@ -355,8 +357,27 @@ struct Builder {
                 g.res_W = sp.res.W;
             }
         }
+        // Under-filled launches (DLA-34 level5 at B = 8: 30 M-tiles x 2 N-blocks on 148 SMs; p6 / p7): split N until the grid
+        // covers the machine.  Each CTA's serial MMA chain shrinks with N (128 -> 64 -> 32 cycles per K = 16 step) while the
+        // A tiles it re-reads are tiny; K order per output element is unchanged, so results are bit-identical.
+        bool n_split = false;
+        if (!p.taps_n && conv_n_split_enabled()) {
+            int tiles = 0;
+            for (int s = 0; s < p.nseg; ++s)
+                tiles += B * ((p.seg[s].H + p.seg[s].th - 1) / p.seg[s].th) * ((p.seg[s].W + p.seg[s].tw - 1) / p.seg[s].tw);
+            while (tiles * p.n_blocks * 2 <= E->num_sms && p.block_n % 32 == 0 && p.block_n / 2 >= 64) {
+                p.block_n /= 2;
+                p.n_blocks *= 2;
+                n_split = true;
+            }
+        }
         conv_finalize_params(&p);
-        p.w_map = p.taps_n ? L.w_map_taps : (p.cta2 ? L.w_map_half : L.w_map);
+        if (n_split) {
+            if (!make_weight_map(&p.w_map, L.d_w, L.ktot, L.cout_pad, p.cta2 ? p.block_n / 2 : p.block_n, E->fp16))
+                fail(DD3D_ERR_CUDA, conv_last_error());
+        } else {
+            p.w_map = p.taps_n ? L.w_map_taps : (p.cta2 ? L.w_map_half : L.w_map);
+        }
         for (int s = 0; s < p.nseg; ++s)
             op.flops += 2.0 * B * p.seg[s].H * p.seg[s].W * static_cast<double>(L.cout) * L.cin * L.taps;
         if (!f32_out) {
@@ -450,16 +471,33 @@ struct Builder {
     void build_dla34(View input, std::vector<View>* feats) {
         const std::string p = "backbone.bottom_up";
         const int H = input.H, W = input.W;
-        View a0 = alloc(H, W, 16);
-        stem(p + ".base_layer", p + ".base_layer.norm", input, a0, 7, 1);
-        View a1 = alloc(H, W, 16);
-        conv1(p + ".level0.0", p + ".level0.0.norm", false, a0, a1, 3, 1, true);
-        View a2 = alloc(H / 2, W / 2, 32);
-        conv1(p + ".level1.0", p + ".level1.0.norm", false, a1, a2, 3, 2, true);
+        // both forms of the front end are packed at finalize (host weights are dropped afterwards), so that the
+        // "dla_front" option can be flipped on a finalized engine
+        const FrontLayer& F = E->front_layer(p);
+        E->stem_layer(p + ".base_layer", p + ".base_layer.norm", 7, 1);
+        E->conv_layer(p + ".level0.0", {p + ".level0.0"}, 16, 3);
+        E->bn_epilogue(p + ".level0.0|" + p + ".level0.0.norm", p + ".level0.0.norm", "", 16);
+        E->conv_layer(p + ".level1.0", {p + ".level1.0"}, 16, 3);
+        E->bn_epilogue(p + ".level1.0|" + p + ".level1.0.norm", p + ".level1.0.norm", "", 32);
+        View a2, bottom;
+        if (E->opt_dla_front && H % 4 == 0 && W % 4 == 0) {
+            // base_layer -> level0 -> level1 -> 2x2 max-pool in one kernel (dla_front.cu); the two full-resolution
+            // 16-channel maps never reach HBM
+            a2 = alloc(H / 2, W / 2, 32);
+            bottom = alloc(H / 4, W / 4, 32);
+            front(F, input, a2, bottom);
+        } else {
+            View a0 = alloc(H, W, 16);
+            stem(p + ".base_layer", p + ".base_layer.norm", input, a0, 7, 1);
+            View a1 = alloc(H, W, 16);
+            conv1(p + ".level0.0", p + ".level0.0.norm", false, a0, a1, 3, 1, true);
+            a2 = alloc(H / 2, W / 2, 32);
+            conv1(p + ".level1.0", p + ".level1.0.norm", false, a1, a2, 3, 2, true);
+            bottom = alloc(H / 4, W / 4, 32);
+            maxpool(a2, bottom, 2);
+        }
         // level2: Tree(levels=1, 32->64, stride 2)
         View rc = alloc(H / 4, W / 4, 128);
-        View bottom = alloc(H / 4, W / 4, 32);
-        maxpool(a2, bottom, 2);
         View l2 = alloc(H / 4, W / 4, 64);
         dla_tree1(p + ".level2", a2, 32, 64, 2, rc, bottom, l2);
         View l3 = dla_tree2(p + ".level3", l2, 64, 128);
@@ -471,6 +509,26 @@ struct Builder {
         View l5 = alloc(H / 32, W / 32, 512);
         dla_tree1(p + ".level5", l4, 256, 512, 2, rc5, bottom5, l5);
         feats->assign({l3, l4, l5});
+    }
+
+    void front(const FrontLayer& F, View in4, View out, View pooled) {
+        touch(out);
+        touch(pooled);
+        ++op_idx;
+        if (dry) return;
+        Op op;
+        op.type = Op::FRONT;
+        op.in = in4;
+        op.out = out;
+        op.identity = pooled;
+        op.front = &F;
+        op.outs[0] = out;
+        op.outs[1] = pooled;
+        op.nouts = 2;
+        const double px = static_cast<double>(B) * in4.H * in4.W;
+        op.flops = 2.0 * px * (16.0 * 3 * 49 + 16.0 * 16 * 9 + 32.0 * 16 * 9 / 4);
+        op.bytes = px * (8.0 + 64.0 / 4 + 64.0 / 16);
+        P->ops.push_back(op);
     }
 
     void stem(const std::string& wname, const std::string& bn, View in4, View out, int ksize, int stride) {
@@ -821,6 +879,51 @@ const StemLayer& Engine::stem_layer(const std::string& wname, const std::string&
     return stems.emplace(wname, S).first->second;
 }
 
+// DLA-34 base_layer / level0 / level1 in the layouts dla_front.cu reads: base_layer [16][7][8][4] (kernel column 7 and
+// the 4th input channel are zero), level0 [16][9][16], level1 [32][9][16]; folded BN as scale[cout] | bias[cout].
+const FrontLayer& Engine::front_layer(const std::string& prefix) {
+    auto it = fronts.find(prefix);
+    if (it != fronts.end()) return it->second;
+    const HostTensor& w0 = weight(prefix + ".base_layer.weight");
+    const HostTensor& w1 = weight(prefix + ".level0.0.weight");
+    const HostTensor& w2 = weight(prefix + ".level1.0.weight");
+    auto is = [](const HostTensor& w, int64_t a, int64_t b, int64_t k) {
+        return w.shape.size() == 4 && w.shape[0] == a && w.shape[1] == b && w.shape[2] == k && w.shape[3] == k;
+    };
+    if (!is(w0, 16, 3, 7) || !is(w1, 16, 16, 3) || !is(w2, 32, 16, 3)) fail(DD3D_ERR_INVALID, "bad DLA front weights: " + prefix);
+    std::vector<uint16_t> p0(16 * 7 * 8 * 4, 0), p1(16 * 9 * 16, 0), p2(32 * 9 * 16, 0);
+    for (int co = 0; co < 16; ++co)
+        for (int c = 0; c < 3; ++c)
+            for (int ky = 0; ky < 7; ++ky)
+                for (int kx = 0; kx < 7; ++kx)
+                    p0[((co * 7 + ky) * 8 + kx) * 4 + c] = host_f32_to_act(w0.data[((co * 3 + c) * 7 + ky) * 7 + kx], fp16);
+    for (int co = 0; co < 16; ++co)
+        for (int ci = 0; ci < 16; ++ci)
+            for (int t = 0; t < 9; ++t) p1[(co * 9 + t) * 16 + ci] = host_f32_to_act(w1.data[(co * 16 + ci) * 9 + t], fp16);
+    for (int co = 0; co < 32; ++co)
+        for (int ci = 0; ci < 16; ++ci)
+            for (int t = 0; t < 9; ++t) p2[(co * 9 + t) * 16 + ci] = host_f32_to_act(w2.data[(co * 16 + ci) * 9 + t], fp16);
+    auto up16 = [&](const std::vector<uint16_t>& v) {
+        __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dev_alloc(v.size() * 2));
+        cuda_check(cudaMemcpy(d, v.data(), v.size() * 2, cudaMemcpyHostToDevice), "upload DLA front weights");
+        return d;
+    };
+    auto sb = [&](const std::string& bn, int cout) {
+        std::vector<float> s, b;
+        bn_fold(bn, "", cout, &s, &b);
+        s.insert(s.end(), b.begin(), b.end());
+        return upload_f32(s);
+    };
+    FrontLayer F;
+    F.d_w0 = up16(p0);
+    F.d_w1 = up16(p1);
+    F.d_w2 = up16(p2);
+    F.d_sb0 = sb(prefix + ".base_layer.norm", 16);
+    F.d_sb1 = sb(prefix + ".level0.0.norm", 16);
+    F.d_sb2 = sb(prefix + ".level1.0.norm", 32);
+    return fronts.emplace(prefix, F).first->second;
+}
+
 const EseLayer& Engine::ese_layer(const std::string& fc, int C) {
     auto it = eses.find(fc);
     if (it != eses.end()) return it->second;
@@ -922,7 +1025,7 @@ size_t Engine::build(Plan* P, int B, int Hs, int Ws, void* workspace, bool dry) 
         bld.build_heads(fpn);
         // detection scratch + staging for the host-facing path
         P->detect_scratch = bld.alloc_bytes(decode_scratch_bytes(B, desc.pre_nms_topk));
-        P->nms_scratch = bld.alloc_bytes(nms_scratch_bytes(B, desc.pre_nms_topk));
+        P->nms_scratch = bld.alloc_bytes(nms_scratch_bytes(B, desc.pre_nms_topk, desc.num_classes));
         P->d_K = static_cast<float*>(bld.alloc_bytes(static_cast<size_t>(B) * 9 * 4));
         P->d_sizes = static_cast<int32_t*>(bld.alloc_bytes(static_cast<size_t>(B) * 4 * 4));
         P->d_out = static_cast<Det*>(bld.alloc_bytes(static_cast<size_t>(B) * desc.out_cap * sizeof(Det)));
@@ -963,6 +1066,13 @@ void Engine::free_plan(Plan* P) {
 }
 
 void Engine::release_plan() { free_plan(&plan); }
+
+void Engine::drop_plans() {
+    if (slot_busy[0] || slot_busy[1]) fail(DD3D_ERR_STATE, "plan change with a pending dd3d_submit_host");
+    release_plan();
+    for (auto& kv : plan_cache) free_plan(&kv.second);
+    plan_cache.clear();
+}
 
 void Engine::make_plan(int B, int Hs, int Ws, void* workspace, size_t bytes) {
     if (!finalized) fail(DD3D_ERR_STATE, "plan before finalize");
@@ -1069,7 +1179,7 @@ void fill_nms_params(NmsParams* np, const dd3d_model_desc& desc, const DecodePar
 }
 
 int Engine::launches_per_forward() const {
-    int n = 1 /*preprocess*/ + 5 /*decode*/ + ((desc.do_nms && desc.nms_thresh > 0.f) ? 3 : 1) /*nms: sort, per class, finish*/;
+    int n = 1 /*preprocess*/ + 5 /*decode*/ + ((desc.do_nms && desc.nms_thresh > 0.f) ? 4 : 1) /*nms: sort, IoU bit matrix, scan, finish*/;
     for (const Op& op : plan.ops) n += (op.type == Op::ESE) ? 3 : 1;
     return n;
 }
@@ -1180,8 +1290,14 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
                                        num_sms, stream),
                            "relu");
                 break;
+            case Op::FRONT:
+                cuda_check(launch_dla_front(op.in.ptr, op.front->d_w0, op.front->d_w1, op.front->d_w2, op.front->d_sb0,
+                                            op.front->d_sb1, op.front->d_sb2, op.out.ptr, op.out.pitch, op.identity.ptr,
+                                            op.identity.pitch, P.B, op.in.H, op.in.W, num_sms, stream, fp16),
+                           "dla front");
+                break;
         }
-        mark(op.type == Op::STEM ? 1 : op.type == Op::CONV ? 2 : op.type == Op::POOL ? 3 : op.type == Op::ESE ? 4 : 5);
+        mark((op.type == Op::STEM || op.type == Op::FRONT) ? 1 : op.type == Op::CONV ? 2 : op.type == Op::POOL ? 3 : op.type == Op::ESE ? 4 : 5);
     }
     DecodeParams dp = P.decode;
     dp.K = d_K;
@@ -1251,10 +1367,15 @@ void Engine::get_profile(double* ms, double* flops, double* bytes, int32_t* laun
                 launches[5] += 1;
                 bytes[5] += in_px * op.in.C * 4;
                 break;
+            case Op::FRONT:
+                launches[1] += 1;
+                flops[1] += op.flops;
+                bytes[1] += op.bytes;
+                break;
         }
     }
     launches[6] = 5;
-    launches[7] = (desc.do_nms && desc.nms_thresh > 0.f) ? 3 : 1;
+    launches[7] = (desc.do_nms && desc.nms_thresh > 0.f) ? 4 : 1;
     for (int l = 0; l < kLevels; ++l)  // two dense passes over the fp32 logits + centerness
         bytes[6] += 2.0 * P.B * P.lvl_h[l] * P.lvl_w[l] * (C + 1) * 4;
 }

@@ -60,6 +60,10 @@ struct StemLayer {
     int ksize, stride, cout;
     Epilogue epi;
 };
+struct FrontLayer {  // DLA-34 base_layer + level0 + level1 packed for dla_front.cu
+    __nv_bfloat16 *d_w0, *d_w1, *d_w2;
+    float *d_sb0, *d_sb1, *d_sb2;
+};
 struct EseLayer {
     float* d_w;
     float* d_b;
@@ -67,7 +71,7 @@ struct EseLayer {
 };
 
 struct Op {
-    enum Type { CONV, STEM, POOL, ESE, RELU } type;
+    enum Type { CONV, STEM, POOL, ESE, RELU, FRONT } type;
     ConvParams conv;
     View in, out, identity;
     View outs[kMaxSeg];  // bf16 output views (CONV: one per segment; others: outs[0] == out), for dd3d_get_tensor "op<i>"
@@ -76,6 +80,7 @@ struct Op {
     int ksize = 0, stride = 0;
     const StemLayer* stem = nullptr;
     const EseLayer* ese = nullptr;
+    const FrontLayer* front = nullptr;  // FRONT: in = input, out = level1 output, identity = its 2x2 max-pool
     float* f0 = nullptr;
     float* f1 = nullptr;
     float* f2 = nullptr;
@@ -145,6 +150,7 @@ class Engine {
     void forward_resized(const uint8_t* d_raw, int raw_h, int raw_w, const int32_t* h_raw_sizes, const int32_t* h_new_sizes,
                          const int32_t* h_flip, const float* h_K, const int32_t* h_sizes4, Det* d_out, int32_t* d_counts,
                          cudaStream_t stream);
+    void drop_plans();  // frees the active and the cached plans (an option that changes the op graph was flipped)
     int launches_per_forward() const;
     // categories: 0 preprocess, 1 stem, 2 conv (tcgen05), 3 pool, 4 eSE, 5 relu, 6 decode, 7 nms
     void get_profile(double* ms, double* flops, double* bytes, int32_t* launches);
@@ -161,6 +167,7 @@ class Engine {
                                 int cout);
     const StemLayer& stem_layer(const std::string& wname, const std::string& bn, int ksize, int stride);
     const EseLayer& ese_layer(const std::string& fc, int C);
+    const FrontLayer& front_layer(const std::string& prefix);
 
     dd3d_model_desc desc;
     int device = 0;
@@ -170,6 +177,7 @@ class Engine {
     int opt_do_postprocess = 1;
     int opt_profile = 0;
     int opt_workspace_reuse = 1;  // 0: bump allocation, every op output keeps its own memory (stage-level tests / debugging)
+    int opt_dla_front = 1;  // 1: DLA-34 base_layer + level0 + level1 (+ pool) as ONE kernel (dla_front.cu); 0: layer by layer
     int opt_workspace_fill = -1;  // >= 0: byte the whole arena is filled with at dd3d_plan (poison test)
     std::vector<cudaEvent_t> prof_ev;
     std::vector<int> prof_cat;
@@ -180,6 +188,7 @@ class Engine {
     std::map<std::string, Epilogue> epis;
     std::map<std::string, StemLayer> stems;
     std::map<std::string, EseLayer> eses;
+    std::map<std::string, FrontLayer> fronts;
     std::vector<void*> device_allocs;
     float* d_canon = nullptr;
     Plan plan;

@@ -320,31 +320,55 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     finish_image(p, b, cand, m, n, suppress, s_warp_sums, &s_base);
 }
 
-// ---------------------------------------------------------------------------------------------- class-parallel path
+// ---------------------------------------------------------------------------------------------- multi-CTA path
 // batched_nms never lets boxes of different classes suppress each other (detectron2 batched_nms -> torchvision: per-class
-// coordinate offsets), so the greedy scan is independent per (image, class): with one CTA per image the 32 CTAs of a V2-99
-// batch leave 116 SMs idle for ~0.9 ms (8 CTAs for the DLA-34 batch: 8 % of its step).  Three launches:
-//   nms_sort_kernel  (B CTAs)      : sort the image's candidates by score_3d, publish order / class
-//   nms_class_kernel (C x B CTAs)  : ordered sub-list of one class -> greedy NMS -> removed flags by sorted position
-//   nms_finish_kernel(B CTAs)      : survivors in sorted order -> post-NMS top-k -> postprocess -> output
+// coordinate offsets), so the greedy scan is independent per (image, class) -- but one class can hold most of an image's
+// candidates (the DLA-34 bench batch: 616 of 623 in one class), and the n^2 / 2 IoUs of a 600-box class on ONE SM cost
+// 205 us (ncu, profiles/r02i_launches_dla34.csv): the NMS was 9 % of the DLA-34 step.  Four launches:
+//   nms_sort_kernel  (B CTAs)            : sort the image's candidates by score_3d; publish order / class and a CLASS-MAJOR
+//                                          copy (boxes + sorted position, score order inside a class, 64-aligned segments)
+//   nms_mask_kernel  (row blocks x B)    : IoU bit matrix of every class segment, 64 x 64 boxes per step, on all SMs
+//   nms_scan_kernel  (C x B CTAs)        : the serial greedy pass over the bit matrix only (no IoU): resolve the 64 x 64
+//                                          diagonal word by word, OR the survivors' rows into the removed bit vector
+//   nms_finish_kernel(B CTAs)            : survivors in sorted order -> post-NMS top-k -> postprocess -> output
 // Same kept set and order as the single-CTA kernel (tests/test_kernels_gpu.py compares both with the oracle).
 struct NmsScratch {
     uint16_t* order;   // [B][cap] sorted position -> candidate slot
     uint8_t* cls;      // [B][cap]
     uint8_t* removed;  // [B][cap]
     int32_t* n;        // [B]
+    int32_t* seg_blk;  // [B][C + 1] first 64-row block of class c in the class-major list ([C] = total blocks)
+    int32_t* seg_cnt;  // [B][C] boxes of class c
+    uint16_t* cpos;    // [B][capP] class-major row -> sorted position
+    float4* cbox;      // [B][capP] class-major row -> box
+    unsigned long long* mask;  // [B][capP][W] bit j of word w of row i: box 64 w + j of the same class (j > i) has IoU > thr
+    int capP, W;
 };
 
-__device__ __forceinline__ NmsScratch bind_nms_scratch(void* scratch, int B, int cap) {
+__host__ __device__ __forceinline__ size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+
+__host__ __device__ __forceinline__ NmsScratch bind_nms_scratch(void* scratch, int B, int cap, int C) {
     NmsScratch s;
+    s.W = (cap + 63) / 64;
+    s.capP = 64 * (s.W + C);
     uint8_t* q = static_cast<uint8_t*>(scratch);
     s.order = reinterpret_cast<uint16_t*>(q);
-    q += (static_cast<size_t>(B) * cap * 2 + 255) / 256 * 256;
+    q += up256(static_cast<size_t>(B) * cap * 2);
     s.cls = q;
-    q += (static_cast<size_t>(B) * cap + 255) / 256 * 256;
+    q += up256(static_cast<size_t>(B) * cap);
     s.removed = q;
-    q += (static_cast<size_t>(B) * cap + 255) / 256 * 256;
+    q += up256(static_cast<size_t>(B) * cap);
     s.n = reinterpret_cast<int32_t*>(q);
+    q += up256(static_cast<size_t>(B) * 4);
+    s.seg_blk = reinterpret_cast<int32_t*>(q);
+    q += up256(static_cast<size_t>(B) * (C + 1) * 4);
+    s.seg_cnt = reinterpret_cast<int32_t*>(q);
+    q += up256(static_cast<size_t>(B) * C * 4);
+    s.cpos = reinterpret_cast<uint16_t*>(q);
+    q += up256(static_cast<size_t>(B) * s.capP * 2);
+    s.cbox = reinterpret_cast<float4*>(q);
+    q += up256(static_cast<size_t>(B) * s.capP * 16);
+    s.mask = reinterpret_cast<unsigned long long*>(q);
     return s;
 }
 
@@ -352,73 +376,167 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_sort_kernel(const __grid_c
     extern __shared__ uint8_t smem_raw[];
     const int b = blockIdx.x;
     const int cap = kLevels * p.topk;
+    const int C = p.num_classes;
     NmsSmem m = carve(smem_raw, cap);
     __shared__ int s_lvl_off[kLevels + 1];
+    __shared__ int s_cnt[256], s_run[256], s_seg[257];
     const Det* cand = p.cand + static_cast<size_t>(b) * cap;
     const int n = sort_candidates(p, b, cand, m, s_lvl_off);
-    const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap);
+    const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap, C);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s_cnt[c] = s_run[c] = 0;
+    __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int slot = m.val[i];
+        const int c = cand[slot].cls;
         sc.order[static_cast<size_t>(b) * cap + i] = static_cast<uint16_t>(slot);
-        sc.cls[static_cast<size_t>(b) * cap + i] = static_cast<uint8_t>(cand[slot].cls);
+        sc.cls[static_cast<size_t>(b) * cap + i] = static_cast<uint8_t>(c);
         sc.removed[static_cast<size_t>(b) * cap + i] = 0;
+        m.cls[i] = static_cast<uint8_t>(c);
+        atomicAdd(&s_cnt[c], 1);  // a count: independent of the order of the atomics
     }
     if (threadIdx.x == 0) sc.n[b] = n;
-}
-
-constexpr int kClassThreads = 512;
-
-__global__ void __launch_bounds__(kClassThreads, 1) nms_class_kernel(const __grid_constant__ NmsParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    const int c = blockIdx.x, b = blockIdx.y;
-    const int cap = kLevels * p.topk;
-    float4* boxes = reinterpret_cast<float4*>(smem_raw);            // [cap]
-    uint16_t* pos = reinterpret_cast<uint16_t*>(boxes + cap);       // [cap] sorted position of the class's k-th box
-    uint8_t* flag = reinterpret_cast<uint8_t*>(pos + cap);          // [cap]
-    __shared__ int s_warp_sums[kClassThreads / 32];
-    __shared__ int s_base;
-    __shared__ unsigned long long s_kept_mask;
-    __shared__ unsigned long long s_diag[64];
-    const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap);
-    const int n = sc.n[b];
-    const uint8_t* cls = sc.cls + static_cast<size_t>(b) * cap;
-    const uint16_t* order = sc.order + static_cast<size_t>(b) * cap;
-    const Det* cand = p.cand + static_cast<size_t>(b) * cap;
-    // order-preserving compaction of the sorted positions that hold class c
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        int blk = 0;
+        for (int c = 0; c < C; ++c) {
+            s_seg[c] = blk;
+            blk += (s_cnt[c] + 63) >> 6;
+        }
+        s_seg[C] = blk;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c <= C; c += blockDim.x) {
+        sc.seg_blk[b * (C + 1) + c] = s_seg[c];
+        if (c < C) sc.seg_cnt[b * C + c] = s_cnt[c];
+    }
+    // stable counting sort by class of the score-sorted list: rank inside the warp by __match_any_sync, warps and chunks in
+    // order through the per-(warp, class) table (reuses the dead sort keys)
+    int* wcnt = reinterpret_cast<int*>(m.key);  // [32 warps][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int start = 0; start < n; start += blockDim.x) {
-        const int i = start + threadIdx.x;
-        const int f = (i < n && cls[i] == c) ? 1 : 0;
-        const unsigned mk = __ballot_sync(0xffffffffu, f);
-        const int prefix = __popc(mk & ((1u << lane) - 1));
-        if (lane == 0) s_warp_sums[warp] = __popc(mk);
+        for (int j = threadIdx.x; j < nwarp * C; j += blockDim.x) wcnt[j] = 0;
         __syncthreads();
-        int before = 0;
-        for (int w = 0; w < warp; ++w) before += s_warp_sums[w];
-        const int base = s_base;
-        if (f) {
-            const int k = base + before + prefix;
-            pos[k] = static_cast<uint16_t>(i);
-            const Det& d = cand[order[i]];
-            boxes[k] = make_float4(d.box[0], d.box[1], d.box[2], d.box[3]);
-            flag[k] = 0;
+        const int i = start + threadIdx.x;
+        const int c = i < n ? m.cls[i] : 0xFFFF;
+        const unsigned same = __match_any_sync(0xffffffffu, c);
+        const int rank = __popc(same & ((1u << lane) - 1));
+        if (i < n && rank == 0) wcnt[warp * C + c] = __popc(same);
+        __syncthreads();
+        if (i < n) {
+            int before = s_run[c];
+            for (int w = 0; w < warp; ++w) before += wcnt[w * C + c];
+            const size_t row = static_cast<size_t>(b) * sc.capP + static_cast<size_t>(s_seg[c]) * 64 + before + rank;
+            const Det& d = cand[m.val[i]];
+            sc.cpos[row] = static_cast<uint16_t>(i);
+            sc.cbox[row] = make_float4(d.box[0], d.box[1], d.box[2], d.box[3]);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
             int tot = 0;
-            for (int w = 0; w < kClassThreads / 32; ++w) tot += s_warp_sums[w];
-            s_base = base + tot;
+            for (int w = 0; w < nwarp; ++w) tot += wcnt[w * C + cc];
+            s_run[cc] += tot;
         }
         __syncthreads();
     }
-    const int nc = s_base;
-    if (nc <= 1) return;  // nothing to suppress (block-uniform)
-    greedy_nms(boxes, nullptr, flag, nc, p.nms_thresh, s_diag, &s_kept_mask);
+}
+
+constexpr int kMaskThreads = 256;
+
+// CTA (r, b): 64-row block r of image b's class-major list; its class c is found in the segment table.  Thread = (row,
+// column-block lane): 64 IoUs of one row against one 64-box column block -> one 64-bit word.
+__global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const __grid_constant__ NmsParams p) {
+    const int b = blockIdx.y, r = blockIdx.x;
+    const int cap = kLevels * p.topk, C = p.num_classes;
+    const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap, C);
+    const int32_t* seg = sc.seg_blk + b * (C + 1);
+    if (r >= seg[C]) return;
+    int c = 0;
+    while (c + 1 < C && seg[c + 1] <= r) ++c;
+    const int nc = sc.seg_cnt[b * C + c];
+    if (nc <= 1) return;  // nothing to suppress; the scan kernel skips the class too
+    const int rb = r - seg[c], nblk = (nc + 63) >> 6;
+    const size_t row0 = static_cast<size_t>(b) * sc.capP + static_cast<size_t>(seg[c]) * 64;
+    const float4* boxes = sc.cbox + row0;
+    const int row = rb * 64 + (threadIdx.x & 63);
+    const float4 bi = boxes[min(row, nc - 1)];
+    for (int cb = rb + (threadIdx.x >> 6); cb < nblk; cb += kMaskThreads / 64) {
+        const int j0 = cb * 64, jn = min(64, nc - j0);
+        unsigned long long word = 0ull;
+        for (int j = 0; j < jn; ++j) {
+            if (j0 + j > row && iou_tv(bi, __ldg(boxes + j0 + j)) > p.nms_thresh) word |= 1ull << j;
+        }
+        if (row < nc) sc.mask[(row0 + row) * sc.W + cb] = word;
+    }
+}
+
+constexpr int kScanThreads = 128;  // >= W (cap <= 8192)
+
+__global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const __grid_constant__ NmsParams p) {
+    const int c = blockIdx.x, b = blockIdx.y;
+    const int cap = kLevels * p.topk, C = p.num_classes;
+    const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap, C);
+    const int nc = sc.seg_cnt[b * C + c];
+    if (nc <= 1) return;
+    const int nblk = (nc + 63) >> 6;
+    const size_t row0 = static_cast<size_t>(b) * sc.capP + static_cast<size_t>(sc.seg_blk[b * (C + 1) + c]) * 64;
+    const unsigned long long* mask = sc.mask + row0 * sc.W;
+    __shared__ unsigned long long s_removed[kScanThreads];
+    __shared__ unsigned long long s_diag[64];
+    __shared__ unsigned long long s_kept;
+    const int tid = threadIdx.x;
+    s_removed[tid] = 0ull;
+    __syncthreads();
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int cn = min(64, nc - blk * 64);
+        if (tid < 64) s_diag[tid] = tid < cn ? mask[static_cast<size_t>(blk * 64 + tid) * sc.W + blk] : 0ull;
+        __syncthreads();
+        if (tid == 0) {
+            // greedy pass over the 64 x 64 diagonal block: 16 words at a time in registers, then a pure ALU chain
+            unsigned long long removed = s_removed[blk];
+            if (cn < 64) removed |= ~0ull << cn;
+            unsigned long long kept = 0ull;
+#pragma unroll
+            for (int i0 = 0; i0 < 64; i0 += 16) {
+                unsigned long long d[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) d[i] = s_diag[i0 + i];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (!((removed >> (i0 + i)) & 1ull)) {
+                        kept |= 1ull << (i0 + i);
+                        removed |= d[i];
+                    }
+                }
+            }
+            s_kept = kept;
+            s_removed[blk] = ~kept;  // bits >= cn are never read
+        }
+        __syncthreads();
+        const int w = blk + 1 + tid;
+        if (w < nblk) {
+            unsigned long long acc = s_removed[w];
+            unsigned long long m = s_kept;
+            const unsigned long long* rows = mask + static_cast<size_t>(blk) * 64 * sc.W + w;
+            while (m) {  // four independent row loads in flight per step
+                int i[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    i[u] = m ? __ffsll(static_cast<long long>(m)) - 1 : -1;
+                    m &= m - 1;  // 0 stays 0
+                }
+                unsigned long long v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = i[u] >= 0 ? rows[static_cast<size_t>(i[u]) * sc.W] : 0ull;
+                acc |= (v[0] | v[1]) | (v[2] | v[3]);
+            }
+            s_removed[w] = acc;
+        }
+        __syncthreads();
+    }
     uint8_t* removed = sc.removed + static_cast<size_t>(b) * cap;
-    for (int k = threadIdx.x; k < nc; k += blockDim.x)
-        if (flag[k]) removed[pos[k]] = 1;
+    const uint16_t* cpos = sc.cpos + row0;
+    for (int k = tid; k < nc; k += kScanThreads)
+        if ((s_removed[k >> 6] >> (k & 63)) & 1ull) removed[cpos[k]] = 1;
 }
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_finish_kernel(const __grid_constant__ NmsParams p) {
@@ -428,7 +546,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_finish_kernel(const __grid
     NmsSmem m = carve(smem_raw, cap);
     __shared__ int s_warp_sums[33];
     __shared__ int s_base;
-    const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap);
+    const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap, p.num_classes);
     const Det* cand = p.cand + static_cast<size_t>(b) * cap;
     const int n = sc.n[b];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -447,10 +565,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_finish_kernel(const __grid
 static int g_class_parallel = -1;
 void nms_set_class_parallel(int mode) { g_class_parallel = (mode == 0 || mode == 1) ? mode : -1; }
 
-size_t nms_scratch_bytes(int B, int topk) {
-    const size_t cap = static_cast<size_t>(kLevels) * topk;
-    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-    return up(B * cap * 2) + 2 * up(B * cap) + up(static_cast<size_t>(B) * 4);
+size_t nms_scratch_bytes(int B, int topk, int num_classes) {
+    const int cap = kLevels * topk;
+    const NmsScratch sc = bind_nms_scratch(nullptr, B, cap, num_classes);
+    return static_cast<size_t>(reinterpret_cast<uintptr_t>(sc.mask)) /* offset: bound at address 0 */ +
+           up256(static_cast<size_t>(B) * sc.capP * sc.W * 8);
 }
 
 cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream) {
@@ -458,7 +577,6 @@ cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream) {
     if (cap > kMaxCand || p.B <= 0) return cudaErrorInvalidValue;
     const size_t smem = static_cast<size_t>(kMaxCand) * 8 + static_cast<size_t>(cap) * 16 +
                         static_cast<size_t>(cap) * 8 + static_cast<size_t>(kMaxCand) * 2 + static_cast<size_t>(cap) * 2;
-    const size_t smem_cls = static_cast<size_t>(cap) * (16 + 2 + 1);
     static size_t attr_smem_dev[64] = {};  // per device; the limit is 227 KiB minus the static shared memory: ask for what we use
     size_t& attr_smem = attr_smem_dev[current_device_or_zero()];
     if (smem > attr_smem) {
@@ -467,8 +585,6 @@ cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream) {
             e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(nms_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cls));
         if (e != cudaSuccess) {
             cudaGetLastError();
             return e;
@@ -481,7 +597,8 @@ cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream) {
     }
     if (g_class_parallel && p.scratch != nullptr && p.do_nms && p.nms_thresh > 0.f && p.num_classes >= 1 && p.num_classes <= 255) {
         nms_sort_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);
-        nms_class_kernel<<<dim3(p.num_classes, p.B), kClassThreads, smem_cls, stream>>>(p);
+        nms_mask_kernel<<<dim3((cap + 63) / 64 + p.num_classes, p.B), kMaskThreads, 0, stream>>>(p);
+        nms_scan_kernel<<<dim3(p.num_classes, p.B), kScanThreads, 0, stream>>>(p);
         nms_finish_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);
         return cudaGetLastError();
     }

@@ -20,6 +20,14 @@ cudaError_t launch_stem_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, cons
                            __nv_bfloat16* out, int B, int H, int W, int ksize, int stride, int cout, int out_pitch,
                            int num_sms, cudaStream_t stream, int fp16 = 0);
 
+// DLA-34 front end fused (dla_front.cu): base_layer 7x7 -> level0 3x3 -> level1 3x3/s2 (+ 2x2 max-pool of the result), conv +
+// BN + ReLU each, intermediates in shared memory.  in4: [B][H][W][4]; w0 [16][7][8][4], w1 [16][9][16], w2 [32][9][16] 16-bit;
+// sb* = fp32 scale[cout] | bias[cout]; out [B][H/2][W/2][out_pitch]; pool (may be null) [B][H/4][W/4][pool_pitch].
+cudaError_t launch_dla_front(const __nv_bfloat16* in4, const __nv_bfloat16* w0, const __nv_bfloat16* w1,
+                             const __nv_bfloat16* w2, const float* sb0, const float* sb1, const float* sb2,
+                             __nv_bfloat16* out, int out_pitch, __nv_bfloat16* pool, int pool_pitch, int B, int H, int W,
+                             int num_sms, cudaStream_t stream, int fp16 = 0);
+
 cudaError_t launch_maxpool(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, int in_pitch,
                            int Ho, int Wo, int out_pitch, int ksize, int num_sms, cudaStream_t stream, int fp16 = 0);
 

@@ -434,6 +434,12 @@ class DD3DB200(nn.Module):
 
     PROFILE_CATEGORIES = ("preprocess", "stem_conv", "conv_igemm", "maxpool", "ese", "relu", "decode", "nms")
 
+    def set_engine_option(self, name, value):
+        """dd3d_set_option pass-through for the switches that change the op graph or the workspace ("dla_front",
+        "workspace_reuse", "workspace_fill"): the next forward re-plans."""
+        _lib.check(_lib.load().dd3d_set_option(self._engine(), name.encode(), int(value)), self._handle)
+        self._plan_key = None
+
     def set_profile(self, on):
         """Record CUDA events around every engine op of the following forwards (dd3d_get_profile)."""
         _lib.check(_lib.load().dd3d_set_option(self._engine(), b"profile", int(on)), self._handle)

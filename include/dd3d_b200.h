@@ -154,7 +154,8 @@ int dd3d_wait_host(dd3d_handle h, int slot);
 int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags);
 /* Runtime switches the reference's callers toggle on the meta-arch: "do_postprocess" (postprocess_in_inference,
  * scripts/train.py:206-209, test_time_augmentation.py:107), "do_nms" (core.py:134), "profile" (see
- * dd3d_get_profile), "workspace_reuse" (default 1: activation buffers with disjoint lifetimes share workspace memory --
+ * dd3d_get_profile), "dla_front" (default 1: DLA-34 base_layer + level0 + level1 + pool run as one kernel; 0: layer by layer; flipping it
+ * drops the engine's plans), "workspace_reuse" (default 1: activation buffers with disjoint lifetimes share workspace memory --
  * after a forward only "input", "p0".."p4" and the head maps of dd3d_get_tensor are intact; 0: every op output keeps its own
  * memory, for stage-level tests; applies to plans made afterwards), and "workspace_fill" (0..255: dd3d_plan fills the whole workspace with that byte first, -1 = off;
  * the poison test of tests/test_determinism_gpu.py: results must not depend on what the arena held). */
@@ -164,7 +165,9 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value);
  * pairs for block_n >= 160 and >= 296 tiles), -1 back to the DD3D_CONV_CTA2 environment setting.
  * "op_fp16" = 1: the dd3d_op_* entry points below treat their 16-bit buffers as fp16 (default 0: bf16).
  * "nms_class_parallel" = 0: one CTA per image does the whole NMS instead of one CTA per (class, image) (default 1).
- * "taps" = 0: 3x3 convs with <= 16 output channels use the per-tap kernels instead of the taps-in-N kernel (default 1). */
+ * "taps" = 0: 3x3 convs with <= 16 output channels use the per-tap kernels instead of the taps-in-N kernel (default 1).
+ * "n_split" = 0: conv launches with fewer work items than half the SMs keep their N tile instead of splitting it (default 1;
+ * bit-identical results either way). */
 int dd3d_set_conv_policy(const char* name, int value);
 /* Number of kernel launches one dd3d_forward enqueues (for the bench's gpu_launches claim). */
 int dd3d_launches_per_forward(dd3d_handle h);
@@ -243,6 +246,14 @@ int dd3d_op_conv2d(const void* d_in, int B, int H, int W, int cin, int in_pitch,
                    int res_pitch, int res_up2, void* d_out, int out_pitch, int out_f32, dd3d_stream stream);
 int dd3d_op_stem_conv(const void* d_in4, const void* d_w, const float* d_scale, const float* d_bias, void* d_out,
                       int B, int H, int W, int ksize, int stride, int cout, int out_pitch, dd3d_stream stream);
+/* dd3d_op_dla_front: the fused DLA-34 front end (csrc/dla_front.cu; reference dla.py:271-283,346-350 base_layer -> level0
+ * -> level1, each conv + FrozenBN + ReLU, plus the 2x2 max-pool of level1's output, dla.py:235).  d_in4 as for
+ * dd3d_op_stem_conv; d_w0 = 16-bit [16][7][8][4] (ky, kx padded to 8, c padded to 4), d_w1 = [16][9][16], d_w2 = [32][9][16]
+ * (cout, tap, cin); d_sb* = fp32 scale[cout] | bias[cout]; d_out = [B][H/2][W/2][out_pitch], d_pool (may be NULL) =
+ * [B][H/4][W/4][pool_pitch].  H, W multiples of 4. */
+int dd3d_op_dla_front(const void* d_in4, const void* d_w0, const void* d_w1, const void* d_w2, const float* d_sb0,
+                      const float* d_sb1, const float* d_sb2, void* d_out, int out_pitch, void* d_pool, int pool_pitch,
+                      int B, int H, int W, dd3d_stream stream);
 int dd3d_op_preprocess(const void* d_images, int img_dtype, const int32_t* d_sizes2, void* d_out4, int B, int Hs, int Ws,
                        int Hp, int Wp, const float* h_mean, const float* h_std, dd3d_stream stream);
 int dd3d_op_maxpool(const void* d_in, void* d_out, int B, int H, int W, int C, int in_pitch, int out_pitch, int ksize,
