@@ -208,6 +208,9 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value) {
             e.opt_profile = value ? 1 : 0;
         } else if (n == "workspace_reuse") {  // applies to plans made afterwards
             e.opt_workspace_reuse = value ? 1 : 0;
+        } else if (n == "sparse_box3d") {  // 1 (default): box3d predictor at the final candidates only; 0: dense fp32 maps
+            if (e.opt_sparse_box3d != (value ? 1 : 0)) e.drop_plans();
+            e.opt_sparse_box3d = value ? 1 : 0;
         } else if (n == "dla_front") {  // 1 (default): fused DLA-34 front end (dla_front.cu); 0: layer by layer
             if (e.opt_dla_front != (value ? 1 : 0)) e.drop_plans();
             e.opt_dla_front = value ? 1 : 0;
@@ -287,7 +290,9 @@ int dd3d_get_tensor(dd3d_handle h, const char* name, void** d_ptr, int32_t dims[
             memcpy(dims, d, sizeof(d));
         } else if (n.rfind("b3d", 0) == 0) {
             const int l = level(3);
-            if (P.b3d_map[l] == nullptr) throw EngineError(DD3D_ERR_INVALID, "no 3-D head (box3d_on = 0): " + n);
+            if (P.b3d_map[l] == nullptr)
+                throw EngineError(DD3D_ERR_INVALID, P.sparse_b3d ? "dense box3d maps are not computed with option sparse_box3d = 1: " + n
+                                                                 : "no 3-D head (box3d_on = 0): " + n);
             *d_ptr = P.b3d_map[l];
             const int32_t d[6] = {P.B, P.lvl_h[l], P.lvl_w[l], 11 * (e.desc.class_agnostic_box3d ? 1 : e.desc.num_classes),
                                   P.b3d_pitch, 4};

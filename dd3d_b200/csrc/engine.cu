@@ -51,6 +51,7 @@ Engine::Engine(const dd3d_model_desc& d) : desc(d) {
     }
     num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("DD3D_DLA_FRONT")) opt_dla_front = atoi(e) ? 1 : 0;  // A/B runs of bench.py; default 1
+    if (const char* e = getenv("DD3D_SPARSE_BOX3D")) opt_sparse_box3d = atoi(e) ? 1 : 0;
 }
 
 Engine::~Engine() {
@@ -365,7 +366,9 @@ struct Builder {
             int tiles = 0;
             for (int s = 0; s < p.nseg; ++s)
                 tiles += B * ((p.seg[s].H + p.seg[s].th - 1) / p.seg[s].th) * ((p.seg[s].W + p.seg[s].tw - 1) / p.seg[s].tw);
-            while (tiles * p.n_blocks * 2 <= E->num_sms && p.block_n % 32 == 0 && p.block_n / 2 >= 64) {
+            // halves must stay multiples of 64: the epilogue stores 64-channel TMA boxes, and a box that starts inside this
+            // n-block but ends in the next one would overwrite the neighbour's channels (only the tensor edge is clipped)
+            while (tiles * p.n_blocks * 2 <= E->num_sms && p.block_n % 128 == 0) {
                 p.block_n /= 2;
                 p.n_blocks *= 2;
                 n_split = true;
@@ -715,6 +718,9 @@ struct Builder {
         const bool per_level = E->desc.per_level_predictors != 0, box3d_on = E->desc.box3d_on != 0;
         const int C3 = E->desc.class_agnostic_box3d ? 1 : C;
         const int cls_pitch = round_up(C + (nusc ? kNumAttributes + 1 : 0), 16), b3d_pitch = round_up(11 * C3, 16);
+        const bool sparse3 = box3d_on && E->opt_sparse_box3d != 0 && b3d_pitch <= kB3dSparseMaxN;
+        P->sparse_b3d = sparse3;
+        P->b3d_rows = sparse3 ? alloc_f32(static_cast<size_t>(B) * kLevels * E->desc.pre_nms_topk * b3d_pitch) : nullptr;
         P->cls_pitch = cls_pitch;
         P->b3d_pitch = b3d_pitch;
         // each tower is followed at once by its predictor, so that its ping-pong buffers die before the next tower starts
@@ -724,7 +730,7 @@ struct Builder {
             const size_t hw = static_cast<size_t>(B) * feats[l].H * feats[l].W;
             P->cls_map[l] = alloc_f32(hw * cls_pitch);
             P->box_map[l] = alloc_f32(hw * 16);
-            P->b3d_map[l] = box3d_on ? alloc_f32(hw * b3d_pitch) : nullptr;
+            P->b3d_map[l] = (box3d_on && !sparse3) ? alloc_f32(hw * b3d_pitch) : nullptr;
             P->lvl_h[l] = feats[l].H;
             P->lvl_w[l] = feats[l].W;
         }
@@ -841,7 +847,32 @@ struct Builder {
                 segs[l].out_f32 = P->b3d_map[l];
                 segs[l].out_pitch = b3d_pitch;
             }
-            if (!per_level) {
+            if (sparse3) {
+                // no dense launch: the predictor runs on the final candidates, after the threshold / top-k half of the decode
+                // (Engine::forward).  The tower outputs must outlive every op: a phantom op index keeps them in the arena.
+                B3dSparseParams& sp = P->b3d_sparse;
+                memset(&sp, 0, sizeof(sp));
+                for (int l = 0; l < L; ++l) {
+                    const ConvLayer& Lw = layer_for(per_level ? l : 0);
+                    touch(b3d_t[l]);
+                    sp.lvl[l].in = b3d_t[l].ptr;
+                    sp.lvl[l].H = b3d_t[l].H;
+                    sp.lvl[l].W = b3d_t[l].W;
+                    sp.lvl[l].pitch = b3d_t[l].pitch;
+                    sp.lvl[l].w = Lw.d_w;
+                    sp.lvl[l].scale = segs[l].epi->d_scale;
+                    sp.lvl[l].bias = segs[l].epi->d_bias;
+                    if (Lw.cout_pad != b3d_pitch || Lw.cin != 256) fail(DD3D_ERR_INVALID, "box3d predictor shape");
+                }
+                ++op_idx;
+                sp.rows = P->b3d_rows;
+                sp.B = B;
+                sp.C = C;
+                sp.topk = E->desc.pre_nms_topk;
+                sp.n_pad = b3d_pitch;
+                sp.out_pitch = b3d_pitch;
+                sp.fp16 = E->fp16;
+            } else if (!per_level) {
                 conv(layer_for(0), 1, false, segs, true);
             } else {
                 for (int l = 0; l < L; ++l) {
@@ -1136,6 +1167,11 @@ void Engine::make_plan(int B, int Hs, int Ws, void* workspace, size_t bytes) {
     fill_decode_params(&dp, desc, B, plan.cls_pitch, plan.b3d_pitch, d_canon);
     decode_bind_scratch(&dp, plan.detect_scratch);
     decode_finalize_params(&dp);
+    if (plan.sparse_b3d) {
+        dp.b3d_rows = plan.b3d_rows;
+        plan.b3d_sparse.fin = dp.fin;
+        plan.b3d_sparse.cand_count = dp.cand_count;
+    }
     fill_nms_params(&plan.nms, desc, dp, B);
     plan.nms.scratch = plan.nms_scratch;
 }
@@ -1179,7 +1215,7 @@ void fill_nms_params(NmsParams* np, const dd3d_model_desc& desc, const DecodePar
 }
 
 int Engine::launches_per_forward() const {
-    int n = 1 /*preprocess*/ + 5 /*decode*/ + ((desc.do_nms && desc.nms_thresh > 0.f) ? 4 : 1) /*nms: sort, IoU bit matrix, scan, finish*/;
+    int n = 1 /*preprocess*/ + 6 /*decode: clear, 2 dense passes, 2 selects, final*/ + (plan.sparse_b3d ? 1 : 0) + ((desc.do_nms && desc.nms_thresh > 0.f) ? 4 : 1) /*nms: sort, IoU bit matrix, scan, finish*/;
     for (const Op& op : plan.ops) n += (op.type == Op::ESE) ? 3 : 1;
     return n;
 }
@@ -1301,7 +1337,13 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
     }
     DecodeParams dp = P.decode;
     dp.K = d_K;
-    cuda_check(launch_decode(dp, stream), "decode");
+    if (P.sparse_b3d) {
+        cuda_check(launch_decode_select(dp, stream), "decode (threshold + top-k)");
+        cuda_check(launch_b3d_sparse(P.b3d_sparse, stream), "sparse box3d predictor");
+        cuda_check(launch_decode_final(dp, stream), "decode (boxes)");
+    } else {
+        cuda_check(launch_decode(dp, stream), "decode");
+    }
     mark(6);
     NmsParams np = P.nms;
     np.do_postprocess = opt_do_postprocess;
@@ -1374,7 +1416,7 @@ void Engine::get_profile(double* ms, double* flops, double* bytes, int32_t* laun
                 break;
         }
     }
-    launches[6] = 5;
+    launches[6] = 6 + (P.sparse_b3d ? 1 : 0);
     launches[7] = (desc.do_nms && desc.nms_thresh > 0.f) ? 4 : 1;
     for (int l = 0; l < kLevels; ++l)  // two dense passes over the fp32 logits + centerness
         bytes[6] += 2.0 * P.B * P.lvl_h[l] * P.lvl_w[l] * (C + 1) * 4;

@@ -9,6 +9,7 @@
 
 #include "../../include/dd3d_b200.h"
 #include "conv_igemm.cuh"
+#include "b3d_sparse.cuh"
 #include "detect.cuh"
 #include "resize.cuh"
 #include "small_kernels.cuh"
@@ -118,6 +119,11 @@ struct Plan {
     const float* d_canon = nullptr;
     DecodeParams decode;
     NmsParams nms;
+    // sparse FCOS3D predictor (b3d_sparse.cu): the fused box3d conv runs only at the final 2-D candidates, between the two
+    // halves of the decode; the dense fp32 maps b3d_map[] then do not exist
+    bool sparse_b3d = false;
+    float* b3d_rows = nullptr;  // [B][L][topk][b3d_pitch]
+    B3dSparseParams b3d_sparse;
 };
 
 void fill_decode_params(DecodeParams* dp, const dd3d_model_desc& desc, int B, int cls_pitch, int b3d_pitch,
@@ -177,6 +183,7 @@ class Engine {
     int opt_do_postprocess = 1;
     int opt_profile = 0;
     int opt_workspace_reuse = 1;  // 0: bump allocation, every op output keeps its own memory (stage-level tests / debugging)
+    int opt_sparse_box3d = 1;  // 1: box3d predictor evaluated at the final candidates only (b3d_sparse.cu); 0: dense maps
     int opt_dla_front = 1;  // 1: DLA-34 base_layer + level0 + level1 (+ pool) as ONE kernel (dla_front.cu); 0: layer by layer
     int opt_workspace_fill = -1;  // >= 0: byte the whole arena is filled with at dd3d_plan (poison test)
     std::vector<cudaEvent_t> prof_ev;

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
 // 205 us (ncu, profiles/r02i_launches_dla34.csv): the NMS was 9 % of the DLA-34 step.  Four launches:
 //   nms_sort_kernel  (B CTAs)            : sort the image's candidates by score_3d; publish order / class and a CLASS-MAJOR
 //                                          copy (boxes + sorted position, score order inside a class, 64-aligned segments)
-//   nms_mask_kernel  (row blocks x B)    : IoU bit matrix of every class segment, 64 x 64 boxes per step, on all SMs
+//   nms_mask_kernel  (16 x B CTAs)       : IoU bit matrix of every class segment, 64 x 64 boxes per step, on all SMs
 //   nms_scan_kernel  (C x B CTAs)        : the serial greedy pass over the bit matrix only (no IoU): resolve the 64 x 64
 //                                          diagonal word by word, OR the survivors' rows into the removed bit vector
 //   nms_finish_kernel(B CTAs)            : survivors in sorted order -> post-NMS top-k -> postprocess -> output
@@ -441,36 +441,68 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_sort_kernel(const __grid_c
 }
 
 constexpr int kMaskThreads = 256;
+constexpr int kMaskCtasPerImage = 16;
 
-// CTA (r, b): 64-row block r of image b's class-major list; its class c is found in the segment table.  Thread = (row,
-// column-block lane): 64 IoUs of one row against one 64-box column block -> one 64-bit word.
+// IoU bit matrix.  kMaskCtasPerImage CTAs per image stride over the image's (row block, column block) pairs -- the upper
+// triangles of all class segments, enumerated class by class -- so the n^2 / 2 IoUs of a large class spread over many SMs
+// instead of sitting in one CTA's serial loops.  One pair = 64 x 64 boxes: thread = (row, quarter of the columns), the four
+// 16-bit quarters of a word are merged with two shuffles.
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const __grid_constant__ NmsParams p) {
-    const int b = blockIdx.y, r = blockIdx.x;
+    const int b = blockIdx.y;
     const int cap = kLevels * p.topk, C = p.num_classes;
     const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap, C);
+    __shared__ int s_first[257];  // first pair index of class c
+    __shared__ float4 s_col[64];
     const int32_t* seg = sc.seg_blk + b * (C + 1);
-    if (r >= seg[C]) return;
-    int c = 0;
-    while (c + 1 < C && seg[c + 1] <= r) ++c;
-    const int nc = sc.seg_cnt[b * C + c];
-    if (nc <= 1) return;  // nothing to suppress; the scan kernel skips the class too
-    const int rb = r - seg[c], nblk = (nc + 63) >> 6;
-    const size_t row0 = static_cast<size_t>(b) * sc.capP + static_cast<size_t>(seg[c]) * 64;
-    const float4* boxes = sc.cbox + row0;
-    const int row = rb * 64 + (threadIdx.x & 63);
-    const float4 bi = boxes[min(row, nc - 1)];
-    for (int cb = rb + (threadIdx.x >> 6); cb < nblk; cb += kMaskThreads / 64) {
-        const int j0 = cb * 64, jn = min(64, nc - j0);
-        unsigned long long word = 0ull;
-        for (int j = 0; j < jn; ++j) {
-            if (j0 + j > row && iou_tv(bi, __ldg(boxes + j0 + j)) > p.nms_thresh) word |= 1ull << j;
+    const int32_t* cnt = sc.seg_cnt + b * C;
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int c = 0; c < C; ++c) {
+            s_first[c] = tot;
+            const int nc = cnt[c], nb = (nc + 63) >> 6;
+            if (nc > 1) tot += nb * (nb + 1) / 2;
         }
-        if (row < nc) sc.mask[(row0 + row) * sc.W + cb] = word;
+        s_first[C] = tot;
+    }
+    __syncthreads();
+    const int total = s_first[C];
+    const int r_in = threadIdx.x >> 2, part = threadIdx.x & 3;
+    for (int q = blockIdx.x; q < total; q += gridDim.x) {
+        int c = 0;
+        while (s_first[c + 1] <= q) ++c;  // classes without pairs have s_first[c + 1] == s_first[c] and are skipped
+        const int nc = cnt[c], nb = (nc + 63) >> 6;
+        int local = q - s_first[c], rb = 0;
+        while (local >= nb - rb) {
+            local -= nb - rb;
+            ++rb;
+        }
+        const int cb = rb + local;
+        const size_t row0 = static_cast<size_t>(b) * sc.capP + static_cast<size_t>(seg[c]) * 64;
+        const float4* boxes = sc.cbox + row0;
+        __syncthreads();  // the previous pair's readers of s_col are done
+        if (threadIdx.x < 64) s_col[threadIdx.x] = boxes[min(cb * 64 + threadIdx.x, nc - 1)];
+        __syncthreads();
+        const int row = rb * 64 + r_in;
+        const float4 bi = boxes[min(row, nc - 1)];
+        unsigned m16 = 0u;
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const int j = 16 * part + k, col = cb * 64 + j;
+            if (col < nc && col > row && iou_tv(bi, s_col[j]) > p.nms_thresh) m16 |= 1u << k;
+        }
+        unsigned long long word = static_cast<unsigned long long>(m16) << (16 * part);
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        if (part == 0 && row < nc) sc.mask[(row0 + row) * sc.W + cb] = word;
     }
 }
 
 constexpr int kScanThreads = 128;  // >= W (cap <= 8192)
 
+// The serial part of the greedy NMS of one (class, image), on the bit matrix only.  Per 64-box block: the diagonal words
+// (prefetched during the previous block) are resolved by one thread in registers; the rows of the survivors are then OR-ed
+// into the removed bit vector by all threads at once -- (survivor, word) items are independent loads, merged with
+// shared-memory atomicOr (commutative: the result does not depend on the order).
 __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const __grid_constant__ NmsParams p) {
     const int c = blockIdx.x, b = blockIdx.y;
     const int cap = kLevels * p.topk, C = p.num_classes;
@@ -481,17 +513,18 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const __grid_con
     const size_t row0 = static_cast<size_t>(b) * sc.capP + static_cast<size_t>(sc.seg_blk[b * (C + 1) + c]) * 64;
     const unsigned long long* mask = sc.mask + row0 * sc.W;
     __shared__ unsigned long long s_removed[kScanThreads];
-    __shared__ unsigned long long s_diag[64];
-    __shared__ unsigned long long s_kept;
+    __shared__ unsigned long long s_diag[2][64];
+    __shared__ unsigned char s_kept_idx[64];
+    __shared__ int s_nkept;
     const int tid = threadIdx.x;
     s_removed[tid] = 0ull;
+    if (tid < 64) s_diag[0][tid] = tid < nc ? mask[static_cast<size_t>(tid) * sc.W] : 0ull;
     __syncthreads();
     for (int blk = 0; blk < nblk; ++blk) {
         const int cn = min(64, nc - blk * 64);
-        if (tid < 64) s_diag[tid] = tid < cn ? mask[static_cast<size_t>(blk * 64 + tid) * sc.W + blk] : 0ull;
-        __syncthreads();
         if (tid == 0) {
             // greedy pass over the 64 x 64 diagonal block: 16 words at a time in registers, then a pure ALU chain
+            const unsigned long long* dg = s_diag[blk & 1];
             unsigned long long removed = s_removed[blk];
             if (cn < 64) removed |= ~0ull << cn;
             unsigned long long kept = 0ull;
@@ -499,7 +532,7 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const __grid_con
             for (int i0 = 0; i0 < 64; i0 += 16) {
                 unsigned long long d[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) d[i] = s_diag[i0 + i];
+                for (int i = 0; i < 16; ++i) d[i] = dg[i0 + i];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     if (!((removed >> (i0 + i)) & 1ull)) {
@@ -508,28 +541,29 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const __grid_con
                     }
                 }
             }
-            s_kept = kept;
             s_removed[blk] = ~kept;  // bits >= cn are never read
+            int nk = 0;
+            while (kept) {
+                s_kept_idx[nk++] = static_cast<unsigned char>(__ffsll(static_cast<long long>(kept)) - 1);
+                kept &= kept - 1;
+            }
+            s_nkept = nk;
         }
         __syncthreads();
-        const int w = blk + 1 + tid;
-        if (w < nblk) {
-            unsigned long long acc = s_removed[w];
-            unsigned long long m = s_kept;
-            const unsigned long long* rows = mask + static_cast<size_t>(blk) * 64 * sc.W + w;
-            while (m) {  // four independent row loads in flight per step
-                int i[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    i[u] = m ? __ffsll(static_cast<long long>(m)) - 1 : -1;
-                    m &= m - 1;  // 0 stays 0
-                }
-                unsigned long long v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = i[u] >= 0 ? rows[static_cast<size_t>(i[u]) * sc.W] : 0ull;
-                acc |= (v[0] | v[1]) | (v[2] | v[3]);
+        const int nrem = nblk - blk - 1;  // words after this block
+        if (nrem > 0) {
+            // next block's diagonal words (static data) ride along with the row loads
+            if (tid < 64) {
+                const int r = (blk + 1) * 64 + tid;
+                s_diag[(blk + 1) & 1][tid] = r < nc ? mask[static_cast<size_t>(r) * sc.W + blk + 1] : 0ull;
             }
-            s_removed[w] = acc;
+            const int items = s_nkept * nrem;
+            const unsigned long long* rows = mask + static_cast<size_t>(blk) * 64 * sc.W + blk + 1;
+            for (int it = tid; it < items; it += kScanThreads) {
+                const int ki = it / nrem, w = it - ki * nrem;
+                const unsigned long long v = rows[static_cast<size_t>(s_kept_idx[ki]) * sc.W + w];
+                if (v) atomicOr(&s_removed[blk + 1 + w], v);
+            }
         }
         __syncthreads();
     }
@@ -597,7 +631,7 @@ cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream) {
     }
     if (g_class_parallel && p.scratch != nullptr && p.do_nms && p.nms_thresh > 0.f && p.num_classes >= 1 && p.num_classes <= 255) {
         nms_sort_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);
-        nms_mask_kernel<<<dim3((cap + 63) / 64 + p.num_classes, p.B), kMaskThreads, 0, stream>>>(p);
+        nms_mask_kernel<<<dim3(kMaskCtasPerImage, p.B), kMaskThreads, 0, stream>>>(p);
         nms_scan_kernel<<<dim3(p.num_classes, p.B), kScanThreads, 0, stream>>>(p);
         nms_finish_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);
         return cudaGetLastError();

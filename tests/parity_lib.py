@@ -177,12 +177,33 @@ def measure_case(name, dtype, emu_threads=1, want_fp32=True):
     inputs = case_inputs(name)
     model = DD3DB200(cfg).to("cuda")
     model.load_state_dict(sd)
+    # default engine: the box3d predictor runs only at the final 2-D candidates (csrc/b3d_sparse.cu) ...
+    out_sparse = model(inputs)
+    torch.cuda.synchronize()
+    assert model.overflow_flags() == 0
+    sparse_dets = [dets_from_instances(o["instances"]) for o in out_sparse]
+    # ... everything below (stage maps, operator-level decode + NMS on the engine's own maps) needs the dense 3-D maps
+    model.set_engine_option("sparse_box3d", 0)
     out = model(inputs)
     torch.cuda.synchronize()
     assert model.overflow_flags() == 0
     Cn = cfg.DD3D.NUM_CLASSES
     B = len(inputs)
     rep = dict(case=name, dtype=dtype, images=B)
+    # sparse vs dense predictor: same detections in the same order; the 3-D fields differ only by the fp32 summation order
+    # of the two tensor paths (mma.sync vs tcgen05) over K = 2304
+    sv = dict(same_keys_and_order=True, n=0, max_err={f: 0.0 for f in FIELDS})
+    for b in range(B):
+        d_, s_ = dets_from_instances(out[b]["instances"]), sparse_dets[b]
+        same = d_["box"].shape[0] == s_["box"].shape[0] and keys_of(d_) == keys_of(s_)
+        sv["same_keys_and_order"] &= bool(same)
+        if same and d_["box"].shape[0]:
+            idx = np.arange(d_["box"].shape[0])
+            e = field_errors(s_, d_, idx, idx)
+            for f in FIELDS:
+                sv["max_err"][f] = max(sv["max_err"][f], float(e[f].max()))
+            sv["n"] += len(idx)
+    rep["sparse_vs_dense_box3d"] = sv
 
     g_cls = [model.get_tensor(f"cls{l}") for l in range(5)]
     g_box = [model.get_tensor(f"box{l}") for l in range(5)]

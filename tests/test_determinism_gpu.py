@@ -29,7 +29,7 @@ def _bits(t):
     return t.view(torch.int16) if t.element_size() == 2 else t.view(torch.int32)
 
 
-def _run(case, dtype, fill, reuse=1):
+def _run(case, dtype, fill, reuse=1, sparse=0):
     cfg = case_cfg(case, act_dtype=dtype)
     model = DD3DB200(cfg).to("cuda")
     model.load_state_dict(make_state_dict(cfg))
@@ -37,6 +37,7 @@ def _run(case, dtype, fill, reuse=1):
     h = model._engine()
     lib.check(L.dd3d_set_option(h, b"workspace_fill", fill), h)
     lib.check(L.dd3d_set_option(h, b"workspace_reuse", reuse), h)
+    lib.check(L.dd3d_set_option(h, b"sparse_box3d", sparse), h)  # sparse = 0: the snapshot includes the dense 3-D maps
     out = model(case_inputs(case))
     torch.cuda.synchronize()
     assert model.overflow_flags() == 0
@@ -50,7 +51,7 @@ def _run(case, dtype, fill, reuse=1):
                 break
             s += 1
     for l in range(5):
-        for n in ("cls", "box", "b3d"):
+        for n in ("cls", "box") + (() if sparse else ("b3d", )):
             snap[f"{n}{l}"] = _bits(model.get_tensor(f"{n}{l}")).clone()
     for b, o in enumerate(out):
         inst = o["instances"]
@@ -89,6 +90,20 @@ def test_workspace_liveness_reuse_changes_nothing_but_the_footprint(case, dtype)
         lib.check(L.dd3d_set_option(h, b"workspace_reuse", reuse), h)
         sizes[reuse] = L.dd3d_workspace_bytes(h, 8, 384, 1280)
     assert 0 < sizes[1] < 0.6 * sizes[0], sizes
+
+
+@pytest.mark.parametrize("case,dtype", [("dla34", "bf16"), ("v2_99", "bf16"), ("dla34_full", "fp16")])
+def test_sparse_box3d_path_is_arena_independent(case, dtype):
+    """Default engine (box3d predictor at the final candidates only, csrc/b3d_sparse.cu): the box3d tower outputs must
+    survive in the liveness-packed arena until the sparse predictor has read them, and nothing may depend on what the
+    workspace held: zeroed / poisoned arena and reuse on / off give bit-identical detections."""
+    a = _run(case, dtype, 0x00, reuse=1, sparse=1)
+    b = _run(case, dtype, 0xFF, reuse=1, sparse=1)
+    c = _run(case, dtype, 0xFF, reuse=0, sparse=1)
+    dets = [k for k in a if k.startswith("dets")]
+    assert dets and sum(a[k].shape[0] for k in dets) > 0
+    for k in dets:
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), f"{case}: {k}"
 
 
 def _probe(env_extra):

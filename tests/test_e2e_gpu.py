@@ -48,9 +48,16 @@ def _keys_inst(inst):
 def test_forward_vs_emulating_oracle(arch):
     cfg, sd, model = _model(arch)
     inputs = case_inputs(arch)
-    out = model(inputs)
+    out = model(inputs)  # default engine: sparse box3d predictor (csrc/b3d_sparse.cu); the detections below come from it
     torch.cuda.synchronize()
     assert model.overflow_flags() == 0
+    model.set_engine_option("sparse_box3d", 0)  # the stage-level check needs the dense 3-D maps
+    out_dense = model(inputs)
+    torch.cuda.synchronize()
+    for o, od in zip(out, out_dense):
+        assert _keys_inst(o["instances"]) == _keys_inst(od["instances"]), "sparse and dense predictors: different detections"
+        assert torch.equal(o["instances"].pred_boxes.tensor, od["instances"].pred_boxes.tensor)
+        assert (o["instances"].scores_3d - od["instances"].scores_3d).abs().max() < 2e-5 if len(o["instances"]) else True
     ref, inter = DD3DOracle(cfg, sd, emulate="bf16", threads=1).forward(inputs, return_intermediates=True)
     C = cfg.DD3D.NUM_CLASSES
     # ---- stage level: preprocessed input (bit exact), FPN outputs, head maps
@@ -220,7 +227,16 @@ def test_non_default_head_configs_vs_oracle(flags):
     model = DD3DB200(cfg).to("cuda")
     model.load_state_dict(sd)
     inputs = make_inputs(2, 128, 256, 721.5, seed_base=7)
-    out = model(inputs)
+    out = model(inputs)  # default: sparse box3d predictor (per-level weights / class-agnostic N = 16 / no 3-D head all covered)
+    torch.cuda.synchronize()
+    model.set_engine_option("sparse_box3d", 0)
+    out_dense = model(inputs)
+    torch.cuda.synchronize()
+    for o, od in zip(out, out_dense):
+        assert _keys_inst(o["instances"]) == _keys_inst(od["instances"])
+        if cfg.MODEL.BOX3D_ON and len(o["instances"]):
+            assert (o["instances"].scores_3d - od["instances"].scores_3d).abs().max() < 2e-5
+            assert (o["instances"].pred_boxes3d.size - od["instances"].pred_boxes3d.size).abs().max() < 1e-4
     ref, inter = DD3DOracle(cfg, sd, emulate="bf16", threads=1).forward(inputs, return_intermediates=True)
     C = cfg.DD3D.NUM_CLASSES
     for l in range(5):
@@ -293,6 +309,7 @@ def test_conv_n_split_is_bit_identical(arch):
         for mode in (0, 1):
             assert L.dd3d_set_conv_policy(b"n_split", mode) == 0
             _, _, model = _model(arch)
+            model.set_engine_option("sparse_box3d", 0)
             model(inputs)
             torch.cuda.synchronize()
             snaps.append([model.get_tensor(n).float().cpu().clone() for l in range(5) for n in (f"p{l}", f"cls{l}", f"b3d{l}")])

@@ -42,6 +42,13 @@ def test_parity_at_baseline_shape(case, dtype):
     # decode + NMS kernels vs the oracle on identical (engine) head maps: exact sets / order, fp32-rounding field errors
     hyb = rep["hybrid"]
     assert hyb["candidate_sets_equal"] and hyb["kept_order_equal"] and hyb["forward_equals_operator"], hyb
+    # the default (sparse) box3d predictor reproduces the dense one: same detections, same order, 2-D fields bit-equal,
+    # 3-D fields within the fp32 summation-order noise of a K = 2304 dot product
+    sv = rep["sparse_vs_dense_box3d"]
+    assert sv["same_keys_and_order"] and sv["n"] > 0, sv
+    assert sv["max_err"]["box"] == 0.0 and sv["max_err"]["score"] == 0.0, sv
+    for f in ("score3d", "quat", "proj_ctr", "depth", "size", "tvec"):
+        assert sv["max_err"][f] < 2e-5, (f, sv)
     assert hyb["candidates"] > 500 and hyb["kept"] >= 50
     for f, e in hyb["max_err"].items():
         assert e < 1e-5, (f, e)  # measured <= 4e-7: fp32 rounding only

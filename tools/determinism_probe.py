@@ -67,6 +67,7 @@ def main():
     L = _lib.load()
     h = model._engine()
     _lib.check(L.dd3d_set_option(h, b"workspace_fill", a.fill), h)
+    _lib.check(L.dd3d_set_option(h, b"sparse_box3d", 0), h)  # the hashes below include the dense 3-D maps
     res = dict(label=a.label, case=a.case, fill=a.fill, no_pdl=os.environ.get("DD3D_NO_PDL", ""), runs=[])
     for it in range(2):
         out = model(inputs)
