@@ -208,6 +208,8 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value) {
             e.opt_profile = value ? 1 : 0;
         } else if (n == "workspace_reuse") {  // applies to plans made afterwards
             e.opt_workspace_reuse = value ? 1 : 0;
+        } else if (n == "stem_mma") {  // 1 (default): VoVNet stem_1 on stem_mma.cu; 0: stem_tc.cu (same op graph)
+            e.opt_stem_mma = value ? 1 : 0;
         } else if (n == "sparse_box3d") {  // 1 (default): box3d predictor at the final candidates only; 0: dense fp32 maps
             if (e.opt_sparse_box3d != (value ? 1 : 0)) e.drop_plans();
             e.opt_sparse_box3d = value ? 1 : 0;
@@ -409,6 +411,14 @@ int dd3d_op_dla_front(const void* d_in4, const void* d_w0, const void* d_w1, con
                                         static_cast<const bf*>(d_w2), d_sb0, d_sb1, d_sb2, static_cast<bf*>(d_out), out_pitch,
                                         static_cast<bf*>(d_pool), pool_pitch, B, H, W, device_sms(),
                                         static_cast<cudaStream_t>(stream), g_op_fp16),
+                       nullptr);
+}
+
+int dd3d_op_stem_s2_mma(const void* d_in4, const void* d_w, const float* d_sb, void* d_out, int out_pitch, int B, int H, int W,
+                        dd3d_stream stream) {
+    return cuda_status(launch_stem_s2_mma(static_cast<const __nv_bfloat16*>(d_in4), static_cast<const __nv_bfloat16*>(d_w), d_sb,
+                                          static_cast<__nv_bfloat16*>(d_out), out_pitch, B, H, W, device_sms(),
+                                          static_cast<cudaStream_t>(stream), g_op_fp16),
                        nullptr);
 }
 

@@ -52,6 +52,7 @@ Engine::Engine(const dd3d_model_desc& d) : desc(d) {
     num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("DD3D_DLA_FRONT")) opt_dla_front = atoi(e) ? 1 : 0;  // A/B runs of bench.py; default 1
     if (const char* e = getenv("DD3D_SPARSE_BOX3D")) opt_sparse_box3d = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("DD3D_STEM_MMA")) opt_stem_mma = atoi(e) ? 1 : 0;
 }
 
 Engine::~Engine() {
@@ -907,6 +908,20 @@ const StemLayer& Engine::stem_layer(const std::string& wname, const std::string&
     S.d_w = static_cast<__nv_bfloat16*>(dev_alloc(packed.size() * 2));
     cuda_check(cudaMemcpy(S.d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice), "upload stem weights");
     S.epi = bn_epilogue(wname + "|" + bn, bn, "", S.cout);
+    if (ksize == 3 && stride == 2 && S.cout == 64) {
+        std::vector<uint16_t> pm(64 * 3 * 4 * 4, 0);
+        for (int co = 0; co < 64; ++co)
+            for (int c = 0; c < 3; ++c)
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int kx = 0; kx < 3; ++kx)
+                        pm[((co * 3 + ky) * 4 + kx) * 4 + c] = host_f32_to_act(w.data[((co * 3 + c) * 3 + ky) * 3 + kx], fp16);
+        S.d_w_mma = static_cast<__nv_bfloat16*>(dev_alloc(pm.size() * 2));
+        cuda_check(cudaMemcpy(S.d_w_mma, pm.data(), pm.size() * 2, cudaMemcpyHostToDevice), "upload stem weights (mma)");
+        std::vector<float> sc, bi;
+        bn_fold(bn, "", 64, &sc, &bi);
+        sc.insert(sc.end(), bi.begin(), bi.end());
+        S.d_sb_mma = upload_f32(sc);
+    }
     return stems.emplace(wname, S).first->second;
 }
 
@@ -1304,6 +1319,12 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
                 cuda_check(launch_conv(op.conv, num_sms, stream), "conv");
                 break;
             case Op::STEM:
+                if (op.stem->d_w_mma != nullptr && opt_stem_mma) {
+                    cuda_check(launch_stem_s2_mma(op.in.ptr, op.stem->d_w_mma, op.stem->d_sb_mma, op.out.ptr, op.out.pitch, P.B,
+                                                  op.in.H, op.in.W, num_sms, stream, fp16),
+                               "stem conv (mma)");
+                    break;
+                }
                 cuda_check(launch_stem_tc(op.in.ptr, op.stem->d_w, op.stem->epi.d_scale, op.stem->epi.d_bias, op.out.ptr,
                                           P.B, op.in.H, op.in.W, op.ksize, op.stride, op.stem->cout, op.out.pitch, num_sms,
                                           stream, fp16),

@@ -60,6 +60,8 @@ struct StemLayer {
     __nv_bfloat16* d_w;
     int ksize, stride, cout;
     Epilogue epi;
+    __nv_bfloat16* d_w_mma = nullptr;  // 3x3 stride-2 64-channel stem (VoVNet stem_1): [64][3][4][4] for stem_mma.cu
+    float* d_sb_mma = nullptr;         // scale[64] | bias[64]
 };
 struct FrontLayer {  // DLA-34 base_layer + level0 + level1 packed for dla_front.cu
     __nv_bfloat16 *d_w0, *d_w1, *d_w2;
@@ -183,6 +185,7 @@ class Engine {
     int opt_do_postprocess = 1;
     int opt_profile = 0;
     int opt_workspace_reuse = 1;  // 0: bump allocation, every op output keeps its own memory (stage-level tests / debugging)
+    int opt_stem_mma = 1;  // 1: VoVNet stem_1 on the register-fragment kernel (stem_mma.cu); 0: tcgen05 im2col kernel (stem_tc.cu)
     int opt_sparse_box3d = 1;  // 1: box3d predictor evaluated at the final candidates only (b3d_sparse.cu); 0: dense maps
     int opt_dla_front = 1;  // 1: DLA-34 base_layer + level0 + level1 (+ pool) as ONE kernel (dla_front.cu); 0: layer by layer
     int opt_workspace_fill = -1;  // >= 0: byte the whole arena is filled with at dd3d_plan (poison test)

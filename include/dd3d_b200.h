@@ -154,7 +154,7 @@ int dd3d_wait_host(dd3d_handle h, int slot);
 int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags);
 /* Runtime switches the reference's callers toggle on the meta-arch: "do_postprocess" (postprocess_in_inference,
  * scripts/train.py:206-209, test_time_augmentation.py:107), "do_nms" (core.py:134), "profile" (see
- * dd3d_get_profile), "sparse_box3d" (default 1: the fused FCOS3D predictor conv is evaluated only at the pixels that survive the 2-D threshold
+ * dd3d_get_profile), "stem_mma" (default 1: VoVNet stem_1 runs on csrc/stem_mma.cu, 0: on csrc/stem_tc.cu), "sparse_box3d" (default 1: the fused FCOS3D predictor conv is evaluated only at the pixels that survive the 2-D threshold
  * and per-level top-k, between the two halves of the decode -- the dense "b3d<l>" maps of dd3d_get_tensor then do not exist;
  * 0: dense fp32 maps, for stage-level tests; flipping it drops the engine's plans), "dla_front" (default 1: DLA-34 base_layer + level0 + level1 + pool run as one kernel; 0: layer by layer; flipping it
  * drops the engine's plans), "workspace_reuse" (default 1: activation buffers with disjoint lifetimes share workspace memory --
@@ -256,6 +256,11 @@ int dd3d_op_stem_conv(const void* d_in4, const void* d_w, const float* d_scale, 
 int dd3d_op_dla_front(const void* d_in4, const void* d_w0, const void* d_w1, const void* d_w2, const float* d_sb0,
                       const float* d_sb1, const float* d_sb2, void* d_out, int out_pitch, void* d_pool, int pool_pitch,
                       int B, int H, int W, dd3d_stream stream);
+/* dd3d_op_stem_s2_mma: VoVNet stem_1 (3x3 stride 2, 3 -> 64, FrozenBN + ReLU; vovnet.py:302,357-359) on the register-fragment
+ * kernel (csrc/stem_mma.cu), the engine's default for that layer.  d_w = 16-bit [64][3][4][4] (cout, ky, kx, c; kx = 3 and
+ * c = 3 zero), d_sb = fp32 scale[64] | bias[64], d_out = [B][ceil(H/2)][ceil(W/2)][out_pitch]. */
+int dd3d_op_stem_s2_mma(const void* d_in4, const void* d_w, const float* d_sb, void* d_out, int out_pitch, int B, int H, int W,
+                        dd3d_stream stream);
 int dd3d_op_preprocess(const void* d_images, int img_dtype, const int32_t* d_sizes2, void* d_out4, int B, int Hs, int Ws,
                        int Hp, int Wp, const float* h_mean, const float* h_std, dd3d_stream stream);
 int dd3d_op_maxpool(const void* d_in, void* d_out, int B, int H, int W, int C, int in_pitch, int out_pitch, int ksize,

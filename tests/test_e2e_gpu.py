@@ -318,3 +318,20 @@ def test_conv_n_split_is_bit_identical(arch):
         L.dd3d_set_conv_policy(b"n_split", -1)
     for a, b in zip(*snaps):
         assert torch.equal(a, b)
+
+
+def test_v2_99_stem_mma_matches_stem_tc():
+    """VoVNet stem_1 on the register-fragment kernel (csrc/stem_mma.cu, default) against the tcgen05 im2col kernel
+    (csrc/stem_tc.cu, engine option "stem_mma" = 0) inside the engine: same FPN maps up to isolated 1-ulp flips of the stem's
+    16-bit outputs (different fp32 summation order), amplified like any other rounding by the random-weight network."""
+    cfg, sd, model = _model("v2_99")
+    inputs = case_inputs("v2_99")
+    model(inputs)
+    torch.cuda.synchronize()
+    a = [model.get_tensor(f"p{l}").float().cpu().clone() for l in range(5)]
+    model.set_engine_option("stem_mma", 0)
+    model(inputs)
+    torch.cuda.synchronize()
+    for l in range(5):
+        e = _rel_l2(a[l], model.get_tensor(f"p{l}").float().cpu())
+        assert e < 1.5e-2, f"FPN level {l}: stem_mma vs stem_tc rel L2 {e}"

@@ -170,6 +170,45 @@ def test_stem_conv_and_preprocess(act):
         y = F.conv2d(ref.float(), wq, None, stride, (ksize - 1) // 2)
         y = F.relu(y * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
         _check_bf16(out, y, f"stem k{ksize}")
+        if (ksize, stride, cout) == (3, 2, 64):
+            # the engine's default for VoVNet stem_1: register-fragment kernel (csrc/stem_mma.cu), written into a channel slice
+            wm = torch.zeros(64, 3, 4, 4)
+            wm[:, :, :3, :3] = wq.permute(0, 2, 3, 1)
+            wm = wm.to(gpu_ops.ACT).cuda()
+            sb = torch.cat([scale, bias]).cuda()
+            out2 = torch.full((B, Ho, Wo, 96), 7.0, dtype=gpu_ops.ACT, device="cuda")
+            st = L.dd3d_op_stem_s2_mma(gpu_ops._p(out4), gpu_ops._p(wm), gpu_ops._p(sb), gpu_ops._p(out2), 96, B, Hp, Wp,
+                                       gpu_ops._stream())
+            assert st == 0
+            torch.cuda.synchronize()
+            _check_bf16(out2[..., :64], y, "stem_1 (mma.sync)")
+            assert (out2[..., 64:].float() == 7.0).all()
+            assert float((out2[..., :64].float() == out.float()).float().mean()) > 0.9  # vs stem_tc: same up to summation order
+
+
+def test_stem_s2_mma_ragged_and_multi_tile(act):
+    """csrc/stem_mma.cu on shapes with partial tiles in both directions, odd sizes (ceil(H/2) outputs) and more tiles than
+    CTAs (persistent loop, both input buffers), against fp32 torch on the same 16-bit operands."""
+    L = lib.load()
+    g = torch.Generator().manual_seed(21)
+    for B, H, W in ((1, 38, 90), (2, 33, 75), (3, 384, 640)):
+        x4 = torch.zeros(B, H, W, 4)
+        x4[..., :3] = torch.randn(B, H, W, 3, generator=g)
+        x4 = x4.to(gpu_ops.ACT)
+        w = (torch.randn(64, 3, 3, 3, generator=g) / 27**0.5).to(gpu_ops.ACT).float()
+        scale, bias = 0.5 + torch.rand(64, generator=g), torch.randn(64, generator=g) * 0.2
+        wm = torch.zeros(64, 3, 4, 4)
+        wm[:, :, :3, :3] = w.permute(0, 2, 3, 1)
+        d_in, d_w, d_sb = x4.cuda(), wm.to(gpu_ops.ACT).cuda(), torch.cat([scale, bias]).cuda()
+        Ho, Wo = (H + 1) // 2, (W + 1) // 2
+        out = torch.full((B, Ho, Wo, 64), 7.0, dtype=gpu_ops.ACT, device="cuda")
+        assert L.dd3d_op_stem_s2_mma(gpu_ops._p(d_in), gpu_ops._p(d_w), gpu_ops._p(d_sb), gpu_ops._p(out), 64, B, H, W,
+                                     gpu_ops._stream()) == 0
+        torch.cuda.synchronize()
+        y = F.conv2d(x4[..., :3].float().permute(0, 3, 1, 2), w, None, 2, 1)
+        y = F.relu(y * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+        assert y.shape[1:3] == (Ho, Wo)
+        _check_bf16(out, y, f"stem_1 mma {B}x{H}x{W}")
 
 
 @pytest.mark.parametrize("B,H,W,out_pitch,pool_pitch", [(2, 64, 128, 32, 32), (1, 44, 76, 48, 40), (3, 128, 256, 32, 0)])

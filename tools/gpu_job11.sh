@@ -1,15 +1,16 @@
 #!/bin/bash
-# round-2 GPU job 11: sparse box3d predictor, NMS mask/scan v2, decode_final spread, n_split fix: full suite + A/B + launch lists
+# round-2 GPU job 11: stem_mma (VoVNet stem_1 on register fragments), sparse box3d predictor, NMS mask/scan v2, decode_final spread, n_split fix: full suite + A/B + launch lists
 O=gpurun_out/r02k
 mkdir -p $O
 T="timeout -k 10"
-$T 400 python -m pytest tests/test_kernels_gpu.py -x -q -k "nms or decode or dla_front" > $O/canary.log 2>&1
+$T 400 python -m pytest tests/test_kernels_gpu.py -x -q -k "nms or decode or dla_front or stem" > $O/canary.log 2>&1
 rc=$?; echo "canary rc=$rc"; tail -12 $O/canary.log
 $T 600 python -m pytest tests/test_e2e_gpu.py -x -q > $O/canary2.log 2>&1
 rc2=$?; echo "canary2 rc=$rc2"; tail -15 $O/canary2.log
 for round in 1 2; do
-  DD3D_SPARSE_BOX3D=0 $T 300 python bench.py --cpu-images 0 > $O/ab_dense_$round.json 2> $O/ab_dense_$round.err
-  $T 300 python bench.py --cpu-images 0 > $O/ab_sparse_$round.json 2> $O/ab_sparse_$round.err
+  DD3D_SPARSE_BOX3D=0 DD3D_STEM_MMA=0 $T 300 python bench.py --cpu-images 0 > $O/ab_a_dense_$round.json 2> $O/ab_a_dense_$round.err
+  DD3D_STEM_MMA=0 $T 300 python bench.py --cpu-images 0 > $O/ab_b_sparse_$round.json 2> $O/ab_b_sparse_$round.err
+  $T 300 python bench.py --cpu-images 0 > $O/ab_c_sparse_stem_$round.json 2> $O/ab_c_sparse_stem_$round.err
 done
 python - <<'PY'
 import json,glob
