@@ -129,6 +129,10 @@ int dd3d_set_conv_policy(const char* name, int value) {
         conv_set_taps(value);
         return DD3D_OK;
     }
+    if (!strcmp(name, "wstat")) {
+        conv_set_wstat(value);
+        return DD3D_OK;
+    }
     if (!strcmp(name, "n_split")) {
         conv_set_n_split(value);
         return DD3D_OK;
@@ -210,9 +214,10 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value) {
             e.opt_workspace_reuse = value ? 1 : 0;
         } else if (n == "stem_mma") {  // 1 (default): VoVNet stem_1 on stem_mma.cu; 0: stem_tc.cu (same op graph)
             e.opt_stem_mma = value ? 1 : 0;
-        } else if (n == "sparse_box3d") {  // 1 (default): box3d predictor at the final candidates only; 0: dense fp32 maps
-            if (e.opt_sparse_box3d != (value ? 1 : 0)) e.drop_plans();
-            e.opt_sparse_box3d = value ? 1 : 0;
+        } else if (n == "sparse_box3d") {  // 2 (default): auto by head size; 1: always sparse; 0: dense fp32 maps
+            const int v = value < 0 ? 0 : (value > 2 ? 2 : value);
+            if (e.opt_sparse_box3d != v) e.drop_plans();
+            e.opt_sparse_box3d = v;
         } else if (n == "dla_front") {  // 1 (default): fused DLA-34 front end (dla_front.cu); 0: layer by layer
             if (e.opt_dla_front != (value ? 1 : 0)) e.drop_plans();
             e.opt_dla_front = value ? 1 : 0;

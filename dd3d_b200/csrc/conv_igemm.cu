@@ -52,7 +52,8 @@ constexpr int kSmemBudget = 227 * 1024;
 // 128B-swizzled by TMA; the slot is rounded up to a multiple of 1024 B so every patch keeps the swizzle-atom alignment
 constexpr int kHaloPW = kHaloTw + 2, kHaloPH = kHaloTh + 2;
 constexpr int kHaloABytes = (kHaloPW * kHaloPH * 128 + 1023) / 1024 * 1024;  // 23552
-constexpr int kHaloAStages = 3;
+constexpr int kHaloAStages = 3;   // default number of A patches in flight
+constexpr int kMaxAStages = 5;    // weight-stationary layers (ConvParams::wstat) spend the freed B ring on deeper A prefetch
 constexpr int kBarBytes = 512;
 constexpr int kSbBytes = 2 * 256 * 4;  // staged (scale, bias) vectors of the current (segment, n-block)
 constexpr int kFirstEpiWarp = 3, kEpiWarps = 8, kEpiThreads = kEpiWarps * 32;
@@ -204,16 +205,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const int w_total = CTA2 ? p.pair_work : p.total_work;
     const int b_rows = CTA2 ? p.block_n / 2 : p.block_n;
     const int stage_bytes = (HALO ? 0 : kABytes) + b_rows * 128;
-    uint8_t* halo_a = smem + p.num_stages * stage_bytes;
-    uint8_t* staging = halo_a + (HALO ? kHaloAStages * kHaloABytes : 0);
+    // weight-stationary (HALO, single CTA, one n-block, cin <= 64): ALL k-blocks of the weight tensor stay resident in the B
+    // region (loaded once per CTA) instead of cycling through the stage ring for every tile
+    const bool wstat = HALO && !CTA2 && p.wstat != 0;
+    const int a_stages = HALO ? p.a_stages : 0;
+    uint8_t* halo_a = smem + (wstat ? p.taps * p.kchunks : p.num_stages) * stage_bytes;
+    uint8_t* staging = halo_a + a_stages * kHaloABytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
     uint64_t* full_bar = bars;                     // [kMaxStages]
     uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
     uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
     uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-    uint64_t* afull_bar = tempty_bar + 2;          // [kHaloAStages]
-    uint64_t* aempty_bar = afull_bar + kHaloAStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + kHaloAStages);
+    uint64_t* afull_bar = tempty_bar + 2;          // [kMaxAStages]
+    uint64_t* aempty_bar = afull_bar + kMaxAStages;
+    uint64_t* wfull_bar = aempty_bar + kMaxAStages;  // [1] resident weights landed (wstat)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
     // shared-window addresses of the epilogue's staging tiles and of the staged folded-BN vectors (explicit LDS / STS)
     const uint32_t staging_u32 = ptx::smem_u32(staging);
     const uint32_t s_scale_u32 = ptx::smem_u32(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [256] fp32 scale
@@ -236,10 +242,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             ptx::mbar_init(&tfull_bar[i], 1);
             ptx::mbar_init(&tempty_bar[i], (CTA2 ? 2 : 1) * kEpiWarps);  // one arrival per epilogue warp (of both CTAs of a pair)
         }
-        for (int i = 0; i < kHaloAStages; ++i) {
+        for (int i = 0; i < kMaxAStages; ++i) {
             ptx::mbar_init(&afull_bar[i], 1);
             ptx::mbar_init(&aempty_bar[i], 1);
         }
+        ptx::mbar_init(wfull_bar, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -273,7 +280,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         // generic variant, weight (B) producer in the halo variant.  Whole warp runs the loop; one elected lane issues.
         int stage = 0;
         uint32_t phase = 0;
-        for (int work = w_first; work < w_total; work += w_step) {
+        if (wstat) {
+            // the whole weight tensor (<= 9 x 8 KiB), once: one barrier, one transaction count
+            if (elect_one()) {
+                ptx::mbar_expect_tx(wfull_bar, kblocks * p.block_n * 128);
+                for (int kb = 0; kb < kblocks; ++kb)
+                    ptx::tma_load_2d(smem + kb * stage_bytes, &p.w_map, wfull_bar, kb * kBlockK, 0);
+            }
+            __syncwarp();
+        }
+        for (int work = w_first; work < w_total && !wstat; work += w_step) {
             const TileCoord t = decode_tile<CTA2>(p, work, rank);
             const ConvSeg& g = p.seg[t.seg];
             if (HALO) {
@@ -388,7 +404,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         }
                     }
                     __syncwarp();
-                    if (++as == kHaloAStages) {
+                    if (++as == a_stages) {
                         as = 0;
                         aphase ^= 1;
                     }
@@ -411,6 +427,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         uint32_t acc_phase = 0;
         int as = 0;
         uint32_t aphase = 0;
+        if (wstat) {
+            ptx::mbar_wait(wfull_bar, 0, 4);
+            ptx::tc_fence_after();
+        }
         for (int work = w_first; work < w_total; work += w_step) {
             ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
             ptx::tc_fence_after();
@@ -420,11 +440,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     ptx::mbar_wait(&afull_bar[as], aphase, 6);
                     const uint32_t a_lo = halo_lo0 + static_cast<uint32_t>(as) * (kHaloABytes >> 4);
                     for (int tap = 0; tap < 9; ++tap) {
-                        ptx::mbar_wait(&full_bar[stage], phase, 3);
+                        if (!wstat) ptx::mbar_wait(&full_bar[stage], phase, 3);
                         ptx::tc_fence_after();
                         const int r = tap / 3, s = tap - 3 * r;
                         const uint32_t a_tap = a_lo + (r * kHaloPW + s) * 8;  // whole pixels: 128 B = 8 x 16 B
-                        const uint32_t b_lo = lo0 + static_cast<uint32_t>(stage) * stage_units;
+                        const uint32_t b_lo = lo0 + static_cast<uint32_t>(wstat ? tap * p.kchunks + kc : stage) * stage_units;
                         const int ksteps = (kc == p.kchunks - 1) ? p.last_ksteps : kBlockK / 16;
                         if (elect_one()) {
 #pragma unroll
@@ -443,17 +463,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                                 ptx::umma_commit2(&empty_bar[stage], 3);
                                 if (tap == 8) ptx::umma_commit2(&aempty_bar[as], 3);
                             } else {
-                                ptx::umma_commit(&empty_bar[stage]);
+                                if (!wstat) ptx::umma_commit(&empty_bar[stage]);
                                 if (tap == 8) ptx::umma_commit(&aempty_bar[as]);  // patch free once its 36 MMAs retire
                             }
                         }
                         __syncwarp();
-                        if (++stage == p.num_stages) {
+                        if (!wstat && ++stage == p.num_stages) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    if (++as == kHaloAStages) {
+                    if (++as == a_stages) {
                         as = 0;
                         aphase ^= 1;
                     }
@@ -1180,10 +1200,26 @@ void conv_finalize_params(ConvParams* p) {
     if (p->taps_n) p->cta2 = 0;
     p->pair_work = ((tile + 1) / 2) * p->n_blocks;
     const int stage_bytes = (p->halo ? 0 : kABytes) + (p->cta2 ? p->block_n / 2 : p->block_n) * 128;
-    const int fixed = 2 * kStagingBytes + 1024 /*alignment slack*/ + kBarBytes + kSbBytes +
-                      (p->halo ? kHaloAStages * kHaloABytes : 0);
+    const int base = 2 * kStagingBytes + 1024 /*alignment slack*/ + kBarBytes + kSbBytes;
+    p->a_stages = p->halo ? kHaloAStages : 0;
+    p->wstat = 0;
+    // Weight-stationary: a 3x3 layer whose whole weight tensor is a few k-blocks (64 -> 64: 9 x 8 KiB; DLA-34 level2, VoVNet
+    // stem_2) re-streamed it through the 8-deep B ring for every 128-pixel tile -- barely one tile of lookahead against a TMA
+    // round trip of ~2 tiles' worth of MMAs, so the MMA warp waited on weights (ncu: 5.4 k cycles per tile for 1.2 k cycles
+    // of MMAs).  The tensor stays resident instead and the freed barriers / shared memory go to deeper A-patch prefetch.
+    if (p->halo && !p->cta2 && !p->taps_n && p->n_blocks == 1 && conv_wstat_enabled()) {
+        const int resident = p->taps * p->kchunks * stage_bytes;
+        for (int a = kMaxAStages; a >= kHaloAStages; --a) {
+            if (base + resident + a * kHaloABytes <= kSmemBudget) {
+                p->wstat = 1;
+                p->a_stages = a;
+                break;
+            }
+        }
+    }
+    const int fixed = base + p->a_stages * kHaloABytes;
     int stages = (kSmemBudget - fixed) / stage_bytes;
-    p->num_stages = std::max(2, std::min(kMaxStages, stages));
+    p->num_stages = p->wstat ? 2 : std::max(2, std::min(kMaxStages, stages));
     const int chains = 1;  // split-K accumulator chains were measured and dropped; field kept = 1
     p->chains = chains;
     p->acc_stages = (2 * chains * p->block_n <= 512) ? 2 : 1;
@@ -1198,6 +1234,16 @@ void conv_finalize_params(ConvParams* p) {
 
 static int g_cta2_mode = -1;
 static int g_n_split = -1;
+static int g_wstat = -1;
+
+bool conv_wstat_enabled() {
+    if (g_wstat < 0) {
+        const char* e = getenv("DD3D_CONV_WSTAT");
+        g_wstat = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return g_wstat != 0;
+}
+void conv_set_wstat(int mode) { g_wstat = (mode == 0 || mode == 1) ? mode : -1; }
 
 bool conv_n_split_enabled() {
     if (g_n_split < 0) {
@@ -1220,8 +1266,8 @@ void conv_set_cta2(int mode) { g_cta2_mode = (mode >= 0 && mode <= 2) ? mode : -
 
 cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
     const int stage_bytes = (p.halo ? 0 : kABytes) + (p.cta2 ? p.block_n / 2 : p.block_n) * 128;
-    const int smem_bytes = p.num_stages * stage_bytes + 2 * kStagingBytes + 1024 + kBarBytes + kSbBytes +
-                           (p.halo ? kHaloAStages * kHaloABytes : 0);
+    const int smem_bytes = (p.wstat ? p.taps * p.kchunks : p.num_stages) * stage_bytes + 2 * kStagingBytes + 1024 + kBarBytes +
+                           kSbBytes + p.a_stages * kHaloABytes;
     static uint64_t attr_devices = 0;  // per-device opt-in to > 48 KB dynamic shared memory
     if (first_use_on_device(&attr_devices)) {
         cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -63,6 +63,8 @@ struct ConvParams {
     float inv_n_blocks;
     int taps_n;       // 1: taps-in-N variant for 3x3 stride-1 convs with <= 16 output channels (conv_taps_kernel)
     int fp16;         // 16-bit storage type of activations and weights: 0 bf16, 1 fp16 (act16.cuh)
+    int wstat;        // 1: weight-stationary halo variant -- all taps * kchunks weight blocks resident in shared memory
+    int a_stages;     // halo variants: A patches in flight (3, or up to 5 with wstat)
 };
 static_assert(sizeof(ConvParams) <= 4096, "kernel parameter space");
 constexpr int kConvCta2Default = 2;  // auto; DD3D_CONV_CTA2=0|1|auto overrides
@@ -94,6 +96,8 @@ bool make_weight_map_taps(CUtensorMap* map, const void* base, int cin_pad, int f
 bool conv_taps_eligible(int taps, int stride, int cout_pad, int nseg, const int* Hs, const int* Ws);
 void conv_set_taps(int mode);
 // N-split of under-filled launches (engine.cu Builder::conv): 1 on (default; DD3D_CONV_NSPLIT=0 turns it off), -1 = environment
+bool conv_wstat_enabled();       // weight-stationary halo layers: on by default, DD3D_CONV_WSTAT=0 / conv_set_wstat(0) turn it off
+void conv_set_wstat(int mode);   // 0 off, 1 on, -1 environment / default
 bool conv_n_split_enabled();
 void conv_set_n_split(int mode);  // 0 off, 1 on, -1 environment / default (on)
 // Fills num_stages / tmem_cols / total_work / tile bookkeeping from the already-set fields.

@@ -51,7 +51,7 @@ Engine::Engine(const dd3d_model_desc& d) : desc(d) {
     }
     num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("DD3D_DLA_FRONT")) opt_dla_front = atoi(e) ? 1 : 0;  // A/B runs of bench.py; default 1
-    if (const char* e = getenv("DD3D_SPARSE_BOX3D")) opt_sparse_box3d = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("DD3D_SPARSE_BOX3D")) opt_sparse_box3d = std::max(0, std::min(2, atoi(e)));
     if (const char* e = getenv("DD3D_STEM_MMA")) opt_stem_mma = atoi(e) ? 1 : 0;
 }
 
@@ -719,7 +719,13 @@ struct Builder {
         const bool per_level = E->desc.per_level_predictors != 0, box3d_on = E->desc.box3d_on != 0;
         const int C3 = E->desc.class_agnostic_box3d ? 1 : C;
         const int cls_pitch = round_up(C + (nusc ? kNumAttributes + 1 : 0), 16), b3d_pitch = round_up(11 * C3, 16);
-        const bool sparse3 = box3d_on && E->opt_sparse_box3d != 0 && b3d_pitch <= kB3dSparseMaxN;
+        // sparse box3d predictor: forced (1), off (0) or auto (2, default): the dense launch costs ~0.45 us per 1 000 head
+        // pixels, the gathered one a near-constant 0.08 - 0.12 ms of latency-bound K loop -- V2-99 at B = 32 (4.1 M pixels):
+        // 1.75 ms dense vs 0.12 ms sparse; DLA-34 at B = 8 (82 k pixels): 0.05 ms dense vs 0.08 ms sparse
+        size_t head_px = 0;
+        for (int l = 0; l < L; ++l) head_px += static_cast<size_t>(B) * feats[l].H * feats[l].W;
+        const bool sparse3 = box3d_on && b3d_pitch <= kB3dSparseMaxN &&
+                             (E->opt_sparse_box3d == 1 || (E->opt_sparse_box3d == 2 && head_px >= 250000));
         P->sparse_b3d = sparse3;
         P->b3d_rows = sparse3 ? alloc_f32(static_cast<size_t>(B) * kLevels * E->desc.pre_nms_topk * b3d_pitch) : nullptr;
         P->cls_pitch = cls_pitch;

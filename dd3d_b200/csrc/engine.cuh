@@ -186,7 +186,7 @@ class Engine {
     int opt_profile = 0;
     int opt_workspace_reuse = 1;  // 0: bump allocation, every op output keeps its own memory (stage-level tests / debugging)
     int opt_stem_mma = 1;  // 1: VoVNet stem_1 on the register-fragment kernel (stem_mma.cu); 0: tcgen05 im2col kernel (stem_tc.cu)
-    int opt_sparse_box3d = 1;  // 1: box3d predictor evaluated at the final candidates only (b3d_sparse.cu); 0: dense maps
+    int opt_sparse_box3d = 2;  // box3d predictor at the final candidates only (b3d_sparse.cu): 0 never (dense maps), 1 always, 2 auto (by head size)
     int opt_dla_front = 1;  // 1: DLA-34 base_layer + level0 + level1 (+ pool) as ONE kernel (dla_front.cu); 0: layer by layer
     int opt_workspace_fill = -1;  // >= 0: byte the whole arena is filled with at dd3d_plan (poison test)
     std::vector<cudaEvent_t> prof_ev;

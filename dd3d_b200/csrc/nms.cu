@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
 // 205 us (ncu, profiles/r02i_launches_dla34.csv): the NMS was 9 % of the DLA-34 step.  Four launches:
 //   nms_sort_kernel  (B CTAs)            : sort the image's candidates by score_3d; publish order / class and a CLASS-MAJOR
 //                                          copy (boxes + sorted position, score order inside a class, 64-aligned segments)
-//   nms_mask_kernel  (16 x B CTAs)       : IoU bit matrix of every class segment, 64 x 64 boxes per step, on all SMs
+//   nms_mask_kernel  (64 x B CTAs)       : IoU bit matrix of every class segment, 64 x 64 boxes per step, on all SMs
 //   nms_scan_kernel  (C x B CTAs)        : the serial greedy pass over the bit matrix only (no IoU): resolve the 64 x 64
 //                                          diagonal word by word, OR the survivors' rows into the removed bit vector
 //   nms_finish_kernel(B CTAs)            : survivors in sorted order -> post-NMS top-k -> postprocess -> output
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_sort_kernel(const __grid_c
 }
 
 constexpr int kMaskThreads = 256;
-constexpr int kMaskCtasPerImage = 16;
+constexpr int kMaskCtasPerImage = 64;
 
 // IoU bit matrix.  kMaskCtasPerImage CTAs per image stride over the image's (row block, column block) pairs -- the upper
 // triangles of all class segments, enumerated class by class -- so the n^2 / 2 IoUs of a large class spread over many SMs
@@ -514,8 +514,7 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const __grid_con
     const unsigned long long* mask = sc.mask + row0 * sc.W;
     __shared__ unsigned long long s_removed[kScanThreads];
     __shared__ unsigned long long s_diag[2][64];
-    __shared__ unsigned char s_kept_idx[64];
-    __shared__ int s_nkept;
+    __shared__ unsigned long long s_kept;
     const int tid = threadIdx.x;
     s_removed[tid] = 0ull;
     if (tid < 64) s_diag[0][tid] = tid < nc ? mask[static_cast<size_t>(tid) * sc.W] : 0ull;
@@ -542,12 +541,7 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const __grid_con
                 }
             }
             s_removed[blk] = ~kept;  // bits >= cn are never read
-            int nk = 0;
-            while (kept) {
-                s_kept_idx[nk++] = static_cast<unsigned char>(__ffsll(static_cast<long long>(kept)) - 1);
-                kept &= kept - 1;
-            }
-            s_nkept = nk;
+            s_kept = kept;
         }
         __syncthreads();
         const int nrem = nblk - blk - 1;  // words after this block
@@ -557,12 +551,15 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const __grid_con
                 const int r = (blk + 1) * 64 + tid;
                 s_diag[(blk + 1) & 1][tid] = r < nc ? mask[static_cast<size_t>(r) * sc.W + blk + 1] : 0ull;
             }
-            const int items = s_nkept * nrem;
+            // (row, word) items of the whole 64-row block; rows that were suppressed are skipped by their bit
+            const unsigned long long kept = s_kept;
             const unsigned long long* rows = mask + static_cast<size_t>(blk) * 64 * sc.W + blk + 1;
-            for (int it = tid; it < items; it += kScanThreads) {
-                const int ki = it / nrem, w = it - ki * nrem;
-                const unsigned long long v = rows[static_cast<size_t>(s_kept_idx[ki]) * sc.W + w];
-                if (v) atomicOr(&s_removed[blk + 1 + w], v);
+            for (int it = tid; it < 64 * nrem; it += kScanThreads) {
+                const int i = it / nrem, w = it - i * nrem;
+                if ((kept >> i) & 1ull) {
+                    const unsigned long long v = rows[static_cast<size_t>(i) * sc.W + w];
+                    if (v) atomicOr(&s_removed[blk + 1 + w], v);
+                }
             }
         }
         __syncthreads();

@@ -7,8 +7,10 @@
 // and ran at 1.09 ms = 1.8 TB/s.  Here a CTA copies the 17 x 66 input patch of an 8 x 32 output tile with cp.async (double
 // buffered), and every warp feeds mma.sync.m16n8k16 straight from it: one K step per kernel row, its 16 k slots = 4
 // consecutive input pixels x 4 channels (4th pixel / 4th channel carry zero weights), so lane t's fragment registers are ONE
-// 8-byte shared-memory load of input pixel 2x - 1 + t.  The 64 x 48 weight fragments stay in registers for the whole kernel;
-// results are rounded in registers, staged per warp and leave as full 128-byte rows.
+// 8-byte shared-memory load of input pixel 2x - 1 + t.  The 64 x 48 weight fragments stay in registers for the whole kernel.
+// Output channels are PERMUTED across the n-tiles (column j of n-tile nt = channel 16 (j / 2) + 2 nt + (j % 2)) so that the
+// 16 accumulator columns a lane holds for one pixel are 16 consecutive channels: BN + ReLU + rounding happen in registers and
+// the results leave as two 16-byte global stores per pixel and lane -- no shared-memory staging, no shuffles.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -28,8 +30,7 @@ constexpr int TH = 8, TW = 32;                   // output tile
 constexpr int IH = 2 * TH + 1, IW = 2 * TW + 2;  // input patch 17 x 66 (one spare column for the zero-weight k slot)
 constexpr int kInBytes = IH * IW * 8;
 constexpr int kThreads = 256, kWarps = 8;
-constexpr int kStageBytes = kWarps * 16 * 128;   // one 16-pixel x 64-channel tile per warp
-constexpr int kSmemBytes = 2 * kInBytes + kStageBytes;
+constexpr int kSmemBytes = 2 * kInBytes;
 static_assert(TH * TW == kWarps * 2 * 16, "two 16-pixel M tiles per warp");
 
 struct StemParams {
@@ -61,14 +62,6 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -103,16 +96,17 @@ __global__ void __launch_bounds__(kThreads, 2) stem_s2_mma_kernel(const StemPara
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int g = lane >> 2, t = lane & 3;
-    const uint32_t s_stage = s_in + 2 * kInBytes + warp * (16 * 128);
     const int total = p.B * p.tiles_x * p.tiles_y;
 
-    // weight fragments of all 8 n-tiles x 3 kernel rows, resident for the whole kernel: lane (g, t) holds cout nt*8 + g,
-    // input pixel kx = t, channels (0, 1) in b0 and (2, 3) in b1 -- the same k-slot mapping as the A loads below
+    // weight fragments of all 8 n-tiles x 3 kernel rows, resident for the whole kernel: lane (g, t) holds output channel
+    // 16 (g / 2) + 2 nt + (g % 2) (the column permutation above), input pixel kx = t, channels (0, 1) in b0 and (2, 3) in b1
+    // -- the same k-slot mapping as the A loads below
     uint2 wb[3][8];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) wb[ky][nt] = __ldg(reinterpret_cast<const uint2*>(p.w) + ((nt * 8 + g) * 3 + ky) * 4 + t);
+        for (int nt = 0; nt < 8; ++nt)
+            wb[ky][nt] = __ldg(reinterpret_cast<const uint2*>(p.w) + ((16 * (g >> 1) + 2 * nt + (g & 1)) * 3 + ky) * 4 + t);
 
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -147,27 +141,28 @@ __global__ void __launch_bounds__(kThreads, 2) stem_s2_mma_kernel(const StemPara
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) mma16816<FP16>(acc[nt], lo.x, hi.x, lo.y, hi.y, wb[ky][nt].x, wb[ky][nt].y);
             }
-            // BN + ReLU + rounding in registers; stage 16 pixels x 128 B (16-byte chunks XOR-swizzled by the pixel index)
+            // BN + ReLU + rounding in registers: this lane's columns are channels 16 t .. 16 t + 15 of rows g and g + 8
+            uint32_t o_lo[8], o_hi[8];
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const float s0 = __ldg(p.sb + nt * 8 + 2 * t), s1 = __ldg(p.sb + nt * 8 + 2 * t + 1);
-                const float b0 = __ldg(p.sb + 64 + nt * 8 + 2 * t), b1 = __ldg(p.sb + 64 + nt * 8 + 2 * t + 1);
-                const uint32_t v_lo = pack2_act(fmaxf(fmaf(acc[nt][0], s0, b0), 0.f), fmaxf(fmaf(acc[nt][1], s1, b1), 0.f), FP16);
-                const uint32_t v_hi = pack2_act(fmaxf(fmaf(acc[nt][2], s0, b0), 0.f), fmaxf(fmaf(acc[nt][3], s1, b1), 0.f), FP16);
-                sts32(s_stage + g * 128 + ((nt ^ g) << 4) + t * 4, v_lo);
-                sts32(s_stage + (g + 8) * 128 + ((nt ^ g) << 4) + t * 4, v_hi);
+            for (int q = 0; q < 4; ++q) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(p.sb + 16 * t) + q);
+                const float4 bi = __ldg(reinterpret_cast<const float4*>(p.sb + 64 + 16 * t) + q);
+                o_lo[2 * q] = pack2_act(fmaxf(fmaf(acc[2 * q][0], sc.x, bi.x), 0.f), fmaxf(fmaf(acc[2 * q][1], sc.y, bi.y), 0.f), FP16);
+                o_hi[2 * q] = pack2_act(fmaxf(fmaf(acc[2 * q][2], sc.x, bi.x), 0.f), fmaxf(fmaf(acc[2 * q][3], sc.y, bi.y), 0.f), FP16);
+                o_lo[2 * q + 1] = pack2_act(fmaxf(fmaf(acc[2 * q + 1][0], sc.z, bi.z), 0.f), fmaxf(fmaf(acc[2 * q + 1][1], sc.w, bi.w), 0.f), FP16);
+                o_hi[2 * q + 1] = pack2_act(fmaxf(fmaf(acc[2 * q + 1][2], sc.z, bi.z), 0.f), fmaxf(fmaf(acc[2 * q + 1][3], sc.w, bi.w), 0.f), FP16);
             }
-            __syncwarp();
             const int gy = oy0 + oy;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {  // 16 pixels x 8 chunks = 128 chunks: 4 pixels per instruction, full 128-byte rows
-                const int c = j * 32 + lane, x = c >> 3, ch = c & 7;
-                const uint4 v = lds128(s_stage + x * 128 + ((ch ^ (x & 7)) << 4));
-                const int gx = ox0 + oxl + x;
-                if (gy < p.Ho && gx < p.Wo)
-                    *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b * p.Ho + gy) * p.Wo + gx) * p.out_pitch + ch * 8) = v;
+            for (int h = 0; h < 2; ++h) {
+                const int gx = ox0 + oxl + g + 8 * h;
+                if (gy < p.Ho && gx < p.Wo) {
+                    const uint32_t* o = h ? o_hi : o_lo;
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b * p.Ho + gy) * p.Wo + gx) * p.out_pitch + 16 * t);
+                    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                }
             }
-            __syncwarp();  // the staging tile is reused by the next M tile
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");

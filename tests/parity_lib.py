@@ -177,7 +177,8 @@ def measure_case(name, dtype, emu_threads=1, want_fp32=True):
     inputs = case_inputs(name)
     model = DD3DB200(cfg).to("cuda")
     model.load_state_dict(sd)
-    # default engine: the box3d predictor runs only at the final 2-D candidates (csrc/b3d_sparse.cu) ...
+    # the box3d predictor evaluated only at the final 2-D candidates (csrc/b3d_sparse.cu; the engine's choice for large heads) ...
+    model.set_engine_option("sparse_box3d", 1)
     out_sparse = model(inputs)
     torch.cuda.synchronize()
     assert model.overflow_flags() == 0

@@ -94,7 +94,7 @@ def test_workspace_liveness_reuse_changes_nothing_but_the_footprint(case, dtype)
 
 @pytest.mark.parametrize("case,dtype", [("dla34", "bf16"), ("v2_99", "bf16"), ("dla34_full", "fp16")])
 def test_sparse_box3d_path_is_arena_independent(case, dtype):
-    """Default engine (box3d predictor at the final candidates only, csrc/b3d_sparse.cu): the box3d tower outputs must
+    """Sparse box3d predictor (at the final candidates only, csrc/b3d_sparse.cu; forced on here): the box3d tower outputs must
     survive in the liveness-packed arena until the sparse predictor has read them, and nothing may depend on what the
     workspace held: zeroed / poisoned arena and reuse on / off give bit-identical detections."""
     a = _run(case, dtype, 0x00, reuse=1, sparse=1)

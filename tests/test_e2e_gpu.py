@@ -48,7 +48,8 @@ def _keys_inst(inst):
 def test_forward_vs_emulating_oracle(arch):
     cfg, sd, model = _model(arch)
     inputs = case_inputs(arch)
-    out = model(inputs)  # default engine: sparse box3d predictor (csrc/b3d_sparse.cu); the detections below come from it
+    model.set_engine_option("sparse_box3d", 1)  # sparse box3d predictor (csrc/b3d_sparse.cu); the detections below come from it
+    out = model(inputs)
     torch.cuda.synchronize()
     assert model.overflow_flags() == 0
     model.set_engine_option("sparse_box3d", 0)  # the stage-level check needs the dense 3-D maps
@@ -227,7 +228,8 @@ def test_non_default_head_configs_vs_oracle(flags):
     model = DD3DB200(cfg).to("cuda")
     model.load_state_dict(sd)
     inputs = make_inputs(2, 128, 256, 721.5, seed_base=7)
-    out = model(inputs)  # default: sparse box3d predictor (per-level weights / class-agnostic N = 16 / no 3-D head all covered)
+    model.set_engine_option("sparse_box3d", 1)  # per-level weights / class-agnostic N = 16 / no 3-D head on the sparse predictor
+    out = model(inputs)
     torch.cuda.synchronize()
     model.set_engine_option("sparse_box3d", 0)
     out_dense = model(inputs)

@@ -537,3 +537,28 @@ def test_conv_cta_pair_bitwise_equals_single_cta(cin, cout, k, stride, H, W, B, 
     for a, b in zip(outs[:n], outs[n:]):
         assert torch.equal(a.view(torch.int16) if a.dtype == torch.bfloat16 else a.view(torch.int32),
                            b.view(torch.int16) if b.dtype == torch.bfloat16 else b.view(torch.int32))
+
+
+@pytest.mark.parametrize("cin,cout,H,W,B,res", [(64, 64, 192, 320, 4, 0), (64, 64, 45, 77, 2, 1), (48, 64, 33, 40, 1, 0), (64, 32, 64, 64, 3, 0)])
+def test_conv_weight_stationary_is_bit_identical(cin, cout, H, W, B, res, act):
+    """3x3 stride-1 layers whose whole weight tensor fits next to the activation patches (<= 64 -> 64 channels: DLA-34 level2,
+    VoVNet stem_2) keep it resident in shared memory and run 5 A patches deep (conv_igemm.cu, ConvParams::wstat) instead of
+    re-streaming it per tile: same MMAs in the same order -> bit-identical to the streaming variant, on maps with many tiles
+    per CTA (the A ring wraps), ragged maps, a K tail (48 channels) and a residual; and equal to torch within one rounding."""
+    L = lib.load()
+    g = torch.Generator().manual_seed(cin + cout + H)
+    x = _rand_act(B, H, W, cin, seed=cin + W)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9)**0.5
+    scale = 0.5 + torch.rand(cout, generator=g)
+    bias = torch.randn(cout, generator=g) * 0.5
+    residual = _rand_act(B, H, W, cout, seed=5) if res else None
+    outs = []
+    try:
+        for mode in (1, 0):
+            assert L.dd3d_set_conv_policy(b"wstat", mode) == 0
+            outs.append(gpu_ops.conv2d(x, w, scale, bias, 1, True, residual, False))
+    finally:
+        L.dd3d_set_conv_policy(b"wstat", -1)
+    assert torch.equal(outs[0], outs[1]), "weight-stationary and streaming variants differ"
+    ref = gpu_ops.conv2d_ref(x.cpu(), w, scale, bias, 1, True, None if residual is None else residual.cpu(), False)
+    _check_bf16(outs[0], ref, f"wstat conv {cin}->{cout} {H}x{W}")
