@@ -212,6 +212,9 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value) {
             e.opt_profile = value ? 1 : 0;
         } else if (n == "workspace_reuse") {  // applies to plans made afterwards
             e.opt_workspace_reuse = value ? 1 : 0;
+        } else if (n == "ese_pool") {  // 1 (default): stage-final eSE pass fused with the next stage's max-pool; 0: separate
+            if (e.opt_ese_pool != (value ? 1 : 0)) e.drop_plans();
+            e.opt_ese_pool = value ? 1 : 0;
         } else if (n == "stem_mma") {  // 1 (default): VoVNet stem_1 on stem_mma.cu; 0: stem_tc.cu (same op graph)
             e.opt_stem_mma = value ? 1 : 0;
         } else if (n == "sparse_box3d") {  // 2 (default): auto by head size; 1: always sparse; 0: dense fp32 maps
@@ -447,6 +450,19 @@ int dd3d_op_maxpool(const void* d_in, void* d_out, int B, int H, int W, int C, i
 
 int64_t dd3d_op_ese_scratch_bytes(int B, int HW, int C) {
     return static_cast<int64_t>(B) * (ese_nsplit(HW) + 1) * C * 4;
+}
+
+int dd3d_op_ese_pool(const void* d_x, int x_pitch, const float* d_fc_w, const float* d_fc_b, const void* d_identity, int id_pitch,
+                     void* d_out, int out_pitch, void* d_pool, int pool_pitch, float* d_scratch, int B, int H, int W, int C,
+                     dd3d_stream stream) {
+    if (C % 8 || !d_pool) return DD3D_ERR_INVALID;
+    float* partial = d_scratch;
+    float* gate = d_scratch + static_cast<size_t>(B) * ese_nsplit(H * W) * C;
+    return cuda_status(launch_ese(static_cast<const __nv_bfloat16*>(d_x), x_pitch, d_fc_w, d_fc_b,
+                                  static_cast<const __nv_bfloat16*>(d_identity), id_pitch, static_cast<__nv_bfloat16*>(d_out),
+                                  out_pitch, partial, gate, B, H * W, C, device_sms(), static_cast<cudaStream_t>(stream),
+                                  g_op_fp16, static_cast<__nv_bfloat16*>(d_pool), pool_pitch, H, W),
+                       nullptr);
 }
 
 int dd3d_op_ese(const void* d_x, int x_pitch, const float* d_fc_w, const float* d_fc_b, const void* d_identity,

@@ -53,6 +53,7 @@ Engine::Engine(const dd3d_model_desc& d) : desc(d) {
     if (const char* e = getenv("DD3D_DLA_FRONT")) opt_dla_front = atoi(e) ? 1 : 0;  // A/B runs of bench.py; default 1
     if (const char* e = getenv("DD3D_SPARSE_BOX3D")) opt_sparse_box3d = std::max(0, std::min(2, atoi(e)));
     if (const char* e = getenv("DD3D_STEM_MMA")) opt_stem_mma = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("DD3D_ESE_POOL")) opt_ese_pool = atoi(e) ? 1 : 0;
 }
 
 Engine::~Engine() {
@@ -568,15 +569,21 @@ struct Builder {
         View cat = alloc(h, w, in_ch + 5 * stage_ch[0]);
         conv1(p + ".stem.stem_3/conv", p + ".stem.stem_3/norm", false, s2, slice(cat, 0, in_ch), 3, 2, true);
         View stage_out;
+        View pooled_cat;  // next stage's concat buffer when its pooled slice was produced by the previous stage's eSE pass
         for (int si = 0; si < 4; ++si) {
             const int sc = stage_ch[si], oc = out_ch[si];
             if (si > 0) {
                 const int hp = (h - 3 + 1) / 2 + 1, wp = (w - 3 + 1) / 2 + 1;  // 3x3 / s2, ceil_mode (vovnet.py:249)
-                cat = alloc(hp, wp, in_ch + 5 * sc);
-                maxpool(stage_out, slice(cat, 0, in_ch), 3);
+                if (pooled_cat.ptr != nullptr || pooled_cat.buf >= 0) {
+                    cat = pooled_cat;  // the previous stage's last eSE pass already wrote the pooled map (ese_scale_pool_kernel)
+                } else {
+                    cat = alloc(hp, wp, in_ch + 5 * sc);
+                    maxpool(stage_out, slice(cat, 0, in_ch), 3);
+                }
                 h = hp;
                 w = wp;
             }
+            View pooled_next;  // stays empty unless this stage's last module fuses the next stage's pool
             for (int b = 0; b < blocks[si]; ++b) {
                 const std::string name = "OSA" + std::to_string(si + 2) + "_" + std::to_string(b + 1);
                 const std::string q = p + ".stage" + std::to_string(si + 2) + "." + name;
@@ -597,13 +604,19 @@ struct Builder {
                 View dst;
                 View next_cat;
                 const bool last = (b == blocks[si] - 1);
+                View pooled;
                 if (last) {
                     dst = alloc(h, w, oc);
+                    if (si < 3 && E->opt_ese_pool && h >= 3 && w >= 3) {
+                        // the eSE scale pass of a stage's last module also writes the next stage's 3x3 / s2 pooled input
+                        pooled_next = alloc((h - 3 + 1) / 2 + 1, (w - 3 + 1) / 2 + 1, oc + 5 * stage_ch[si + 1]);
+                        pooled = slice(pooled_next, 0, oc);
+                    }
                 } else {
                     next_cat = alloc(h, w, oc + 5 * sc);
                     dst = slice(next_cat, 0, oc);
                 }
-                ese(q + ".ese.fc", xt, b > 0 ? &x : nullptr, dst);
+                ese(q + ".ese.fc", xt, b > 0 ? &x : nullptr, dst, pooled.buf >= 0 ? &pooled : nullptr);
                 if (last) {
                     stage_out = dst;
                 } else {
@@ -611,11 +624,12 @@ struct Builder {
                 }
                 in_ch = oc;
             }
+            pooled_cat = pooled_next;
             feats->push_back(stage_out);
         }
     }
 
-    void ese(const std::string& fc, View xt, const View* identity, View dst) {
+    void ese(const std::string& fc, View xt, const View* identity, View dst, const View* pooled = nullptr) {
         const EseLayer& L = E->ese_layer(fc, xt.C);
         // The concat conv (the op just emitted) writes per-tile channel sums from its epilogue: [B][T][C], T = 4 * tiles
         const int T = 4 * conv_tiles_per_image(xt.H, xt.W);
@@ -625,6 +639,7 @@ struct Builder {
         touch(xt);
         if (identity) touch(*identity);
         touch(dst);
+        if (pooled) touch(*pooled);
         ++op_idx;
         if (dry) return;
         Op& cv = P->ops.back();
@@ -646,6 +661,10 @@ struct Builder {
         op.ksize = T;
         op.outs[0] = dst;
         op.nouts = 1;
+        if (pooled) {  // outs[1]: the 3x3 / s2 ceil-mode max-pool of dst, written by the same pass
+            op.outs[1] = *pooled;
+            op.nouts = 2;
+        }
         P->ops.push_back(op);
     }
 
@@ -1345,7 +1364,9 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
                 cuda_check(launch_ese_fused(op.in.ptr, op.in.pitch, op.f2, op.ksize, op.ese->d_w, op.ese->d_b,
                                             op.has_identity ? op.identity.ptr : nullptr,
                                             op.has_identity ? op.identity.pitch : 0, op.out.ptr, op.out.pitch, op.f0, op.f1,
-                                            P.B, op.in.H * op.in.W, op.in.C, num_sms, stream, fp16),
+                                            P.B, op.in.H * op.in.W, op.in.C, num_sms, stream, fp16,
+                                            op.nouts == 2 ? op.outs[1].ptr : nullptr, op.nouts == 2 ? op.outs[1].pitch : 0,
+                                            op.in.H, op.in.W),
                            "eSE");
                 break;
             case Op::RELU:
@@ -1431,6 +1452,7 @@ void Engine::get_profile(double* ms, double* flops, double* bytes, int32_t* laun
             case Op::ESE:
                 launches[4] += 3;
                 bytes[4] += in_px * op.in.C * 2 * (op.has_identity ? 3 : 2);  // pooling is fused into the concat conv
+                if (op.nouts == 2) bytes[4] += static_cast<double>(P.B) * op.outs[1].H * op.outs[1].W * op.in.C * 2;
                 break;
             case Op::RELU:
                 launches[5] += 1;

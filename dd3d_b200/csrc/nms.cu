@@ -325,8 +325,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
 // coordinate offsets), so the greedy scan is independent per (image, class) -- but one class can hold most of an image's
 // candidates (the DLA-34 bench batch: 616 of 623 in one class), and the n^2 / 2 IoUs of a 600-box class on ONE SM cost
 // 205 us (ncu, profiles/r02i_launches_dla34.csv): the NMS was 9 % of the DLA-34 step.  Four launches:
-//   nms_sort_kernel  (B CTAs)            : sort the image's candidates by score_3d; publish order / class and a CLASS-MAJOR
-//                                          copy (boxes + sorted position, score order inside a class, 64-aligned segments)
+//   nms_sort_kernel  (32 x B CTAs)       : rank sort of the image's candidates by score_3d; publish order / class and a
+//                                          CLASS-MAJOR copy (boxes + sorted position, score order inside a class, 64-aligned)
 //   nms_mask_kernel  (64 x B CTAs)       : IoU bit matrix of every class segment, 64 x 64 boxes per step, on all SMs
 //   nms_scan_kernel  (C x B CTAs)        : the serial greedy pass over the bit matrix only (no IoU): resolve the 64 x 64
 //                                          diagonal word by word, OR the survivors' rows into the removed bit vector
@@ -372,29 +372,49 @@ __host__ __device__ __forceinline__ NmsScratch bind_nms_scratch(void* scratch, i
     return s;
 }
 
-__global__ void __launch_bounds__(kNmsThreads, 1) nms_sort_kernel(const __grid_constant__ NmsParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    const int b = blockIdx.x;
-    const int cap = kLevels * p.topk;
-    const int C = p.num_classes;
-    NmsSmem m = carve(smem_raw, cap);
+constexpr int kSortThreads = 256, kSortCtasPerImage = 32;
+
+// Rank sort.  The keys (score_3d desc, level asc, index asc) are unique, so the sorted position of a candidate is the number
+// of smaller keys -- n^2 independent comparisons that spread over kSortCtasPerImage CTAs per image (64 candidates per CTA
+// step, four threads per candidate) instead of the 55 - 91 barrier-separated passes of a one-CTA bitonic sort (22 - 46 us).
+// The same loop counts the smaller keys OF THE SAME CLASS: the candidate's row in the class-major copy (score order inside a
+// class, 64-aligned class segments) that the bit-matrix kernels work on.  Every CTA rebuilds the key table and the class
+// histogram itself (n <= 8192 candidates, three words each); no cross-CTA dependency, no atomics on results.
+__global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const __grid_constant__ NmsParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int b = blockIdx.y;
+    const int cap = kLevels * p.topk, C = p.num_classes;
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);       // [cap]
+    uint16_t* slots = reinterpret_cast<uint16_t*>(keys + cap);    // [cap]
+    uint8_t* scls = reinterpret_cast<uint8_t*>(slots + cap);      // [cap]
     __shared__ int s_lvl_off[kLevels + 1];
-    __shared__ int s_cnt[256], s_run[256], s_seg[257];
+    __shared__ int s_cnt[256], s_seg[257];
     const Det* cand = p.cand + static_cast<size_t>(b) * cap;
-    const int n = sort_candidates(p, b, cand, m, s_lvl_off);
     const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap, C);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) s_cnt[c] = s_run[c] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int slot = m.val[i];
-        const int c = cand[slot].cls;
-        sc.order[static_cast<size_t>(b) * cap + i] = static_cast<uint16_t>(slot);
-        sc.cls[static_cast<size_t>(b) * cap + i] = static_cast<uint8_t>(c);
-        sc.removed[static_cast<size_t>(b) * cap + i] = 0;
-        m.cls[i] = static_cast<uint8_t>(c);
-        atomicAdd(&s_cnt[c], 1);  // a count: independent of the order of the atomics
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int l = 0; l < kLevels; ++l) {
+            s_lvl_off[l] = off;
+            off += min(p.cand_count[b * kLevels + l], p.topk);
+        }
+        s_lvl_off[kLevels] = off;
     }
-    if (threadIdx.x == 0) sc.n[b] = n;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s_cnt[c] = 0;
+    __syncthreads();
+    const int n = s_lvl_off[kLevels];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int l = 0;
+#pragma unroll
+        for (int t = 1; t < kLevels; ++t)
+            if (i >= s_lvl_off[t]) l = t;
+        const int slot = l * p.topk + (i - s_lvl_off[l]);
+        const Det& d = cand[slot];
+        const uint32_t sb = ~__float_as_uint(d.score3d);  // positive floats: larger score -> smaller key
+        keys[i] = (static_cast<uint64_t>(sb) << 32) | (static_cast<uint64_t>(l) << 28) | static_cast<uint32_t>(d.index);
+        slots[i] = static_cast<uint16_t>(slot);
+        scls[i] = static_cast<uint8_t>(d.cls);
+        atomicAdd(&s_cnt[d.cls], 1);  // a count: independent of the order of the atomics
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         int blk = 0;
@@ -405,38 +425,39 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_sort_kernel(const __grid_c
         s_seg[C] = blk;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c <= C; c += blockDim.x) {
-        sc.seg_blk[b * (C + 1) + c] = s_seg[c];
-        if (c < C) sc.seg_cnt[b * C + c] = s_cnt[c];
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) sc.n[b] = n;
+        for (int c = threadIdx.x; c <= C; c += blockDim.x) {
+            sc.seg_blk[b * (C + 1) + c] = s_seg[c];
+            if (c < C) sc.seg_cnt[b * C + c] = s_cnt[c];
+        }
     }
-    // stable counting sort by class of the score-sorted list: rank inside the warp by __match_any_sync, warps and chunks in
-    // order through the per-(warp, class) table (reuses the dead sort keys)
-    int* wcnt = reinterpret_cast<int*>(m.key);  // [32 warps][C]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int start = 0; start < n; start += blockDim.x) {
-        for (int j = threadIdx.x; j < nwarp * C; j += blockDim.x) wcnt[j] = 0;
-        __syncthreads();
-        const int i = start + threadIdx.x;
-        const int c = i < n ? m.cls[i] : 0xFFFF;
-        const unsigned same = __match_any_sync(0xffffffffu, c);
-        const int rank = __popc(same & ((1u << lane) - 1));
-        if (i < n && rank == 0) wcnt[warp * C + c] = __popc(same);
-        __syncthreads();
-        if (i < n) {
-            int before = s_run[c];
-            for (int w = 0; w < warp; ++w) before += wcnt[w * C + c];
-            const size_t row = static_cast<size_t>(b) * sc.capP + static_cast<size_t>(s_seg[c]) * 64 + before + rank;
-            const Det& d = cand[m.val[i]];
-            sc.cpos[row] = static_cast<uint16_t>(i);
+    const int e = threadIdx.x >> 2, part = threadIdx.x & 3;
+    for (int grp = blockIdx.x; grp * 64 < n; grp += gridDim.x) {
+        const int i = grp * 64 + e;
+        const uint64_t ki = i < n ? keys[i] : 0ull;
+        const int ci = i < n ? scls[i] : 255;  // class ids are < 255
+        int r = 0, rc = 0;
+        for (int j = part; j < n; j += 4) {
+            const int lt = keys[j] < ki ? 1 : 0;
+            r += lt;
+            rc += (scls[j] == ci) ? lt : 0;
+        }
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        rc += __shfl_xor_sync(0xffffffffu, rc, 1);
+        rc += __shfl_xor_sync(0xffffffffu, rc, 2);
+        if (part == 0 && i < n) {
+            const int slot = slots[i];
+            const size_t o = static_cast<size_t>(b) * cap + r;
+            sc.order[o] = static_cast<uint16_t>(slot);
+            sc.cls[o] = static_cast<uint8_t>(ci);
+            sc.removed[o] = 0;
+            const size_t row = static_cast<size_t>(b) * sc.capP + static_cast<size_t>(s_seg[ci]) * 64 + rc;
+            const Det& d = cand[slot];
+            sc.cpos[row] = static_cast<uint16_t>(r);
             sc.cbox[row] = make_float4(d.box[0], d.box[1], d.box[2], d.box[3]);
         }
-        __syncthreads();
-        for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
-            int tot = 0;
-            for (int w = 0; w < nwarp; ++w) tot += wcnt[w * C + cc];
-            s_run[cc] += tot;
-        }
-        __syncthreads();
     }
 }
 
@@ -608,12 +629,13 @@ cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream) {
     if (cap > kMaxCand || p.B <= 0) return cudaErrorInvalidValue;
     const size_t smem = static_cast<size_t>(kMaxCand) * 8 + static_cast<size_t>(cap) * 16 +
                         static_cast<size_t>(cap) * 8 + static_cast<size_t>(kMaxCand) * 2 + static_cast<size_t>(cap) * 2;
+    const size_t smem_sort = static_cast<size_t>(cap) * (8 + 2 + 1) + 16;
     static size_t attr_smem_dev[64] = {};  // per device; the limit is 227 KiB minus the static shared memory: ask for what we use
     size_t& attr_smem = attr_smem_dev[current_device_or_zero()];
     if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxCand * 11 + 16);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(nms_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) {
@@ -627,7 +649,7 @@ cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream) {
         g_class_parallel = (e && atoi(e) == 0) ? 0 : 1;
     }
     if (g_class_parallel && p.scratch != nullptr && p.do_nms && p.nms_thresh > 0.f && p.num_classes >= 1 && p.num_classes <= 255) {
-        nms_sort_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);
+        nms_sort_kernel<<<dim3(kSortCtasPerImage, p.B), kSortThreads, smem_sort, stream>>>(p);
         nms_mask_kernel<<<dim3(kMaskCtasPerImage, p.B), kMaskThreads, 0, stream>>>(p);
         nms_scan_kernel<<<dim3(p.num_classes, p.B), kScanThreads, 0, stream>>>(p);
         nms_finish_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);

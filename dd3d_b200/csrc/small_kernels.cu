@@ -264,6 +264,76 @@ __global__ void __launch_bounds__(256) ese_scale_kernel(const __nv_bfloat16* __r
     }
 }
 
+// eSE scale pass of the LAST module of a stage fused with the 3x3 / stride-2 ceil-mode max-pool that opens the next stage
+// (vovnet.py:249 `Pooling` after vovnet.py:233-236): one thread per (pooled pixel, 8-channel chunk) computes the up-to-nine
+// window values out = 16-bit(x * gate (+ identity)), writes the ones it OWNS (the 2x2 block at the window's origin, plus the
+// odd last row / column of the map) to the full-resolution output that the FPN lateral reads, and their maximum to the pooled
+// output.  The separate pool re-read the whole stage output from HBM (1.57 GB for V2-99 stage2 at B = 32); here the window
+// overlap (2.25 loads per input element) is served by L1 / L2.  max of rounded values == the pool of the stored tensor.
+__global__ void __launch_bounds__(256) ese_scale_pool_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gate,
+                                                             const __nv_bfloat16* __restrict__ identity,
+                                                             __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pool,
+                                                             int B, int H, int W, int C, int x_pitch, int id_pitch,
+                                                             int out_pitch, int pool_pitch, int Ho, int Wo, int fp16) {
+    const int vc = C >> 3;
+    const size_t total = static_cast<size_t>(B) * Ho * Wo * vc;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(i % vc);
+        size_t pix = i / vc;
+        const int ox = static_cast<int>(pix % Wo);
+        pix /= Wo;
+        const int oy = static_cast<int>(pix % Ho);
+        const int b = static_cast<int>(pix / Ho);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * C + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * C + v * 8 + 4));
+        uint4 u[9], q[9];
+        bool ok[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int iy = 2 * oy + k / 3, ix = 2 * ox + k % 3;
+            ok[k] = iy < H && ix < W;  // ceil_mode: windows are clipped to the input
+            if (ok[k]) {
+                const size_t p = (static_cast<size_t>(b) * H + iy) * W + ix;
+                u[k] = __ldg(reinterpret_cast<const uint4*>(x + p * x_pitch + v * 8));
+                if (identity != nullptr) q[k] = __ldg(reinterpret_cast<const uint4*>(identity + p * id_pitch + v * 8));
+            }
+        }
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);
+        bool first = true;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (!ok[k]) continue;
+            const int dy = k / 3, dx = k % 3;
+            float f[8];
+            float2 t;
+            t = unpack2_act(u[k].x, fp16); f[0] = t.x * g0.x; f[1] = t.y * g0.y;
+            t = unpack2_act(u[k].y, fp16); f[2] = t.x * g0.z; f[3] = t.y * g0.w;
+            t = unpack2_act(u[k].z, fp16); f[4] = t.x * g1.x; f[5] = t.y * g1.y;
+            t = unpack2_act(u[k].w, fp16); f[6] = t.x * g1.z; f[7] = t.y * g1.w;
+            if (identity != nullptr) {
+                t = unpack2_act(q[k].x, fp16); f[0] += t.x; f[1] += t.y;
+                t = unpack2_act(q[k].y, fp16); f[2] += t.x; f[3] += t.y;
+                t = unpack2_act(q[k].z, fp16); f[4] += t.x; f[5] += t.y;
+                t = unpack2_act(q[k].w, fp16); f[6] += t.x; f[7] += t.y;
+            }
+            uint4 o;
+            o.x = pack2_act(f[0], f[1], fp16); o.y = pack2_act(f[2], f[3], fp16); o.z = pack2_act(f[4], f[5], fp16);
+            o.w = pack2_act(f[6], f[7], fp16);
+            // owner of input pixel (2 oy + dy, 2 ox + dx): the window whose 2x2 origin block holds it; the odd last row / column
+            // (never inside an origin block) belongs to the last window
+            const bool own_y = dy < 2 || oy == Ho - 1, own_x = dx < 2 || ox == Wo - 1;
+            if (own_y && own_x) {
+                const size_t p = (static_cast<size_t>(b) * H + 2 * oy + dy) * W + 2 * ox + dx;
+                *reinterpret_cast<uint4*>(out + p * out_pitch + v * 8) = o;
+            }
+            m = first ? o : max8(m, o, fp16);
+            first = false;
+        }
+        *reinterpret_cast<uint4*>(pool + (static_cast<size_t>(b * Ho + oy) * Wo + ox) * pool_pitch + v * 8) = m;
+    }
+}
+
 // relu on packed 16-bit floats: a set sign bit (negative, -0) -> +0; identical for bf16 and fp16
 __global__ void relu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t nvec) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
@@ -323,7 +393,9 @@ int ese_nsplit(int HW) {
 
 cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, const float* fc_b,
                        const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out, int out_pitch, float* partial,
-                       float* gate, int B, int HW, int C, int num_sms, cudaStream_t stream, int fp16) {
+                       float* gate, int B, int HW, int C, int num_sms, cudaStream_t stream, int fp16, __nv_bfloat16* pool,
+                       int pool_pitch, int H, int W) {
+    if (pool != nullptr && (H * W != HW || H < 3 || W < 3)) return cudaErrorInvalidValue;
     const int vc = C / 8;
     int rows = 256 / vc;
     if (rows < 1) rows = 1;
@@ -336,6 +408,13 @@ cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, c
                                                                           1.0f / static_cast<float>(HW));
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (pool != nullptr) {
+        const int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;
+        const size_t tp = static_cast<size_t>(B) * Ho * Wo * vc;
+        ese_scale_pool_kernel<<<grid_for(tp, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, pool, B, H, W, C, x_pitch,
+                                                                             id_pitch, out_pitch, pool_pitch, Ho, Wo, fp16);
+        return cudaGetLastError();
+    }
     const size_t total = static_cast<size_t>(B) * HW * vc;
     ese_scale_kernel<<<grid_for((total + kEseUnroll - 1) / kEseUnroll, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
                                                                       id_pitch, out_pitch, fp16);
@@ -346,7 +425,8 @@ cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, c
 cudaError_t launch_ese_fused(const __nv_bfloat16* x, int x_pitch, const float* tile_partial, int T, const float* fc_w,
                              const float* fc_b, const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out,
                              int out_pitch, float* sums, float* gate, int B, int HW, int C, int num_sms,
-                             cudaStream_t stream, int fp16) {
+                             cudaStream_t stream, int fp16, __nv_bfloat16* pool, int pool_pitch, int H, int W) {
+    if (pool != nullptr && (H * W != HW || H < 3 || W < 3)) return cudaErrorInvalidValue;
     ese_reduce_kernel<<<dim3((C + 63) / 64, B), 256, 0, stream>>>(tile_partial, sums, T, C, C);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -354,6 +434,13 @@ cudaError_t launch_ese_fused(const __nv_bfloat16* x, int x_pitch, const float* t
                                                                           1.0f / static_cast<float>(HW));
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (pool != nullptr) {
+        const int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;  // 3x3 / s2, ceil_mode
+        const size_t total = static_cast<size_t>(B) * Ho * Wo * (C / 8);
+        ese_scale_pool_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, pool, B, H, W, C, x_pitch,
+                                                                                id_pitch, out_pitch, pool_pitch, Ho, Wo, fp16);
+        return cudaGetLastError();
+    }
     const size_t total = static_cast<size_t>(B) * HW * (C / 8);
     ese_scale_kernel<<<grid_for((total + kEseUnroll - 1) / kEseUnroll, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
                                                                       id_pitch, out_pitch, fp16);

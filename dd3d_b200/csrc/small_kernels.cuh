@@ -40,13 +40,15 @@ int ese_nsplit(int HW);
 // partial: [B][ese_nsplit(HW)][C] fp32 scratch, gate: [B][C] fp32 scratch.
 cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, const float* fc_b,
                        const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out, int out_pitch, float* partial,
-                       float* gate, int B, int HW, int C, int num_sms, cudaStream_t stream, int fp16 = 0);
+                       float* gate, int B, int HW, int C, int num_sms, cudaStream_t stream, int fp16 = 0,
+                       __nv_bfloat16* pool = nullptr, int pool_pitch = 0, int H = 0, int W = 0);
 
 // tile_partial: [B][T][C] fp32 rows written by the concat-conv epilogue (T = 4 * tiles per image); sums: [B][C] scratch.
 cudaError_t launch_ese_fused(const __nv_bfloat16* x, int x_pitch, const float* tile_partial, int T, const float* fc_w,
                              const float* fc_b, const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out,
                              int out_pitch, float* sums, float* gate, int B, int HW, int C, int num_sms,
-                             cudaStream_t stream, int fp16 = 0);
+                             cudaStream_t stream, int fp16 = 0, __nv_bfloat16* pool = nullptr, int pool_pitch = 0, int H = 0,
+                             int W = 0);  // pool != null: also writes the 3x3 / s2 ceil-mode max-pool of `out` (H * W == HW)
 
 cudaError_t launch_relu(const __nv_bfloat16* x, __nv_bfloat16* out, size_t n_elems, int num_sms, cudaStream_t stream);
 

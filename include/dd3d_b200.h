@@ -154,7 +154,8 @@ int dd3d_wait_host(dd3d_handle h, int slot);
 int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags);
 /* Runtime switches the reference's callers toggle on the meta-arch: "do_postprocess" (postprocess_in_inference,
  * scripts/train.py:206-209, test_time_augmentation.py:107), "do_nms" (core.py:134), "profile" (see
- * dd3d_get_profile), "stem_mma" (default 1: VoVNet stem_1 runs on csrc/stem_mma.cu, 0: on csrc/stem_tc.cu), "sparse_box3d" (2 = auto, the default: the fused FCOS3D predictor conv is evaluated only at the pixels that survive the 2-D
+ * dd3d_get_profile), "ese_pool" (default 1: the eSE scale pass of a VoVNet stage's last module also writes the 3x3 / stride-2 max-pooled input of
+ * the next stage instead of a separate pool kernel re-reading the stage output; changing it drops the plans), "stem_mma" (default 1: VoVNet stem_1 runs on csrc/stem_mma.cu, 0: on csrc/stem_tc.cu), "sparse_box3d" (2 = auto, the default: the fused FCOS3D predictor conv is evaluated only at the pixels that survive the 2-D
  * threshold and per-level top-k, between the two halves of the decode, when the head maps hold >= 250 000 pixels -- the dense
  * "b3d<l>" maps of dd3d_get_tensor then do not exist; 1: always; 0: never (dense fp32 maps, for stage-level tests); changing
  * it drops the engine's plans), "dla_front" (default 1: DLA-34 base_layer + level0 + level1 + pool run as one kernel; 0: layer by layer; flipping it
@@ -271,6 +272,11 @@ int dd3d_op_maxpool(const void* d_in, void* d_out, int B, int H, int W, int C, i
 int dd3d_op_ese(const void* d_x, int x_pitch, const float* d_fc_w, const float* d_fc_b, const void* d_identity,
                 int id_pitch, void* d_out, int out_pitch, float* d_scratch, int B, int HW, int C, dd3d_stream stream);
 int64_t dd3d_op_ese_scratch_bytes(int B, int HW, int C);
+/* dd3d_op_ese_pool: dd3d_op_ese whose scale pass also writes d_pool = the 3x3 / stride-2 ceil-mode max-pool of d_out
+ * ([B][(H-2)/2+1][(W-2)/2+1][pool_pitch]; vovnet.py:249 after :233-236), the engine's form for the last module of a stage. */
+int dd3d_op_ese_pool(const void* d_x, int x_pitch, const float* d_fc_w, const float* d_fc_b, const void* d_identity, int id_pitch,
+                     void* d_out, int out_pitch, void* d_pool, int pool_pitch, float* d_scratch, int B, int H, int W, int C,
+                     dd3d_stream stream);
 /* Bird's-eye-view rotated NMS (reference DO_BEV_NMS branch, core.py:137-151 -> postprocessing.py:22-108 ->
  * tridet/layers/bev_nms.py:51-133 -> detectron2 batched_nms_rotated), in place on the detections a dd3d_forward run
  * with option "do_postprocess" = 0 produced: d_dets [B][cap], d_counts [B].  d_poses: [B][7] sensor->global pose of

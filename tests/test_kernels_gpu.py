@@ -316,6 +316,38 @@ def test_ese(Cc, H, W, ident, act):
     _check_bf16(out, ref, "eSE")
 
 
+@pytest.mark.parametrize("Cc,H,W,ident", [(256, 24, 40, False), (512, 15, 25, True), (768, 9, 14, True), (64, 3, 3, False)])
+def test_ese_with_fused_pool(Cc, H, W, ident, act):
+    """dd3d_op_ese_pool (csrc/small_kernels.cu ese_scale_pool_kernel): the eSE scale pass that also writes the next stage's
+    3x3 / stride-2 ceil-mode max-pool (vovnet.py:249).  Full-resolution output bit-identical to dd3d_op_ese; pooled output
+    bit-identical to torch's max_pool2d(ceil_mode=True) of it; even, odd (last row / column owned by the last window) and
+    minimal maps; channel-sliced outputs."""
+    L = lib.load()
+    g = torch.Generator().manual_seed(Cc + H)
+    B = 2
+    x = _rand_act(B, H, W, Cc, seed=Cc)
+    idt = _rand_act(B, H, W, 0, seed=Cc + 1, pitch=Cc + 64) if ident else None
+    fw = torch.randn(Cc, Cc, generator=g) / Cc**0.5
+    fb = torch.randn(Cc, generator=g)
+    d_fw, d_fb = fw.cuda(), fb.cuda()
+    scratch = torch.empty(L.dd3d_op_ese_scratch_bytes(B, H * W, Cc) // 4, dtype=torch.float32, device="cuda")
+    ref_out = torch.zeros(B, H, W, Cc, dtype=gpu_ops.ACT, device="cuda")
+    assert L.dd3d_op_ese(gpu_ops._p(x), Cc, gpu_ops._p(d_fw), gpu_ops._p(d_fb), gpu_ops._p(idt), Cc + 64 if ident else 0,
+                         gpu_ops._p(ref_out), Cc, gpu_ops._p(scratch), B, H * W, Cc, gpu_ops._stream()) == 0
+    Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+    out = torch.full((B, H, W, Cc + 32), 7.0, dtype=gpu_ops.ACT, device="cuda")
+    pool = torch.full((B, Ho, Wo, Cc + 16), 7.0, dtype=gpu_ops.ACT, device="cuda")
+    assert L.dd3d_op_ese_pool(gpu_ops._p(x), Cc, gpu_ops._p(d_fw), gpu_ops._p(d_fb), gpu_ops._p(idt), Cc + 64 if ident else 0,
+                              gpu_ops._p(out), Cc + 32, gpu_ops._p(pool), Cc + 16, gpu_ops._p(scratch), B, H, W, Cc,
+                              gpu_ops._stream()) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out[..., :Cc], ref_out), "full-resolution output differs from the unfused scale pass"
+    assert (out[..., Cc:].float() == 7.0).all() and (pool[..., Cc:].float() == 7.0).all()
+    pref = F.max_pool2d(ref_out.float().permute(0, 3, 1, 2), 3, 2, ceil_mode=True).permute(0, 2, 3, 1)
+    assert pref.shape[1:3] == (Ho, Wo)
+    assert torch.equal(pool[..., :Cc].float(), pref), "pooled output != max_pool2d(ceil_mode) of the scale pass's output"
+
+
 # ------------------------------------------------------------------------------------------------ decode + NMS
 def _run_detect(desc, maps, K, sizes, level_hw, strides, topk):
     L = lib.load()

@@ -1,17 +1,17 @@
 #!/bin/bash
-# round-2 GPU job 12: weight-stationary halo convs (64->64), stem_mma with permuted channels / direct stores, sparse-box3d auto
+# round-2 GPU job 12: weight-stationary halo convs (64->64), eSE scale + max-pool fusion, NMS rank sort, stem_mma with permuted channels / direct stores, sparse-box3d auto
 # policy, NMS scan / mask tweaks: canaries, A/B, conv launch table, full suite
 O=gpurun_out/r02l
 mkdir -p $O
 T="timeout -k 10"
-$T 600 python -m pytest tests/test_kernels_gpu.py -x -q -k "conv or nms or decode or dla_front or stem" > $O/canary.log 2>&1
+$T 600 python -m pytest tests/test_kernels_gpu.py -x -q -k "conv or nms or decode or dla_front or stem or ese or maxpool" > $O/canary.log 2>&1
 rc=$?; echo "canary rc=$rc"; tail -12 $O/canary.log
 $T 600 python -m pytest tests/test_e2e_gpu.py -x -q > $O/canary2.log 2>&1
 rc2=$?; echo "canary2 rc=$rc2"; tail -15 $O/canary2.log
 if [ $rc -ne 0 ]; then echo "kernel canary failed"; fi
 for round in 1 2; do
-  DD3D_CONV_WSTAT=0 $T 300 python bench.py --cpu-images 0 > $O/ab_a_stream_$round.json 2> $O/ab_a_stream_$round.err
-  $T 300 python bench.py --cpu-images 0 > $O/ab_b_wstat_$round.json 2> $O/ab_b_wstat_$round.err
+  DD3D_CONV_WSTAT=0 DD3D_ESE_POOL=0 $T 300 python bench.py --cpu-images 0 > $O/ab_a_old_$round.json 2> $O/ab_a_old_$round.err
+  $T 300 python bench.py --cpu-images 0 > $O/ab_b_new_$round.json 2> $O/ab_b_new_$round.err
 done
 python - <<'PY'
 import json,glob
