@@ -212,7 +212,7 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value) {
             e.opt_profile = value ? 1 : 0;
         } else if (n == "workspace_reuse") {  // applies to plans made afterwards
             e.opt_workspace_reuse = value ? 1 : 0;
-        } else if (n == "ese_pool") {  // 1 (default): stage-final eSE pass fused with the next stage's max-pool; 0: separate
+        } else if (n == "ese_pool") {  // 1: stage-final eSE pass fused with the next stage's max-pool; 0 (default): separate kernels
             if (e.opt_ese_pool != (value ? 1 : 0)) e.drop_plans();
             e.opt_ese_pool = value ? 1 : 0;
         } else if (n == "stem_mma") {  // 1 (default): VoVNet stem_1 on stem_mma.cu; 0: stem_tc.cu (same op graph)

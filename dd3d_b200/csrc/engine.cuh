@@ -185,7 +185,8 @@ class Engine {
     int opt_do_postprocess = 1;
     int opt_profile = 0;
     int opt_workspace_reuse = 1;  // 0: bump allocation, every op output keeps its own memory (stage-level tests / debugging)
-    int opt_ese_pool = 1;  // 1: a VoVNet stage's last eSE scale pass also writes the next stage's max-pooled input; 0: separate pool
+    int opt_ese_pool = 0;  // 1: a VoVNet stage's last eSE scale pass also writes the next stage's max-pooled input; 0 (default):
+                           // separate pool kernel -- measured: the fused pass is ~10 % SLOWER (profiles/r02l_*: 1.53 vs 0.75 + 0.56 ms)
     int opt_stem_mma = 1;  // 1: VoVNet stem_1 on the register-fragment kernel (stem_mma.cu); 0: tcgen05 im2col kernel (stem_tc.cu)
     int opt_sparse_box3d = 2;  // box3d predictor at the final candidates only (b3d_sparse.cu): 0 never (dense maps), 1 always, 2 auto (by head size)
     int opt_dla_front = 1;  // 1: DLA-34 base_layer + level0 + level1 (+ pool) as ONE kernel (dla_front.cu); 0: layer by layer

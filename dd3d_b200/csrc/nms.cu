@@ -543,23 +543,16 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const __grid_con
     for (int blk = 0; blk < nblk; ++blk) {
         const int cn = min(64, nc - blk * 64);
         if (tid == 0) {
-            // greedy pass over the 64 x 64 diagonal block: 16 words at a time in registers, then a pure ALU chain
+            // greedy pass over the 64 x 64 diagonal block: jump from survivor to survivor (one step per KEPT box, not per
+            // box): the lowest box still alive is kept and clears everything its diagonal word suppresses
             const unsigned long long* dg = s_diag[blk & 1];
-            unsigned long long removed = s_removed[blk];
-            if (cn < 64) removed |= ~0ull << cn;
+            unsigned long long alive = ~s_removed[blk];
+            if (cn < 64) alive &= (1ull << cn) - 1ull;
             unsigned long long kept = 0ull;
-#pragma unroll
-            for (int i0 = 0; i0 < 64; i0 += 16) {
-                unsigned long long d[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) d[i] = dg[i0 + i];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (!((removed >> (i0 + i)) & 1ull)) {
-                        kept |= 1ull << (i0 + i);
-                        removed |= d[i];
-                    }
-                }
+            while (alive) {
+                const int i = __ffsll(static_cast<long long>(alive)) - 1;
+                kept |= 1ull << i;
+                alive &= ~(dg[i] | (1ull << i));  // dg[i] holds bits j > i only
             }
             s_removed[blk] = ~kept;  // bits >= cn are never read
             s_kept = kept;

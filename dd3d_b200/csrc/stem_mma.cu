@@ -116,11 +116,12 @@ __global__ void __launch_bounds__(kThreads, 2) stem_s2_mma_kernel(const StemPara
     asm volatile("cp.async.commit_group;" ::: "memory");
     int buf = 0;
     for (; tile < total; tile += gridDim.x, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // this tile's patch (issued one iteration ago) is visible to all warps, AND every warp has finished the
+                          // previous tile -- only now may the other buffer, which that tile was read from, be overwritten
         const int next = tile + gridDim.x;
         if (next < total) load_input(p, next, s_in + (buf ^ 1) * kInBytes);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncthreads();  // this tile's patch is visible; every warp finished reading the other buffer one iteration ago
         int b, oy0, ox0;
         tile_coords(p, tile, &b, &oy0, &ox0);
         const uint32_t s_cur = s_in + buf * kInBytes;
