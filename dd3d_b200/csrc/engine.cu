@@ -738,13 +738,16 @@ struct Builder {
         const bool per_level = E->desc.per_level_predictors != 0, box3d_on = E->desc.box3d_on != 0;
         const int C3 = E->desc.class_agnostic_box3d ? 1 : C;
         const int cls_pitch = round_up(C + (nusc ? kNumAttributes + 1 : 0), 16), b3d_pitch = round_up(11 * C3, 16);
-        // sparse box3d predictor: forced (1), off (0) or auto (2, default): the dense launch costs ~0.45 us per 1 000 head
-        // pixels, the gathered one a near-constant 0.08 - 0.12 ms of latency-bound K loop -- V2-99 at B = 32 (4.1 M pixels):
-        // 1.75 ms dense vs 0.12 ms sparse; DLA-34 at B = 8 (82 k pixels): 0.05 ms dense vs 0.08 ms sparse
+        // sparse box3d predictor: forced (1), off (0) or auto (2, default).  The dense launch costs ~0.45 us per 1 000 head
+        // pixels, the gathered one a near-constant 0.08 - 0.12 ms of latency-bound K loop: V2-99 at B = 32 (4.1 M pixels)
+        // 1.75 ms dense vs 0.12 ms sparse; DLA-34 at B = 8 (82 k pixels) 0.05 ms dense vs 0.08 ms sparse.  The rule looks at
+        // the head pixels of ONE image, not of the batch, so that an image gives bit-identical detections whatever batch it
+        // rides in (the two predictors differ in fp32 summation order): 900x1600 V2-99 = 127 875 pixels -> sparse at every
+        // batch size, 384x1280 DLA-34 = 10 230 -> dense.
         size_t head_px = 0;
-        for (int l = 0; l < L; ++l) head_px += static_cast<size_t>(B) * feats[l].H * feats[l].W;
+        for (int l = 0; l < L; ++l) head_px += static_cast<size_t>(feats[l].H) * feats[l].W;
         const bool sparse3 = box3d_on && b3d_pitch <= kB3dSparseMaxN &&
-                             (E->opt_sparse_box3d == 1 || (E->opt_sparse_box3d == 2 && head_px >= 250000));
+                             (E->opt_sparse_box3d == 1 || (E->opt_sparse_box3d == 2 && head_px >= 50000));
         P->sparse_b3d = sparse3;
         P->b3d_rows = sparse3 ? alloc_f32(static_cast<size_t>(B) * kLevels * E->desc.pre_nms_topk * b3d_pitch) : nullptr;
         P->cls_pitch = cls_pitch;

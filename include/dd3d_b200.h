@@ -157,7 +157,7 @@ int dd3d_overflow_flags(dd3d_handle h, dd3d_stream stream, int32_t* h_flags);
  * dd3d_get_profile), "ese_pool" (default 0; 1: the eSE scale pass of a VoVNet stage's last module also writes the 3x3 / stride-2 max-pooled input of
  * the next stage instead of a separate pool kernel re-reading the stage output -- bit-identical, measured ~10 % slower than the
  * two kernels, kept as a tested alternative; changing it drops the plans), "stem_mma" (default 1: VoVNet stem_1 runs on csrc/stem_mma.cu, 0: on csrc/stem_tc.cu), "sparse_box3d" (2 = auto, the default: the fused FCOS3D predictor conv is evaluated only at the pixels that survive the 2-D
- * threshold and per-level top-k, between the two halves of the decode, when the head maps hold >= 250 000 pixels -- the dense
+ * threshold and per-level top-k, between the two halves of the decode, when the head maps of one image hold >= 50 000 pixels (a per-image rule: batch-independent results) -- the dense
  * "b3d<l>" maps of dd3d_get_tensor then do not exist; 1: always; 0: never (dense fp32 maps, for stage-level tests); changing
  * it drops the engine's plans), "dla_front" (default 1: DLA-34 base_layer + level0 + level1 + pool run as one kernel; 0: layer by layer; flipping it
  * drops the engine's plans), "workspace_reuse" (default 1: activation buffers with disjoint lifetimes share workspace memory --
