@@ -30,7 +30,8 @@ constexpr int TH = 8, TW = 32;                   // output tile
 constexpr int IH = 2 * TH + 1, IW = 2 * TW + 2;  // input patch 17 x 66 (one spare column for the zero-weight k slot)
 constexpr int kInBytes = IH * IW * 8;
 constexpr int kThreads = 256, kWarps = 8;
-constexpr int kSmemBytes = 2 * kInBytes;
+constexpr int kBufs = 4;  // input patches in flight: a tile's math is ~700 cycles, a DRAM round trip ~2 000
+constexpr int kSmemBytes = kBufs * kInBytes;
 static_assert(TH * TW == kWarps * 2 * 16, "two 16-pixel M tiles per warp");
 
 struct StemParams {
@@ -111,16 +112,22 @@ __global__ void __launch_bounds__(kThreads, 2) stem_s2_mma_kernel(const StemPara
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+    // kBufs-deep ring of input patches: tiles k .. k + kBufs - 2 are in flight while tile k is computed.  A buffer may be
+    // refilled only after the barrier that retires its readers: the patch of tile k + kBufs - 1 goes into the buffer tile k - 1
+    // was read from, and is issued AFTER the barrier at the top of iteration k.
     int tile = blockIdx.x;
-    if (tile < total) load_input(p, tile, s_in);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < kBufs - 1; ++i) {
+        const int tl = tile + i * static_cast<int>(gridDim.x);
+        if (tl < total) load_input(p, tl, s_in + i * kInBytes);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     int buf = 0;
-    for (; tile < total; tile += gridDim.x, buf ^= 1) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();  // this tile's patch (issued one iteration ago) is visible to all warps, AND every warp has finished the
-                          // previous tile -- only now may the other buffer, which that tile was read from, be overwritten
-        const int next = tile + gridDim.x;
-        if (next < total) load_input(p, next, s_in + (buf ^ 1) * kInBytes);
+    for (; tile < total; tile += gridDim.x, buf = (buf + 1) % kBufs) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kBufs - 2) : "memory");  // all but the newest kBufs - 2 groups: tile k landed
+        __syncthreads();  // ... and is visible to all warps, and every warp has finished tile k - 1
+        const int ahead = tile + (kBufs - 1) * static_cast<int>(gridDim.x);
+        if (ahead < total) load_input(p, ahead, s_in + ((buf + kBufs - 1) % kBufs) * kInBytes);
         asm volatile("cp.async.commit_group;" ::: "memory");
         int b, oy0, ox0;
         tile_coords(p, tile, &b, &oy0, &ox0);
