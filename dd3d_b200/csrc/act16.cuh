@@ -21,6 +21,17 @@ __device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
 __device__ __forceinline__ uint32_t pack2_act(float a, float b, int fp16) {
     return fp16 ? pack2_f16(a, b) : pack2_bf16(a, b);
 }
+// ReLU fused into the conversion (cvt.rn.relu: negative results and -0 become +0): same value as rounding max(x, 0)
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b) {
+    uint32_t r;
+    if (FP16) {
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    } else {
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    }
+    return r;
+}
 __device__ __forceinline__ float2 unpack2_bf16(uint32_t u) {
     return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }

@@ -139,12 +139,18 @@ __device__ __forceinline__ void load_input(const FrontParams& p, int tile, uint3
     tile_coords(p, tile, &b, &oy0, &ox0);
     const int iy0 = 2 * oy0 - 5, ix0 = 2 * ox0 - 5;
     const __nv_bfloat16* img = p.in + static_cast<size_t>(b) * p.H * p.W * 4;
-    for (int i = threadIdx.x; i < IPX; i += kThreads) {
-        const int y = i / IW, x = i - y * IW;
-        const int gy = iy0 + y, gx = ix0 + x;
-        const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-        const __nv_bfloat16* src = img + (ok ? (static_cast<size_t>(gy) * p.W + gx) * 4 : 0);
-        cp_async8(dst + i * 8, src, ok ? 8u : 0u);
+    // warp -> patch rows, lane -> columns: no integer division in the address math
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int y = warp; y < IH; y += kWarps) {
+        const int gy = iy0 + y;
+        const bool row_ok = gy >= 0 && gy < p.H;
+        const __nv_bfloat16* row = img + static_cast<size_t>(row_ok ? gy : 0) * p.W * 4;
+#pragma unroll
+        for (int x = lane; x < IW; x += 32) {
+            const int gx = ix0 + x;
+            const bool ok = row_ok && gx >= 0 && gx < p.W;
+            cp_async8(dst + (y * IW + x) * 8, row + (ok ? gx * 4 : 0), ok ? 8u : 0u);
+        }
     }
 }
 
@@ -219,10 +225,8 @@ __global__ void __launch_bounds__(kThreads, 2) dla_front_kernel(const FrontParam
                 const bool in_hi = (by0 + y_hi) >= 0 && (by0 + y_hi) < p.H && (bx0 + x_hi) >= 0 && (bx0 + x_hi) < p.W;
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
-                    const uint32_t v_lo = pack2<FP16>(fmaxf(fmaf(acc[nt][0], sc[nt][0], bi[nt][0]), 0.f),
-                                                      fmaxf(fmaf(acc[nt][1], sc[nt][1], bi[nt][1]), 0.f));
-                    const uint32_t v_hi = pack2<FP16>(fmaxf(fmaf(acc[nt][2], sc[nt][0], bi[nt][0]), 0.f),
-                                                      fmaxf(fmaf(acc[nt][3], sc[nt][1], bi[nt][1]), 0.f));
+                    const uint32_t v_lo = pack2_relu<FP16>(fmaf(acc[nt][0], sc[nt][0], bi[nt][0]), fmaf(acc[nt][1], sc[nt][1], bi[nt][1]));
+                    const uint32_t v_hi = pack2_relu<FP16>(fmaf(acc[nt][2], sc[nt][0], bi[nt][0]), fmaf(acc[nt][3], sc[nt][1], bi[nt][1]));
                     if (p_lo < RBPX) sts32(s_base + px_off(p_lo, nt) + t * 4, in_lo ? v_lo : 0u);
                     if (p_hi < RBPX) sts32(s_base + px_off(p_hi, nt) + t * 4, in_hi ? v_hi : 0u);
                 }
@@ -269,10 +273,8 @@ __global__ void __launch_bounds__(kThreads, 2) dla_front_kernel(const FrontParam
                 const bool in_hi = (ly0 + y_hi) >= 0 && (ly0 + y_hi) < p.H && (lx0 + x_hi) >= 0 && (lx0 + x_hi) < p.W;
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
-                    const uint32_t v_lo = pack2<FP16>(fmaxf(fmaf(acc[nt][0], sc[nt][0], bi[nt][0]), 0.f),
-                                                      fmaxf(fmaf(acc[nt][1], sc[nt][1], bi[nt][1]), 0.f));
-                    const uint32_t v_hi = pack2<FP16>(fmaxf(fmaf(acc[nt][2], sc[nt][0], bi[nt][0]), 0.f),
-                                                      fmaxf(fmaf(acc[nt][3], sc[nt][1], bi[nt][1]), 0.f));
+                    const uint32_t v_lo = pack2_relu<FP16>(fmaf(acc[nt][0], sc[nt][0], bi[nt][0]), fmaf(acc[nt][1], sc[nt][1], bi[nt][1]));
+                    const uint32_t v_hi = pack2_relu<FP16>(fmaf(acc[nt][2], sc[nt][0], bi[nt][0]), fmaf(acc[nt][3], sc[nt][1], bi[nt][1]));
                     if (p_lo < R0PX) sts32(s_l0 + px_off(p_lo, nt) + t * 4, in_lo ? v_lo : 0u);
                     if (p_hi < R0PX) sts32(s_l0 + px_off(p_hi, nt) + t * 4, in_hi ? v_hi : 0u);
                 }
@@ -315,8 +317,8 @@ __global__ void __launch_bounds__(kThreads, 2) dla_front_kernel(const FrontParam
                 for (int nt = 0; nt < 4; ++nt) {
                     const float s0 = __ldg(p.sb2 + nt * 8 + 2 * t), s1 = __ldg(p.sb2 + nt * 8 + 2 * t + 1);
                     const float b0 = __ldg(p.sb2 + 32 + nt * 8 + 2 * t), b1 = __ldg(p.sb2 + 32 + nt * 8 + 2 * t + 1);
-                    const uint32_t v_lo = pack2<FP16>(fmaxf(fmaf(acc[nt][0], s0, b0), 0.f), fmaxf(fmaf(acc[nt][1], s1, b1), 0.f));
-                    const uint32_t v_hi = pack2<FP16>(fmaxf(fmaf(acc[nt][2], s0, b0), 0.f), fmaxf(fmaf(acc[nt][3], s1, b1), 0.f));
+                    const uint32_t v_lo = pack2_relu<FP16>(fmaf(acc[nt][0], s0, b0), fmaf(acc[nt][1], s1, b1));
+                    const uint32_t v_hi = pack2_relu<FP16>(fmaf(acc[nt][2], s0, b0), fmaf(acc[nt][3], s1, b1));
                     // pixel (m, x): 64 B, its four 16-byte chunks XOR-swizzled by (x >> 1) & 3 (rows g / g+2 / g+4 / g+6
                     // would otherwise share banks)
                     sts32(s_stage + (m * 16 + g) * 64 + ((nt ^ ((g >> 1) & 3)) << 4) + t * 4, v_lo);
