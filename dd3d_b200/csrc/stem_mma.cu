@@ -40,6 +40,7 @@ struct StemParams {
     const float* sb;          // scale[64] | bias[64]
     __nv_bfloat16* out;       // [B][Ho][Wo][out_pitch]
     int B, H, W, Ho, Wo, out_pitch, tiles_x, tiles_y;
+    int wide_store;  // out is 32-byte aligned and out_pitch a multiple of 16 channels: 256-bit stores
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -173,9 +174,16 @@ __global__ void __launch_bounds__(kThreads, 2) stem_s2_mma_kernel(const StemPara
                 const int gx = ox0 + oxl + g + 8 * h;
                 if (gy < p.Ho && gx < p.Wo) {
                     const uint32_t* o = h ? o_hi : o_lo;
-                    uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b * p.Ho + gy) * p.Wo + gx) * p.out_pitch + 16 * t);
-                    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    __nv_bfloat16* dst = p.out + (static_cast<size_t>(b * p.Ho + gy) * p.Wo + gx) * p.out_pitch + 16 * t;
+                    if (p.wide_store) {
+                        // one 256-bit store per (pixel, lane): a whole 32-byte sector at once instead of two half-sector writes
+                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                                     "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                                     : "memory");
+                    } else {
+                        reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
                 }
             }
         }
@@ -194,6 +202,7 @@ cudaError_t launch_stem_s2_mma(const __nv_bfloat16* in4, const __nv_bfloat16* w,
     p.in = in4; p.w = w; p.sb = sb; p.out = out;
     p.B = B; p.H = H; p.W = W; p.Ho = (H + 1) / 2; p.Wo = (W + 1) / 2;
     p.out_pitch = out_pitch;
+    p.wide_store = (reinterpret_cast<uintptr_t>(out) % 32 == 0 && out_pitch % 16 == 0) ? 1 : 0;
     p.tiles_x = (p.Wo + TW - 1) / TW;
     p.tiles_y = (p.Ho + TH - 1) / TH;
     static uint64_t attr_devices[2] = {0, 0};

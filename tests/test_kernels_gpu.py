@@ -201,14 +201,16 @@ def test_stem_s2_mma_ragged_and_multi_tile(act):
         wm[:, :, :3, :3] = w.permute(0, 2, 3, 1)
         d_in, d_w, d_sb = x4.cuda(), wm.to(gpu_ops.ACT).cuda(), torch.cat([scale, bias]).cuda()
         Ho, Wo = (H + 1) // 2, (W + 1) // 2
-        out = torch.full((B, Ho, Wo, 64), 7.0, dtype=gpu_ops.ACT, device="cuda")
-        assert L.dd3d_op_stem_s2_mma(gpu_ops._p(d_in), gpu_ops._p(d_w), gpu_ops._p(d_sb), gpu_ops._p(out), 64, B, H, W,
+        pitch = 72 if B == 1 else 64  # 72: not a multiple of 16 channels -> the 2 x 128-bit store path instead of 256-bit stores
+        out = torch.full((B, Ho, Wo, pitch), 7.0, dtype=gpu_ops.ACT, device="cuda")
+        assert L.dd3d_op_stem_s2_mma(gpu_ops._p(d_in), gpu_ops._p(d_w), gpu_ops._p(d_sb), gpu_ops._p(out), pitch, B, H, W,
                                      gpu_ops._stream()) == 0
         torch.cuda.synchronize()
         y = F.conv2d(x4[..., :3].float().permute(0, 3, 1, 2), w, None, 2, 1)
         y = F.relu(y * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
         assert y.shape[1:3] == (Ho, Wo)
-        _check_bf16(out, y, f"stem_1 mma {B}x{H}x{W}")
+        _check_bf16(out[..., :64], y, f"stem_1 mma {B}x{H}x{W}")
+        assert (out[..., 64:].float() == 7.0).all()
 
 
 @pytest.mark.parametrize("B,H,W,out_pitch,pool_pitch", [(2, 64, 128, 32, 32), (1, 44, 76, 48, 40), (3, 128, 256, 32, 0)])
