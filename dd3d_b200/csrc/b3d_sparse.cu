@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include "b3d_sparse.cuh"
+#include "pdl.cuh"
 
 namespace dd3d {
 
@@ -68,6 +69,7 @@ __device__ __forceinline__ void stage_weights(const __nv_bfloat16* w, int n_pad,
 
 template <int NT, bool FP16>
 __global__ void __launch_bounds__(kThreads) b3d_sparse_kernel(const B3dSparseParams p) {
+    DD3D_PDL_PROLOGUE();
     extern __shared__ __align__(16) uint8_t smem[];
     const int b = blockIdx.z, l = blockIdx.y, r0 = blockIdx.x * kRowsPerCta;
     const int bl = b * kLevels + l;
@@ -173,11 +175,8 @@ template <int NT>
 cudaError_t launch_nt(const B3dSparseParams& p, cudaStream_t stream) {
     const int smem = 2 * p.n_pad * 128;
     dim3 grid((p.topk + kRowsPerCta - 1) / kRowsPerCta, kLevels, p.B);
-    if (p.fp16)
-        b3d_sparse_kernel<NT, true><<<grid, kThreads, smem, stream>>>(p);
-    else
-        b3d_sparse_kernel<NT, false><<<grid, kThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+    if (p.fp16) return launch_pdl(b3d_sparse_kernel<NT, true>, grid, dim3(kThreads), smem, stream, p);
+    return launch_pdl(b3d_sparse_kernel<NT, false>, grid, dim3(kThreads), smem, stream, p);
 }
 
 }  // namespace

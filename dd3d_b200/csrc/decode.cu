@@ -12,6 +12,7 @@
 //                     gathers its 4 + 11 regression values and decodes the 2-D box and the 3-D box.
 // Set semantics match `topk(sorted=False)` (fcos2d.py:312-313); order is fixed later by the NMS sort.
 #include "detect.cuh"
+#include "pdl.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -40,6 +41,7 @@ __device__ __forceinline__ int score_bin(const DecodeParams& p, float s) {
 // mode 0: histogram, mode 1: compaction
 template <int MODE>
 __global__ void __launch_bounds__(kDenseThreads) dense_kernel(const __grid_constant__ DecodeParams p) {
+    DD3D_PDL_PROLOGUE();
     __shared__ uint32_t shist[MODE == 0 ? kHistBins : 1];
     const int l = find_level(p, blockIdx.x);
     const DecodeLevel& L = p.lvl[l];
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(kDenseThreads) dense_kernel(const __grid_const
 
 // One block per (level, image): locate the bin of the k-th largest score.
 __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ DecodeParams p) {
+    DD3D_PDL_PROLOGUE();
     __shared__ uint32_t chunk[256];
     const int bl = blockIdx.y * kLevels + blockIdx.x;
     const uint32_t* gh = p.hist + static_cast<size_t>(bl) * kHistBins;
@@ -330,6 +333,7 @@ __device__ void decode_one(const DecodeParams& p, const DecodeLevel& L, int b, i
 // One block per (level, image): the final candidate list.  Candidates in histogram bins above the k-th score's bin are in
 // ("sure"); inside that bin the exact rank (score desc, index asc) decides.  fin[slot] = (score bits, index).
 __global__ void __launch_bounds__(256) select_final_kernel(const __grid_constant__ DecodeParams p) {
+    DD3D_PDL_PROLOGUE();
     const int l = blockIdx.x, b = blockIdx.y;
     const int bl = b * kLevels + l;
     const int* sel = p.sel + bl * 4;
@@ -362,6 +366,7 @@ __global__ void __launch_bounds__(256) select_final_kernel(const __grid_constant
 // holds most of the candidates, and one 256-thread CTA walking 600 - 1000 of them was 18 - 31 us of pure latency.
 constexpr int kFinalSplit = 8, kFinalThreads = 128;
 __global__ void __launch_bounds__(kFinalThreads) decode_final_kernel(const __grid_constant__ DecodeParams p) {
+    DD3D_PDL_PROLOGUE();
     const int l = blockIdx.x / kFinalSplit, part = blockIdx.x % kFinalSplit, b = blockIdx.y;
     const int bl = b * kLevels + l;
     const int n = p.cand_count[bl];
@@ -381,6 +386,7 @@ __global__ void __launch_bounds__(kFinalThreads) decode_final_kernel(const __gri
 }
 
 __global__ void clear_kernel(uint32_t* ptr, size_t nwords) {
+    DD3D_PDL_PROLOGUE();
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nwords;
          i += static_cast<size_t>(gridDim.x) * blockDim.x)
         ptr[i] = 0;
@@ -450,18 +456,17 @@ void decode_finalize_params(DecodeParams* p) {
 cudaError_t launch_decode_select(const DecodeParams& p, cudaStream_t stream) {
     const size_t bl = static_cast<size_t>(p.B) * kLevels;
     const size_t clear_words = (align_up(bl * kHistBins * 4, 256) + align_up(bl * 2 * 4, 256) + 256) / 4;
-    clear_kernel<<<148, 256, 0, stream>>>(p.hist, clear_words);
+    cudaError_t e = launch_pdl(clear_kernel, dim3(148), dim3(256), 0, stream, p.hist, clear_words);
     dim3 dgrid(p.total_blocks, p.B);
-    dense_kernel<0><<<dgrid, kDenseThreads, 0, stream>>>(p);
-    select_kernel<<<dim3(kLevels, p.B), 256, 0, stream>>>(p);
-    dense_kernel<1><<<dgrid, kDenseThreads, 0, stream>>>(p);
-    select_final_kernel<<<dim3(kLevels, p.B), 256, 0, stream>>>(p);
-    return cudaGetLastError();
+    if (e == cudaSuccess) e = launch_pdl(dense_kernel<0>, dgrid, dim3(kDenseThreads), 0, stream, p);
+    if (e == cudaSuccess) e = launch_pdl(select_kernel, dim3(kLevels, p.B), dim3(256), 0, stream, p);
+    if (e == cudaSuccess) e = launch_pdl(dense_kernel<1>, dgrid, dim3(kDenseThreads), 0, stream, p);
+    if (e == cudaSuccess) e = launch_pdl(select_final_kernel, dim3(kLevels, p.B), dim3(256), 0, stream, p);
+    return e;
 }
 
 cudaError_t launch_decode_final(const DecodeParams& p, cudaStream_t stream) {
-    decode_final_kernel<<<dim3(kLevels * kFinalSplit, p.B), kFinalThreads, 0, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(decode_final_kernel, dim3(kLevels * kFinalSplit, p.B), dim3(kFinalThreads), 0, stream, p);
 }
 
 cudaError_t launch_decode(const DecodeParams& p, cudaStream_t stream) {

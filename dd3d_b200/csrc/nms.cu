@@ -11,6 +11,7 @@
 //   4. scale boxes to the requested output size, clip, drop empty boxes (detector_postprocess).
 #include "detect.cuh"
 #include "device_once.cuh"
+#include "pdl.cuh"
 
 #include <stdlib.h>
 
@@ -293,6 +294,7 @@ __device__ void finish_image(const NmsParams& p, int b, const Det* cand, NmsSmem
 // ---------------------------------------------------------------------------------------------- single-CTA kernel
 // One CTA per image does everything (used when no scratch is given -- the TTA merge -- and when NMS is off).
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_constant__ NmsParams p) {
+    DD3D_PDL_PROLOGUE();
     extern __shared__ uint8_t smem_raw[];
     const int b = blockIdx.x;
     const int cap = kLevels * p.topk;
@@ -381,6 +383,7 @@ constexpr int kSortThreads = 256, kSortCtasPerImage = 32;
 // class, 64-aligned class segments) that the bit-matrix kernels work on.  Every CTA rebuilds the key table and the class
 // histogram itself (n <= 8192 candidates, three words each); no cross-CTA dependency, no atomics on results.
 __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const __grid_constant__ NmsParams p) {
+    DD3D_PDL_PROLOGUE();
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int b = blockIdx.y;
     const int cap = kLevels * p.topk, C = p.num_classes;
@@ -469,6 +472,7 @@ constexpr int kMaskCtasPerImage = 64;
 // instead of sitting in one CTA's serial loops.  One pair = 64 x 64 boxes: thread = (row, quarter of the columns), the four
 // 16-bit quarters of a word are merged with two shuffles.
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const __grid_constant__ NmsParams p) {
+    DD3D_PDL_PROLOGUE();
     const int b = blockIdx.y;
     const int cap = kLevels * p.topk, C = p.num_classes;
     const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap, C);
@@ -525,6 +529,7 @@ constexpr int kScanThreads = 128;  // >= W (cap <= 8192)
 // into the removed bit vector by all threads at once -- (survivor, word) items are independent loads, merged with
 // shared-memory atomicOr (commutative: the result does not depend on the order).
 __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const __grid_constant__ NmsParams p) {
+    DD3D_PDL_PROLOGUE();
     const int c = blockIdx.x, b = blockIdx.y;
     const int cap = kLevels * p.topk, C = p.num_classes;
     const NmsScratch sc = bind_nms_scratch(p.scratch, p.B, cap, C);
@@ -585,6 +590,7 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const __grid_con
 }
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_finish_kernel(const __grid_constant__ NmsParams p) {
+    DD3D_PDL_PROLOGUE();
     extern __shared__ uint8_t smem_raw[];
     const int b = blockIdx.x;
     const int cap = kLevels * p.topk;
@@ -642,14 +648,13 @@ cudaError_t launch_nms(const NmsParams& p, cudaStream_t stream) {
         g_class_parallel = (e && atoi(e) == 0) ? 0 : 1;
     }
     if (g_class_parallel && p.scratch != nullptr && p.do_nms && p.nms_thresh > 0.f && p.num_classes >= 1 && p.num_classes <= 255) {
-        nms_sort_kernel<<<dim3(kSortCtasPerImage, p.B), kSortThreads, smem_sort, stream>>>(p);
-        nms_mask_kernel<<<dim3(kMaskCtasPerImage, p.B), kMaskThreads, 0, stream>>>(p);
-        nms_scan_kernel<<<dim3(p.num_classes, p.B), kScanThreads, 0, stream>>>(p);
-        nms_finish_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);
-        return cudaGetLastError();
+        cudaError_t e = launch_pdl(nms_sort_kernel, dim3(kSortCtasPerImage, p.B), dim3(kSortThreads), smem_sort, stream, p);
+        if (e == cudaSuccess) e = launch_pdl(nms_mask_kernel, dim3(kMaskCtasPerImage, p.B), dim3(kMaskThreads), 0, stream, p);
+        if (e == cudaSuccess) e = launch_pdl(nms_scan_kernel, dim3(p.num_classes, p.B), dim3(kScanThreads), 0, stream, p);
+        if (e == cudaSuccess) e = launch_pdl(nms_finish_kernel, dim3(p.B), dim3(kNmsThreads), smem, stream, p);
+        return e;
     }
-    nms_kernel<<<p.B, kNmsThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(nms_kernel, dim3(p.B), dim3(kNmsThreads), smem, stream, p);
 }
 
 }  // namespace dd3d

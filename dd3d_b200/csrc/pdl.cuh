@@ -1,0 +1,45 @@
+// Programmatic dependent launch for the small kernels of the forward (pre / post-processing, pools, eSE): every one of them
+// used to be a full serialisation point of the stream (drain, then launch latency: ~4 us x 51 kernels per V2-99 forward, x 14
+// per DLA-34 forward).  DD3D_PDL_PROLOGUE() is the FIRST statement of such a kernel: it waits until every earlier kernel of
+// the stream has completed and its memory is visible (so nothing the kernel reads or overwrites can be in flight), then lets
+// the next kernel's CTAs be scheduled as this grid's CTAs retire.  Launch with launch_pdl(); DD3D_NO_PDL=1 turns the launch
+// attribute off (the prologue is then a no-op), which tests/test_determinism_gpu.py uses to compare both modes bit for bit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include <utility>
+
+#define DD3D_PDL_PROLOGUE()                                   \
+    do {                                                      \
+        asm volatile("griddepcontrol.wait;" ::: "memory");    \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+    } while (0)
+
+namespace dd3d {
+
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("DD3D_NO_PDL");
+        on = (e && atoi(e)) ? 0 : 1;
+    }
+    return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+}  // namespace dd3d

@@ -4,6 +4,7 @@
 //   max-pool     : 2x2/s2 (DLA Tree.downsample, dla.py:224-225), 3x3/s2 ceil (VoVNet, vovnet.py:248-249)
 //   eSE          : global avg-pool -> fc -> hsigmoid -> channel scale (+identity)   vovnet.py:169-185,233-236
 //   relu         : p7 input (detectron2 LastLevelP6P7)
+#include "pdl.cuh"
 #include "small_kernels.cuh"
 
 #include "act16.cuh"
@@ -23,6 +24,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const T* __restrict__ s
                                                          __nv_bfloat16* __restrict__ dst, int B, int Hs, int Ws, int Hp, int Wp,
                                                          int size_stride, float m0, float m1, float m2, float s0, float s1,
                                                          float s2, int fp16, int vec_ok) {
+    DD3D_PDL_PROLOGUE();
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
     const int b = blockIdx.z;
@@ -106,6 +108,7 @@ __device__ __forceinline__ uint4 max8(uint4 a, uint4 b, int fp16) {
 
 __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W,
                                int C, int in_pitch, int Ho, int Wo, int out_pitch, int ksize, int fp16) {
+    DD3D_PDL_PROLOGUE();
     const int vc = C >> 3;
     const size_t total = static_cast<size_t>(B) * Ho * Wo * vc;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -138,6 +141,7 @@ __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat
 // partial[b][split][c] = sum over the split's pixels (fixed order -> deterministic).
 __global__ void ese_pool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C,
                                 int pitch, int nsplit, int rows, int fp16) {
+    DD3D_PDL_PROLOGUE();
     extern __shared__ float red[];  // [rows][C]
     const int vc = C >> 3;
     const int b = blockIdx.y, split = blockIdx.x;
@@ -167,6 +171,7 @@ __global__ void ese_pool_kernel(const __nv_bfloat16* __restrict__ x, float* __re
 // sums[b][c] = sum over the T per-tile/per-warp partial rows written by the concat-conv epilogue (fixed order).
 __global__ void ese_reduce_kernel(const float* __restrict__ tile_partial, float* __restrict__ sums, int T, int C,
                                   int pitch) {
+    DD3D_PDL_PROLOGUE();
     __shared__ float red[4][64];
     const int b = blockIdx.y;
     const int c = blockIdx.x * 64 + (threadIdx.x & 63);
@@ -192,6 +197,7 @@ __global__ void ese_reduce_kernel(const float* __restrict__ tile_partial, float*
 // gate[b][co] = relu6(W[co,:] . mean[b,:] + bias[co] + 3) / 6      (one warp per output channel)
 __global__ void ese_fc_kernel(const float* __restrict__ partial, const float* __restrict__ w, const float* __restrict__ bias,
                               float* __restrict__ gate, int C, int nsplit, float inv_hw) {
+    DD3D_PDL_PROLOGUE();
     extern __shared__ float mean[];  // [C]
     const int b = blockIdx.y;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -221,6 +227,7 @@ __global__ void __launch_bounds__(256) ese_scale_kernel(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ identity,
                                                         __nv_bfloat16* __restrict__ out, int B, int HW, int C, int x_pitch,
                                                         int id_pitch, int out_pitch, int fp16) {
+    DD3D_PDL_PROLOGUE();
     const int vc = C >> 3;
     const size_t total = static_cast<size_t>(B) * HW * vc;
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -275,6 +282,7 @@ __global__ void __launch_bounds__(256) ese_scale_pool_kernel(const __nv_bfloat16
                                                              __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pool,
                                                              int B, int H, int W, int C, int x_pitch, int id_pitch,
                                                              int out_pitch, int pool_pitch, int Ho, int Wo, int fp16) {
+    DD3D_PDL_PROLOGUE();
     const int vc = C >> 3;
     const size_t total = static_cast<size_t>(B) * Ho * Wo * vc;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -336,6 +344,7 @@ __global__ void __launch_bounds__(256) ese_scale_pool_kernel(const __nv_bfloat16
 
 // relu on packed 16-bit floats: a set sign bit (negative, -0) -> +0; identical for bf16 and fp16
 __global__ void relu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t nvec) {
+    DD3D_PDL_PROLOGUE();
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + i);
@@ -364,24 +373,18 @@ cudaError_t launch_preprocess(const void* src, int src_is_u8, const int* d_sizes
     const int esz = src_is_u8 ? 1 : 4;
     const int vec_ok = (Ws % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % (4 * esz) == 0) &&
                        ((static_cast<size_t>(Hs) * Ws) % 4 == 0);
-    if (src_is_u8) {
-        preprocess_kernel<uint8_t><<<grid, block, 0, stream>>>(static_cast<const uint8_t*>(src), d_sizes, dst, B, Hs, Ws, Hp, Wp,
-                                                               size_stride, mean[0], mean[1], mean[2], std[0], std[1], std[2],
-                                                               fp16, vec_ok);
-    } else {
-        preprocess_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(src), d_sizes, dst, B, Hs, Ws, Hp, Wp,
-                                                             size_stride, mean[0], mean[1], mean[2], std[0], std[1], std[2], fp16,
-                                                             vec_ok);
-    }
-    return cudaGetLastError();
+    if (src_is_u8)
+        return launch_pdl(preprocess_kernel<uint8_t>, grid, block, 0, stream, static_cast<const uint8_t*>(src), d_sizes, dst, B,
+                          Hs, Ws, Hp, Wp, size_stride, mean[0], mean[1], mean[2], std[0], std[1], std[2], fp16, vec_ok);
+    return launch_pdl(preprocess_kernel<float>, grid, block, 0, stream, static_cast<const float*>(src), d_sizes, dst, B, Hs, Ws,
+                      Hp, Wp, size_stride, mean[0], mean[1], mean[2], std[0], std[1], std[2], fp16, vec_ok);
 }
 
 cudaError_t launch_maxpool(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, int in_pitch,
                            int Ho, int Wo, int out_pitch, int ksize, int num_sms, cudaStream_t stream, int fp16) {
     const size_t total = static_cast<size_t>(B) * Ho * Wo * (C / 8);
-    maxpool_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, out, B, H, W, C, in_pitch, Ho, Wo, out_pitch,
-                                                                    ksize, fp16);
-    return cudaGetLastError();
+    return launch_pdl(maxpool_kernel, dim3(grid_for(total, 256, num_sms)), dim3(256), 0, stream, in, out, B, H, W, C, in_pitch, Ho,
+                      Wo, out_pitch, ksize, fp16);
 }
 
 int ese_nsplit(int HW) {
@@ -390,6 +393,24 @@ int ese_nsplit(int HW) {
     if (n > 64) n = 64;
     return n;
 }
+
+namespace {
+// the scale pass shared by both eSE forms: plain, or fused with the next stage's 3x3 / s2 ceil-mode max-pool
+cudaError_t launch_ese_scale(const __nv_bfloat16* x, int x_pitch, const float* gate, const __nv_bfloat16* identity, int id_pitch,
+                             __nv_bfloat16* out, int out_pitch, int B, int HW, int C, int num_sms, cudaStream_t stream, int fp16,
+                             __nv_bfloat16* pool, int pool_pitch, int H, int W) {
+    const int vc = C / 8;
+    if (pool != nullptr) {
+        const int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;
+        const size_t tp = static_cast<size_t>(B) * Ho * Wo * vc;
+        return launch_pdl(ese_scale_pool_kernel, dim3(grid_for(tp, 256, num_sms)), dim3(256), 0, stream, x, gate, identity, out, pool,
+                          B, H, W, C, x_pitch, id_pitch, out_pitch, pool_pitch, Ho, Wo, fp16);
+    }
+    const size_t total = static_cast<size_t>(B) * HW * vc;
+    return launch_pdl(ese_scale_kernel, dim3(grid_for((total + kEseUnroll - 1) / kEseUnroll, 256, num_sms)), dim3(256), 0, stream, x,
+                      gate, identity, out, B, HW, C, x_pitch, id_pitch, out_pitch, fp16);
+}
+}  // namespace
 
 cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, const float* fc_b,
                        const __nv_bfloat16* identity, int id_pitch, __nv_bfloat16* out, int out_pitch, float* partial,
@@ -400,25 +421,14 @@ cudaError_t launch_ese(const __nv_bfloat16* x, int x_pitch, const float* fc_w, c
     int rows = 256 / vc;
     if (rows < 1) rows = 1;
     const int nsplit = ese_nsplit(HW);
-    ese_pool_kernel<<<dim3(nsplit, B), vc * rows, static_cast<size_t>(rows) * C * sizeof(float), stream>>>(
-        x, partial, HW, C, x_pitch, nsplit, rows, fp16);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(ese_pool_kernel, dim3(nsplit, B), dim3(vc * rows), static_cast<size_t>(rows) * C * sizeof(float),
+                               stream, x, partial, HW, C, x_pitch, nsplit, rows, fp16);
     if (e != cudaSuccess) return e;
-    ese_fc_kernel<<<dim3((C + 7) / 8, B), 256, C * sizeof(float), stream>>>(partial, fc_w, fc_b, gate, C, nsplit,
-                                                                          1.0f / static_cast<float>(HW));
-    e = cudaGetLastError();
+    e = launch_pdl(ese_fc_kernel, dim3((C + 7) / 8, B), dim3(256), C * sizeof(float), stream, static_cast<const float*>(partial),
+                   fc_w, fc_b, gate, C, nsplit, 1.0f / static_cast<float>(HW));
     if (e != cudaSuccess) return e;
-    if (pool != nullptr) {
-        const int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;
-        const size_t tp = static_cast<size_t>(B) * Ho * Wo * vc;
-        ese_scale_pool_kernel<<<grid_for(tp, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, pool, B, H, W, C, x_pitch,
-                                                                             id_pitch, out_pitch, pool_pitch, Ho, Wo, fp16);
-        return cudaGetLastError();
-    }
-    const size_t total = static_cast<size_t>(B) * HW * vc;
-    ese_scale_kernel<<<grid_for((total + kEseUnroll - 1) / kEseUnroll, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
-                                                                      id_pitch, out_pitch, fp16);
-    return cudaGetLastError();
+    return launch_ese_scale(x, x_pitch, gate, identity, id_pitch, out, out_pitch, B, HW, C, num_sms, stream, fp16, pool, pool_pitch,
+                            H, W);
 }
 
 // eSE with the pooling partials produced by the conv epilogue: reduce -> fc -> scale (2 tensor passes instead of 3)
@@ -427,30 +437,18 @@ cudaError_t launch_ese_fused(const __nv_bfloat16* x, int x_pitch, const float* t
                              int out_pitch, float* sums, float* gate, int B, int HW, int C, int num_sms,
                              cudaStream_t stream, int fp16, __nv_bfloat16* pool, int pool_pitch, int H, int W) {
     if (pool != nullptr && (H * W != HW || H < 3 || W < 3)) return cudaErrorInvalidValue;
-    ese_reduce_kernel<<<dim3((C + 63) / 64, B), 256, 0, stream>>>(tile_partial, sums, T, C, C);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(ese_reduce_kernel, dim3((C + 63) / 64, B), dim3(256), 0, stream, tile_partial, sums, T, C, C);
     if (e != cudaSuccess) return e;
-    ese_fc_kernel<<<dim3((C + 7) / 8, B), 256, C * sizeof(float), stream>>>(sums, fc_w, fc_b, gate, C, 1,
-                                                                          1.0f / static_cast<float>(HW));
-    e = cudaGetLastError();
+    e = launch_pdl(ese_fc_kernel, dim3((C + 7) / 8, B), dim3(256), C * sizeof(float), stream, static_cast<const float*>(sums), fc_w,
+                   fc_b, gate, C, 1, 1.0f / static_cast<float>(HW));
     if (e != cudaSuccess) return e;
-    if (pool != nullptr) {
-        const int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;  // 3x3 / s2, ceil_mode
-        const size_t total = static_cast<size_t>(B) * Ho * Wo * (C / 8);
-        ese_scale_pool_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, pool, B, H, W, C, x_pitch,
-                                                                                id_pitch, out_pitch, pool_pitch, Ho, Wo, fp16);
-        return cudaGetLastError();
-    }
-    const size_t total = static_cast<size_t>(B) * HW * (C / 8);
-    ese_scale_kernel<<<grid_for((total + kEseUnroll - 1) / kEseUnroll, 256, num_sms), 256, 0, stream>>>(x, gate, identity, out, B, HW, C, x_pitch,
-                                                                      id_pitch, out_pitch, fp16);
-    return cudaGetLastError();
+    return launch_ese_scale(x, x_pitch, gate, identity, id_pitch, out, out_pitch, B, HW, C, num_sms, stream, fp16, pool, pool_pitch,
+                            H, W);
 }
 
 cudaError_t launch_relu(const __nv_bfloat16* x, __nv_bfloat16* out, size_t n_elems, int num_sms, cudaStream_t stream) {
     const size_t nvec = n_elems / 8;
-    relu_kernel<<<grid_for(nvec, 256, num_sms), 256, 0, stream>>>(x, out, nvec);
-    return cudaGetLastError();
+    return launch_pdl(relu_kernel, dim3(grid_for(nvec, 256, num_sms)), dim3(256), 0, stream, x, out, nvec);
 }
 
 }  // namespace dd3d
