@@ -10,6 +10,7 @@
 #include "engine.cuh"
 
 #include "act16.cuh"
+#include "pdl.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -1341,6 +1342,8 @@ void Engine::forward(const void* d_images, int img_dtype, const float* d_K, cons
                    "preprocess");
     }
     mark(0);
+    // from here on every launch follows one of our kernels: the small kernels may use programmatic dependent launch (pdl.cuh)
+    PdlScope pdl_scope;
     for (const Op& op : P.ops) {
         switch (op.type) {
             case Op::CONV:

@@ -1,9 +1,15 @@
-// Programmatic dependent launch for the small kernels of the forward (pre / post-processing, pools, eSE): every one of them
-// used to be a full serialisation point of the stream (drain, then launch latency: ~4 us x 51 kernels per V2-99 forward, x 14
-// per DLA-34 forward).  DD3D_PDL_PROLOGUE() is the FIRST statement of such a kernel: it waits until every earlier kernel of
+// Programmatic dependent launch for the small kernels of the forward (pools, eSE, decode, NMS, sparse predictor): every one of
+// them used to be a full serialisation point of the stream (drain, then launch latency: ~4 us x 51 kernels per V2-99 forward,
+// x 14 per DLA-34 forward).  DD3D_PDL_PROLOGUE() is the FIRST statement of such a kernel: it waits until every earlier kernel of
 // the stream has completed and its memory is visible (so nothing the kernel reads or overwrites can be in flight), then lets
-// the next kernel's CTAs be scheduled as this grid's CTAs retire.  Launch with launch_pdl(); DD3D_NO_PDL=1 turns the launch
-// attribute off (the prologue is then a no-op), which tests/test_determinism_gpu.py uses to compare both modes bit for bit.
+// the next kernel's CTAs be scheduled as this grid's CTAs retire.
+// RULE: the launch attribute is only used where the preceding operation of the stream is one of OUR KERNELS.  griddepcontrol.wait
+// waits for the primary GRID; a kernel launched programmatically right behind an asynchronous memcpy (the caller's H2D of the
+// images / sizes in front of the preprocess kernel) has no grid to wait for and can overtake the copy -- seen once as a
+// preprocess output that depended on timing (tests/test_determinism_gpu.py).  So launch_pdl() sets the attribute only inside a
+// PdlScope, which Engine::forward opens AFTER its first (normally launched) kernel; the operator-level entry points, which
+// run behind arbitrary caller work, never open one.  DD3D_NO_PDL=1 turns the attribute off everywhere (the prologue is then a
+// no-op): tests/test_determinism_gpu.py compares both modes bit for bit across processes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -27,6 +33,14 @@ inline bool pdl_enabled() {
     return on != 0;
 }
 
+inline thread_local int g_pdl_scope_depth = 0;
+struct PdlScope {
+    PdlScope() { ++g_pdl_scope_depth; }
+    ~PdlScope() { --g_pdl_scope_depth; }
+    PdlScope(const PdlScope&) = delete;
+    PdlScope& operator=(const PdlScope&) = delete;
+};
+
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
@@ -38,7 +52,7 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = (pdl_enabled() && g_pdl_scope_depth > 0) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
