@@ -1,14 +1,15 @@
-// Per-image class-aware greedy NMS + post-NMS top-k + rescale/clip, one CTA per image, no host sync.
+// Per-image class-aware greedy NMS + post-NMS top-k + rescale/clip, no host sync.
 //
 // Replaces Instances.cat over levels + FCOS2DInference.nms_and_top_k (reference core.py:130-135, fcos2d.py:346-367
 // -> detectron2 batched_nms -> torchvision nms) and detectron2 detector_postprocess (core.py:153-160):
-//   1. gather the <= L*topk decoded candidates of the image, sort by (score_3d desc, level asc, index asc)
-//      with an in-smem bitonic sort (deterministic regardless of the atomics order upstream);
-//   2. greedy NMS in sorted order, 64 boxes per step: resolve the 64x64 diagonal block serially, then let all
-//      threads test the remaining boxes against the step's survivors (IoU > thr, same class => suppressed;
-//      IoU = inter / (a + b - inter) exactly as torchvision);
+//   1. gather the <= L*topk decoded candidates of the image, order them by (score_3d desc, level asc, index asc)
+//      (deterministic regardless of the atomics order upstream);
+//   2. greedy NMS in that order (IoU > thr, same class => suppressed; IoU = inter / (a + b - inter) exactly as torchvision);
 //   3. if more than POST_NMS_TOPK remain keep those whose 2-D score >= the k-th largest 2-D score (fcos2d.py:359-365);
 //   4. scale boxes to the requested output size, clip, drop empty boxes (detector_postprocess).
+// Two forms with identical results: `nms_kernel`, one CTA per image doing all four steps (in-smem bitonic sort, 64 boxes per
+// greedy step) -- the TTA merge and DO_NMS = False use it; and the engine's default multi-CTA path further down
+// (rank sort -> IoU bit matrix -> per-class scan -> finish), which keeps all SMs busy when one class holds most candidates.
 #include "detect.cuh"
 #include "device_once.cuh"
 #include "pdl.cuh"

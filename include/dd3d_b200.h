@@ -169,7 +169,8 @@ int dd3d_set_option(dd3d_handle h, const char* name, int value);
  * "cta2" = 0 single-CTA conv kernel everywhere, 1 CTA pairs (tcgen05.mma.cta_group::2) wherever legal, 2 auto (default:
  * pairs for block_n >= 160 and >= 296 tiles), -1 back to the DD3D_CONV_CTA2 environment setting.
  * "op_fp16" = 1: the dd3d_op_* entry points below treat their 16-bit buffers as fp16 (default 0: bf16).
- * "nms_class_parallel" = 0: one CTA per image does the whole NMS instead of one CTA per (class, image) (default 1).
+ * "nms_class_parallel" = 0: one CTA per image does the whole NMS instead of the multi-CTA path (rank sort, IoU bit matrix on
+ * all SMs, one scan CTA per (class, image), finish; default 1; same kept set and order).
  * "taps" = 0: 3x3 convs with <= 16 output channels use the per-tap kernels instead of the taps-in-N kernel (default 1).
  * "wstat" = 0: 3x3 layers whose whole weight tensor fits in shared memory next to the activation patches (64 -> 64 channels)
  * stream it per tile like every other layer instead of keeping it resident (default 1; bit-identical results either way).
