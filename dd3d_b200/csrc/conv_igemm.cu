@@ -1293,8 +1293,7 @@ cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
             cudaError_t e = cudaFuncSetAttribute(conv_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTapsSmem);
             if (e != cudaSuccess) return e;
         }
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(std::min(p.total_work, num_sms));
         cfg.blockDim = dim3(kTapsThreads);
         cfg.dynamicSmemBytes = kTapsSmem;
@@ -1308,8 +1307,7 @@ cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream) {
     }
     // CTA pairs: an even grid of 2-CTA clusters (one pair per TPC), each pair loops over pair-work items
     const int grid = p.cta2 ? 2 * std::min(p.pair_work, num_sms / 2) : std::min(p.total_work, num_sms);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kConvThreads);
     cfg.dynamicSmemBytes = smem_bytes;

@@ -205,8 +205,7 @@ cudaError_t launch_one(const __nv_bfloat16* in, const __nv_bfloat16* w, const fl
     const int ctas_per_sm = std::max(1, std::min(4, (200 * 1024) / smem));
     const int total = B * tiles_x * tiles_y;
     const int grid = std::min(total, num_sms * ctas_per_sm);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(160);
     cfg.dynamicSmemBytes = smem;
